@@ -1,0 +1,878 @@
+// C-ABI entry points (include/gmf_b200.h), weight packing and the launch schedule of the GMF-PointDSC forward.
+#include "../../include/gmf_b200.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "attn_tc.cuh"
+#include "linear_tc.cuh"
+#include "tail.cuh"
+
+using namespace gmf;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return GMF_ERR_CUDA;
+}
+#define CU(x)                                     \
+  do {                                            \
+    cudaError_t e_ = (x);                         \
+    if (e_ != cudaSuccess) return fail_cuda(e_, #x); \
+  } while (0)
+#define LAUNCHED()                                          \
+  do {                                                      \
+    g_launches.fetch_add(1, std::memory_order_relaxed);     \
+    cudaError_t e_ = cudaGetLastError();                    \
+    if (e_ != cudaSuccess) return fail_cuda(e_, "kernel launch"); \
+  } while (0)
+#define TRY(x)            \
+  do {                    \
+    int r_ = (x);         \
+    if (r_ != 0) return r_; \
+  } while (0)
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------------
+// state_dict table (mirror of gmf_b200/weights.py::hot_path_spec)
+// ------------------------------------------------------------------------------------------------
+struct Spec { std::string name; int64_t numel; };
+
+void fusion_spec(std::vector<Spec>& s, const std::string& p, bool pe) {
+  if (pe) {
+    s.push_back({p + "cpe.proj_q.weight", 128 * 3}); s.push_back({p + "cpe.proj_q.bias", 128});
+    s.push_back({p + "cpe.proj_content.weight", 128 * 3}); s.push_back({p + "cpe.proj_content.bias", 128});
+  }
+  const std::string a = p + "cross_attend_blocks.0.", f = p + "cross_attend_blocks.1.";
+  s.push_back({a + "norm.weight", 128}); s.push_back({a + "norm.bias", 128});
+  s.push_back({a + "norm_context.weight", 128}); s.push_back({a + "norm_context.bias", 128});
+  s.push_back({a + "fn.to_q.weight", 64 * 128}); s.push_back({a + "fn.to_kv.weight", 128 * 128});
+  s.push_back({a + "fn.to_out.weight", 128 * 64}); s.push_back({a + "fn.to_out.bias", 128});
+  s.push_back({f + "norm.weight", 128}); s.push_back({f + "norm.bias", 128});
+  s.push_back({f + "fn.net.0.weight", 1024 * 128}); s.push_back({f + "fn.net.0.bias", 1024});
+  s.push_back({f + "fn.net.2.weight", 128 * 512}); s.push_back({f + "fn.net.2.bias", 128});
+}
+void bn_spec(std::vector<Spec>& s, const std::string& p, int ch) {
+  s.push_back({p + "weight", ch}); s.push_back({p + "bias", ch});
+  s.push_back({p + "running_mean", ch}); s.push_back({p + "running_var", ch});
+}
+std::vector<Spec> build_spec(int L) {
+  std::vector<Spec> s;
+  s.push_back({"sigma", 1}); s.push_back({"sigma_spat", 1});
+  s.push_back({"encoder.layer0.weight", 128 * 6}); s.push_back({"encoder.layer0.bias", 128});
+  fusion_spec(s, "encoder.fusion_layer_1.", false);
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "encoder.blocks.PointCN_layer_" + std::to_string(i) + ".";
+    s.push_back({p + "0.weight", 128 * 128}); s.push_back({p + "0.bias", 128});
+    bn_spec(s, p + "1.", 128);
+    const std::string n = "encoder.blocks.NonLocal_layer_" + std::to_string(i) + ".";
+    s.push_back({n + "fc_message.0.weight", 64 * 128}); s.push_back({n + "fc_message.0.bias", 64});
+    bn_spec(s, n + "fc_message.1.", 64);
+    s.push_back({n + "fc_message.3.weight", 64 * 64}); s.push_back({n + "fc_message.3.bias", 64});
+    bn_spec(s, n + "fc_message.4.", 64);
+    s.push_back({n + "fc_message.6.weight", 128 * 64}); s.push_back({n + "fc_message.6.bias", 128});
+    for (const char* q : {"q", "k", "v"}) {
+      s.push_back({n + "projection_" + q + ".weight", 128 * 128}); s.push_back({n + "projection_" + q + ".bias", 128});
+    }
+    fusion_spec(s, n + "fusion_layer_2.", true);
+  }
+  s.push_back({"classification.0.weight", 32 * 128}); s.push_back({"classification.0.bias", 32});
+  s.push_back({"classification.2.weight", 32 * 32}); s.push_back({"classification.2.bias", 32});
+  s.push_back({"classification.4.weight", 32}); s.push_back({"classification.4.bias", 1});
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side weight packing
+// ------------------------------------------------------------------------------------------------
+float tf32_round(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u += 0xFFFu + ((u >> 13) & 1u);
+  u &= 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+struct Blob {
+  std::vector<float> h;
+  size_t push(const float* p, size_t n) {   // 256-byte aligned offsets (bulk copies need 16 B)
+    size_t off = (h.size() + 63) & ~(size_t)63;
+    h.resize(off + n);
+    memcpy(h.data() + off, p, n * sizeof(float));
+    return off;
+  }
+  size_t push(const std::vector<float>& v) { return push(v.data(), v.size()); }
+};
+
+// W: [nout][k] row-major.  Emits the weight chunk images in the linear kernel's issue order: for each block of `nb`
+// TMEM columns (rowmap gives the source row of every column) and each k-chunk of `kch`: [nb rows x kch floats], as
+// kch/32 swizzle atoms of nb x 128 B.
+std::vector<float> pack_linear(const std::vector<float>& W, int nout, int k, int kch, int nb, const std::vector<int>* rowmap = nullptr) {
+  std::vector<float> out((size_t)nout * k, 0.f);
+  size_t chunk = 0;
+  for (int blk = 0; blk < nout / nb; ++blk)
+    for (int kc = 0; kc < k / kch; ++kc, ++chunk) {
+      uint8_t* img = (uint8_t*)(out.data() + chunk * (size_t)nb * kch);
+      for (int n = 0; n < nb; ++n) {
+        const int srow = rowmap ? (*rowmap)[blk * nb + n] : blk * nb + n;
+        for (int kk = 0; kk < kch; ++kk) {
+          const int atom = kk >> 5, c16 = (kk & 31) >> 2, within = kk & 3;
+          float* dst = (float*)(img + (size_t)atom * nb * 128 + swz_off(n, c16)) + within;
+          *dst = tf32_round(W[(size_t)srow * k + kc * kch + kk]);
+        }
+      }
+    }
+  return out;
+}
+
+struct FusionW {
+  bool pe = false;
+  const float *cpe_q_w = nullptr, *cpe_q_b = nullptr, *cpe_c_w = nullptr, *cpe_c_b = nullptr;
+  const float *lnq_g, *lnq_b, *lnc_g, *lnc_b, *lnf_g, *lnf_b;
+  const float *wq, *wkv, *wo, *bo, *w1, *b1, *w2, *b2;
+};
+struct LayerW {
+  const float *pcn_w, *pcn_b, *qkv_w, *qkv_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
+  FusionW f2;
+};
+
+}  // namespace
+
+struct gmf_ctx {
+  int device = 0;
+  gmf_config cfg{};
+  bool loaded = false;
+  float* blob = nullptr;
+  float sigma = 1.f, sigma_spat = 0.1f;
+  const float *l0_w = nullptr, *l0_b = nullptr;
+  FusionW f1;
+  std::vector<LayerW> layers;
+  ClsWeights cls{};
+  int chunk_pairs = 16;
+  // staging for the host-buffer entry point
+  uint8_t* stage = nullptr;
+  size_t stage_bytes = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+struct Work {
+  float *kpts; float4 *src4, *tgt4;
+  float *imgfeat, *featA, *feat1, *x0, *x1, *x2, *of, *g_t, *msg, *m1, *m2;
+  __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts;
+  float *normed, *conf, *key, *seed_w, *seed_trans, *pre_refine;
+  int *seeds, *knn, *counts, *best;
+  unsigned* pair_mask;
+};
+struct Bump {
+  uint8_t* base; size_t off = 0;
+  template <class T> T* take(size_t n) {
+    off = (off + 1023) & ~(size_t)1023;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k) {
+  Bump b{base};
+  const int nt = cdiv(N, 128), tt = cdiv(std::max(T, 1), 128);
+  const size_t Lm = (size_t)std::max(N, T), tm = (size_t)std::max(nt, tt);
+  w.kpts = b.take<float>((size_t)B * nt * 128 * 8);
+  w.src4 = b.take<float4>((size_t)B * N); w.tgt4 = b.take<float4>((size_t)B * N);
+  w.imgfeat = b.take<float>((size_t)B * std::max(T, 1) * 128);
+  w.featA = b.take<float>((size_t)B * N * 128); w.feat1 = b.take<float>((size_t)B * N * 128);
+  w.x0 = b.take<float>(B * Lm * 128); w.x1 = b.take<float>(B * Lm * 128); w.x2 = b.take<float>(B * Lm * 128);
+  w.of = b.take<float>(B * Lm * 64);
+  w.g_t = b.take<float>(B * tm * 128 * 512);
+  w.msg = b.take<float>((size_t)B * N * 128); w.m1 = b.take<float>((size_t)B * N * 64); w.m2 = b.take<float>((size_t)B * N * 64);
+  w.qf = b.take<__nv_bfloat16>(B * tm * 128 * 64);
+  w.kf = b.take<__nv_bfloat16>(B * tm * 128 * 64); w.vtf = b.take<__nv_bfloat16>(B * tm * 128 * 64);
+  w.qs = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128);
+  w.ks = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128); w.vts = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128);
+  w.normed = b.take<float>((size_t)B * N * 128); w.conf = b.take<float>((size_t)B * N); w.key = b.take<float>((size_t)B * N);
+  w.seed_w = b.take<float>((size_t)B * S * k); w.seed_trans = b.take<float>((size_t)B * S * 16);
+  w.pre_refine = b.take<float>((size_t)B * 16);
+  w.seeds = b.take<int>((size_t)B * S); w.knn = b.take<int>((size_t)B * S * k); w.counts = b.take<int>((size_t)B * S);
+  w.best = b.take<int>(B); w.pair_mask = b.take<unsigned>(B);
+  return b.off + 1024;
+}
+
+inline int num_seeds(const gmf_ctx* c, int N) { return (int)((double)N * (double)c->cfg.ratio); }
+inline int eff_k(const gmf_ctx* c, int N) { return std::min(c->cfg.k, N - 1); }
+
+int check_ws(const gmf_ctx* ctx, Work& w, void* ws, size_t bytes, int B, int N, int T) {
+  if (!ws) return fail(GMF_ERR_INVALID, "workspace is NULL");
+  const int S = std::max(num_seeds(ctx, N), 1), k = std::max(eff_k(ctx, N), 1);
+  const size_t need = carve(w, nullptr, B, N, T, S, k);
+  if (bytes < need) return fail(GMF_ERR_STATE, "workspace too small: need " + std::to_string(need) + " bytes");
+  uint8_t* base = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  carve(w, base, B, N, T, S, k);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch schedule
+// ------------------------------------------------------------------------------------------------
+template <int K, int NOUT, int PRO, int EPI>
+int run_linear(const LinArgs& a, int pairs, cudaStream_t st) {
+  cudaError_t e = launch_linear<K, NOUT, PRO, EPI>(a, pairs, st);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail_cuda(e, "linear_tc launch");
+  return 0;
+}
+
+LinArgs lin(const float* x, int L, const float* w, const float* bias) {
+  LinArgs a{};
+  a.x = x; a.L = L; a.tiles = cdiv(L, 128); a.w_packed = w; a.bias = bias;
+  return a;
+}
+
+// FusionLayer.forward (fusion_layer.py:172-201)
+int run_fusion(const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st) {
+  const float* resid0 = xq;
+  {  // queries: (CPE) -> LN -> to_q  => bf16 Q tiles (scale folded)
+    LinArgs a = lin(xq, Lq, f.wq, nullptr);
+    a.ln_g = f.lnq_g; a.ln_b = f.lnq_b; a.t0 = w.qf;
+    if (f.pe) {
+      a.cpe_w = f.cpe_q_w; a.cpe_b = f.cpe_q_b; a.x0_out = w.x0; resid0 = w.x0;
+      TRY((run_linear<128, 64, PRO_CPE_LN, EPI_Q_FUS>(a, B, st)));
+    } else {
+      TRY((run_linear<128, 64, PRO_LN, EPI_Q_FUS>(a, B, st)));
+    }
+  }
+  {  // context: (CPE) -> LN_ctx -> to_kv => bf16 K tiles, V^T tiles
+    LinArgs a = lin(ctxk, Lk, f.wkv, nullptr);
+    a.ln_g = f.lnc_g; a.ln_b = f.lnc_b; a.t1 = w.kf; a.t2 = w.vtf;
+    if (f.pe) {
+      a.cpe_w = f.cpe_c_w; a.cpe_b = f.cpe_c_b; a.x0_out = nullptr;
+      TRY((run_linear<128, 128, PRO_CPE_LN, EPI_KV_FUS>(a, B, st)));
+    } else {
+      TRY((run_linear<128, 128, PRO_LN, EPI_KV_FUS>(a, B, st)));
+    }
+  }
+  {
+    AttnArgs a{};
+    a.q_t = w.qf; a.k_t = w.kf; a.vt_t = w.vtf; a.out = w.of;
+    a.Lq = Lq; a.Lk = Lk; a.q_tiles = cdiv(Lq, 128); a.k_tiles = cdiv(Lk, 128);
+    cudaError_t e = launch_attn<64, false>(a, B, st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail_cuda(e, "attn_tc<64> launch");
+  }
+  {  // to_out + bias + residual
+    LinArgs a = lin(w.of, Lq, f.wo, f.bo);
+    a.residual = resid0; a.out = w.x1;
+    TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st)));
+  }
+  {  // LN -> Linear(128,1024) -> GEGLU => tiled activation image
+    LinArgs a = lin(w.x1, Lq, f.w1, f.b1);
+    a.ln_g = f.lnf_g; a.ln_b = f.lnf_b; a.out = w.g_t;
+    TRY((run_linear<128, 1024, PRO_LN, EPI_GEGLU_TILED>(a, B, st)));
+  }
+  {  // Linear(512,128) + bias + residual
+    LinArgs a = lin(w.g_t, Lq, f.w2, f.b2);
+    a.residual = w.x1; a.out = out;
+    TRY((run_linear<512, 128, PRO_TILED, EPI_BIAS_RES>(a, B, st)));
+  }
+  return 0;
+}
+
+int run_prep(Work& w, const float* src, const float* tgt, int B, int N, cudaStream_t st) {
+  prep_points_kernel<<<B, 256, 0, st>>>(src, tgt, N, cdiv(N, 128) * 128, w.kpts, w.src4, w.tgt4);
+  LAUNCHED();
+  return 0;
+}
+
+// Q/K/V projections + SC-guided attention (PointDSC.py:56-64); feat1 = PointCN output
+int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float* feat1, int B, int N, float* msg, cudaStream_t st) {
+  {
+    LinArgs a = lin(feat1, N, lw.qkv_w, lw.qkv_b);
+    a.t0 = w.qs; a.t1 = w.ks; a.t2 = w.vts;
+    TRY((run_linear<128, 384, PRO_NONE, EPI_QKV_SC>(a, B, st)));
+  }
+  AttnArgs a{};
+  a.q_t = w.qs; a.k_t = w.ks; a.vt_t = w.vts; a.kpts = w.kpts; a.out = msg;
+  a.Lq = N; a.Lk = N; a.q_tiles = a.k_tiles = cdiv(N, 128);
+  a.neg_inv_sigma2 = -1.0f / (ctx->sigma_spat * ctx->sigma_spat);
+  cudaError_t e = launch_attn<128, true>(a, B, st);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail_cuda(e, "attn_tc<128,SC> launch");
+  return 0;
+}
+
+// PointCN_layer_i + NonLocal_layer_i (PointDSC.py:140-142, 40-74)
+int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in, const float* image_feat, int B, int N, int T,
+                      float* feat_out, cudaStream_t st) {
+  const LayerW& lw = ctx->layers[li];
+  {
+    LinArgs a = lin(feat_in, N, lw.pcn_w, lw.pcn_b);
+    a.out = w.feat1;
+    TRY((run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
+  }
+  TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st));
+  {
+    LinArgs a = lin(w.msg, N, lw.fc1_w, lw.fc1_b);
+    a.out = w.m1;
+    TRY((run_linear<128, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
+  }
+  {
+    LinArgs a = lin(w.m1, N, lw.fc2_w, lw.fc2_b);
+    a.out = w.m2;
+    TRY((run_linear<64, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
+  }
+  TRY(run_fusion(lw.f2, w, w.feat1, image_feat, B, N, T, w.x2, st));
+  {
+    LinArgs a = lin(w.m2, N, lw.fc3_w, lw.fc3_b);
+    a.residual = w.x2; a.out = feat_out;
+    TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st)));
+  }
+  return 0;
+}
+
+int run_classify(const gmf_ctx* ctx, const float* feat, long long rows, float* normed, float* conf, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CU(cudaFuncSetAttribute(classify_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClsSmem));
+    configured = true;
+  }
+  classify_normalize_kernel<<<(unsigned)((rows + 63) / 64), 256, kClsSmem, st>>>(feat, rows, ctx->cls, normed, conf);
+  LAUNCHED();
+  return 0;
+}
+
+int run_pick_seeds(const gmf_ctx* ctx, Work& w, const float* conf, int B, int N, int S, int use_nms, int* seeds, cudaStream_t st) {
+  int np2 = 1;
+  while (np2 < N) np2 <<= 1;
+  if (np2 > 16384) return fail(GMF_ERR_INVALID, "pick_seeds supports N <= 16384");
+  nms_key_kernel<<<dim3(cdiv(N, 256), B), 256, 0, st>>>(w.src4, conf, N, ctx->cfg.nms_radius, use_nms, w.key);
+  LAUNCHED();
+  static bool configured = false;
+  if (!configured) {
+    CU(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    configured = true;
+  }
+  topk_sort_kernel<<<B, 1024, (size_t)np2 * 8, st>>>(w.key, N, np2, S, seeds);
+  LAUNCHED();
+  return 0;
+}
+
+template <int SPC>
+int launch_knn(const float* normed, const int* seeds, int B, int N, int S, int k, int* knn, cudaStream_t st) {
+  const size_t smem = (size_t)(64 * 132 + SPC * 128 + (size_t)SPC * N) * 4;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU(cudaFuncSetAttribute(seed_knn_kernel<SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  seed_knn_kernel<SPC><<<dim3(cdiv(S, SPC), B), 256, smem, st>>>(normed, seeds, N, S, k, knn);
+  LAUNCHED();
+  return 0;
+}
+
+int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const float* src, const float* tgt, const int* seeds, int B,
+                        int N, int S, int k, int* knn, float* seed_w, float* seed_trans, cudaStream_t st) {
+  if (k < 1 || k > 40) return fail(GMF_ERR_INVALID, "k must be in [1, 40]");
+  const size_t budget = 180 * 1024 - 64 * 132 * 4;
+  if ((size_t)8 * (128 + N) * 4 <= budget) TRY(launch_knn<8>(normed, seeds, B, N, S, k, knn, st));
+  else if ((size_t)4 * (128 + N) * 4 <= budget) TRY(launch_knn<4>(normed, seeds, B, N, S, k, knn, st));
+  else if ((size_t)2 * (128 + N) * 4 <= budget) TRY(launch_knn<2>(normed, seeds, B, N, S, k, knn, st));
+  else if ((size_t)(128 + N) * 4 <= budget) TRY(launch_knn<1>(normed, seeds, B, N, S, k, knn, st));
+  else return fail(GMF_ERR_INVALID, "seed kNN supports N <= ~37000");
+  CU(cudaMemsetAsync(w.pair_mask, 0xff, (size_t)B * sizeof(unsigned), st));
+  seed_spectral_kernel<0><<<dim3(S, B), 128, 0, st>>>(normed, src, tgt, knn, N, S, k, ctx->sigma, ctx->sigma_spat,
+                                                     ctx->cfg.num_iterations, w.pair_mask, nullptr, nullptr);
+  LAUNCHED();
+  seed_spectral_kernel<1><<<dim3(S, B), 128, 0, st>>>(normed, src, tgt, knn, N, S, k, ctx->sigma, ctx->sigma_spat,
+                                                     ctx->cfg.num_iterations, w.pair_mask, seed_w, seed_trans);
+  LAUNCHED();
+  return 0;
+}
+
+int run_score(const gmf_ctx* ctx, Work& w, const float* seed_trans, int B, int N, int S, int refine, float* final_trans, float* labels,
+              int* counts, int* best, float* pre_refine, cudaStream_t st) {
+  CU(cudaMemsetAsync(counts, 0, (size_t)B * S * sizeof(int), st));
+  score_kernel<<<dim3(cdiv(S, kScoreSeeds), cdiv(N, 256 * kScorePPT), B), 256, 0, st>>>(w.src4, w.tgt4, seed_trans, N, S, ctx->cfg.inlier_threshold, counts);
+  LAUNCHED();
+  const float rtau = (ctx->cfg.inlier_threshold == 0.10f) ? 0.10f : 1.2f;   // PointDSC.py:505-508
+  select_refine_kernel<<<B, 1024, 0, st>>>(w.src4, w.tgt4, seed_trans, counts, N, S, ctx->cfg.inlier_threshold, rtau, 20, refine,
+                                           pre_refine, final_trans, labels, best);
+  LAUNCHED();
+  return 0;
+}
+
+int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
+                  int B, int N, int T, int testing, float* final_trans, float* labels, float* conf_out, int* seeds_out, float* feat_out,
+                  cudaStream_t st) {
+  const int S = num_seeds(ctx, N), k = eff_k(ctx, N);
+  TRY(run_prep(w, src, tgt, B, N, st));
+  {
+    const long long rows = (long long)B * N;
+    layer0_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(corr, ctx->l0_w, ctx->l0_b, w.featA, rows, 6);
+    LAUNCHED();
+  }
+  // Fusion-1: queries = q-image tokens, context = p-image tokens (PointDSC.py:137)
+  TRY(run_fusion(ctx->f1, w, q_tok, p_tok, B, T, T, w.imgfeat, st));
+  for (int li = 0; li < ctx->cfg.num_layers; ++li) TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st));
+  if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
+  TRY(run_classify(ctx, w.featA, (long long)B * N, w.normed, conf_out, st));
+  TRY(run_pick_seeds(ctx, w, conf_out, B, N, S, testing ? 1 : 0, seeds_out, st));
+  TRY(run_seed_hypotheses(ctx, w, w.normed, src, tgt, seeds_out, B, N, S, k, w.knn, w.seed_w, w.seed_trans, st));
+  TRY(run_score(ctx, w, w.seed_trans, B, N, S, testing ? 1 : 0, final_trans, labels, w.counts, w.best, w.pre_refine, st));
+  return 0;
+}
+
+int require_loaded(const gmf_ctx* ctx) {
+  if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
+  if (!ctx->loaded) return fail(GMF_ERR_STATE, "weights not loaded (gmf_load_weights)");
+  return 0;
+}
+
+// fp32 row-major [L][D] -> bf16 UMMA tile images (debug / test path only)
+__global__ void pack_tiles_kernel(const float* __restrict__ src, int L, int D, int tiles, float scale, int transpose,
+                                  __nv_bfloat16* __restrict__ dst) {
+  const int pair = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)tiles * 128 * D;
+  if (e >= total) return;
+  const int row = (int)(e / D), c = (int)(e % D);
+  const int tile = row >> 7, r = row & 127;
+  const float v = row < L ? src[((size_t)pair * L + row) * D + c] * scale : 0.f;
+  uint8_t* base = (uint8_t*)(dst + ((size_t)pair * tiles + tile) * 128 * D);
+  size_t off;
+  if (!transpose) off = (size_t)(c >> 6) * 16384 + swz_off(r, (c & 63) >> 3) + (c & 7) * 2;
+  else off = (size_t)(r >> 6) * (D * 128) + swz_off(c, (r & 63) >> 3) + (r & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16_rn(v);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* gmf_last_error(void) { return g_err.c_str(); }
+const char* gmf_version(void) { return "gmf_b200 0.1 (sm_100a, tcgen05)"; }
+
+int64_t gmf_launch_count(int reset) {
+  const long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+
+int gmf_weight_count(int num_layers) { return (int)build_spec(num_layers).size(); }
+int gmf_weight_spec(int num_layers, int index, char* name, int cap, int64_t* numel) {
+  const auto s = build_spec(num_layers);
+  if (index < 0 || index >= (int)s.size()) return fail(GMF_ERR_INVALID, "weight index out of range");
+  if (name && cap > 0) {
+    strncpy(name, s[index].name.c_str(), cap - 1);
+    name[cap - 1] = 0;
+  }
+  if (numel) *numel = s[index].numel;
+  return 0;
+}
+
+int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
+  if (!out || !cfg) return fail(GMF_ERR_INVALID, "NULL argument");
+  if (cfg->num_layers < 1 || cfg->k < 1 || cfg->k > 40 || cfg->num_iterations < 1 || cfg->num_iterations > 31)
+    return fail(GMF_ERR_INVALID, "unsupported config (need num_layers>=1, 1<=k<=40, 1<=num_iterations<=31)");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(GMF_ERR_INVALID, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(GMF_ERR_INVALID, std::string("gmf_b200 needs an sm_100 (Blackwell B200) device, found ") + prop.name);
+  gmf_ctx* c = new gmf_ctx();
+  c->device = device;
+  c->cfg = *cfg;
+  if (const char* e = getenv("GMF_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, atoi(e));
+  *out = c;
+  return 0;
+}
+
+void gmf_destroy(gmf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->blob) cudaFree(ctx->blob);
+  if (ctx->stage) cudaFree(ctx->stage);
+  delete ctx;
+}
+
+int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
+  if (!ctx || !host) return fail(GMF_ERR_INVALID, "NULL argument");
+  const int L = ctx->cfg.num_layers;
+  const auto spec = build_spec(L);
+  int64_t total = 0;
+  std::vector<int64_t> offs(spec.size());
+  for (size_t i = 0; i < spec.size(); ++i) { offs[i] = total; total += spec[i].numel; }
+  if (numel != total) return fail(GMF_ERR_INVALID, "flat weight buffer has " + std::to_string(numel) + " elements, expected " + std::to_string(total));
+  size_t cursor = 0;
+  auto next = [&](const std::string& suffix) -> const float* {
+    const Spec& s = spec[cursor];
+    if (s.name.size() < suffix.size() || s.name.compare(s.name.size() - suffix.size(), suffix.size(), suffix) != 0) {
+      fprintf(stderr, "gmf_load_weights: internal spec mismatch at %s (wanted *%s)\n", s.name.c_str(), suffix.c_str());
+      abort();
+    }
+    return host + offs[cursor++];
+  };
+  auto vec = [](const float* p, size_t n) { return std::vector<float>(p, p + n); };
+
+  Blob blob;
+  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wkv, wo, bo, w1, b1, w2, b2; };
+  auto pack_fusion = [&](bool pe) {
+    FusionOff o{};
+    o.pe = pe;
+    if (pe) {
+      o.cqw = blob.push(next("cpe.proj_q.weight"), 384); o.cqb = blob.push(next("cpe.proj_q.bias"), 128);
+      o.ccw = blob.push(next("cpe.proj_content.weight"), 384); o.ccb = blob.push(next("cpe.proj_content.bias"), 128);
+    }
+    o.lqg = blob.push(next("0.norm.weight"), 128); o.lqb = blob.push(next("0.norm.bias"), 128);
+    o.lcg = blob.push(next("norm_context.weight"), 128); o.lcb = blob.push(next("norm_context.bias"), 128);
+    std::vector<float> wq = vec(next("to_q.weight"), 64 * 128);
+    const float qs = kLog2e / 8.0f;   // dim_head ** -0.5 (fusion_layer.py:76) in log2 units
+    for (auto& v : wq) v *= qs;
+    o.wq = blob.push(pack_linear(wq, 64, 128, 128, 64));
+    o.wkv = blob.push(pack_linear(vec(next("to_kv.weight"), 128 * 128), 128, 128, 128, 128));
+    o.wo = blob.push(pack_linear(vec(next("to_out.weight"), 128 * 64), 128, 64, 64, 128));
+    o.bo = blob.push(next("to_out.bias"), 128);
+    o.lfg = blob.push(next("1.norm.weight"), 128); o.lfb = blob.push(next("1.norm.bias"), 128);
+    std::vector<int> rowmap(1024);
+    for (int p = 0; p < 2; ++p)
+      for (int nbi = 0; nbi < 4; ++nbi) {
+        const int base = nbi < 2 ? (2 * p + nbi) * 128 : 512 + (2 * p + nbi - 2) * 128;
+        for (int n = 0; n < 128; ++n) rowmap[(p * 4 + nbi) * 128 + n] = base + n;
+      }
+    o.w1 = blob.push(pack_linear(vec(next("net.0.weight"), 1024 * 128), 1024, 128, 128, 128, &rowmap));
+    o.b1 = blob.push(next("net.0.bias"), 1024);
+    o.w2 = blob.push(pack_linear(vec(next("net.2.weight"), 128 * 512), 128, 512, 64, 128));
+    o.b2 = blob.push(next("net.2.bias"), 128);
+    return o;
+  };
+  // conv (k=1) followed by eval BatchNorm folded into (W', b'):  PointDSC.py:104-111, 13-21
+  auto fold_bn = [&](std::vector<float>& W, std::vector<float>& b, int nout, int k, const float* g, const float* beta, const float* mu,
+                     const float* var) {
+    for (int o = 0; o < nout; ++o) {
+      const float s = g[o] / std::sqrt(var[o] + 1e-5f);
+      for (int i = 0; i < k; ++i) W[(size_t)o * k + i] *= s;
+      b[o] = (b[o] - mu[o]) * s + beta[o];
+    }
+  };
+
+  const float sigma = *next("sigma");
+  const float sigma_spat = *next("sigma_spat");
+  const size_t l0w = blob.push(next("layer0.weight"), 768), l0b = blob.push(next("layer0.bias"), 128);
+  const FusionOff f1 = pack_fusion(false);
+  struct LayerOff { size_t pw, pb, qw, qb, f1w, f1b, f2w, f2b, f3w, f3b; FusionOff f2; };
+  std::vector<LayerOff> lo(L);
+  for (int i = 0; i < L; ++i) {
+    LayerOff& o = lo[i];
+    {
+      std::vector<float> W = vec(next("0.weight"), 128 * 128), b = vec(next("0.bias"), 128);
+      const float *g = next("1.weight"), *be = next("1.bias"), *mu = next("1.running_mean"), *va = next("1.running_var");
+      fold_bn(W, b, 128, 128, g, be, mu, va);
+      o.pw = blob.push(pack_linear(W, 128, 128, 128, 128)); o.pb = blob.push(b);
+    }
+    {
+      std::vector<float> W = vec(next("fc_message.0.weight"), 64 * 128), b = vec(next("fc_message.0.bias"), 64);
+      const float *g = next("fc_message.1.weight"), *be = next("fc_message.1.bias"), *mu = next("fc_message.1.running_mean"),
+                  *va = next("fc_message.1.running_var");
+      fold_bn(W, b, 64, 128, g, be, mu, va);
+      o.f1w = blob.push(pack_linear(W, 64, 128, 128, 64)); o.f1b = blob.push(b);
+    }
+    {
+      std::vector<float> W = vec(next("fc_message.3.weight"), 64 * 64), b = vec(next("fc_message.3.bias"), 64);
+      const float *g = next("fc_message.4.weight"), *be = next("fc_message.4.bias"), *mu = next("fc_message.4.running_mean"),
+                  *va = next("fc_message.4.running_var");
+      fold_bn(W, b, 64, 64, g, be, mu, va);
+      o.f2w = blob.push(pack_linear(W, 64, 64, 64, 64)); o.f2b = blob.push(b);
+    }
+    o.f3w = blob.push(pack_linear(vec(next("fc_message.6.weight"), 128 * 64), 128, 64, 64, 128));
+    o.f3b = blob.push(next("fc_message.6.bias"), 128);
+    {
+      std::vector<float> W(384 * 128), b(384);
+      const float qs = kLog2e / std::sqrt(128.0f);   // 1/sqrt(num_channels) (PointDSC.py:60) in log2 units
+      for (int q = 0; q < 3; ++q) {
+        const float* wq = next(".weight");
+        const float* bq = next(".bias");
+        const float s = q == 0 ? qs : 1.0f;
+        for (int j = 0; j < 128 * 128; ++j) W[(size_t)q * 128 * 128 + j] = wq[j] * s;
+        for (int j = 0; j < 128; ++j) b[q * 128 + j] = bq[j] * s;
+      }
+      o.qw = blob.push(pack_linear(W, 384, 128, 128, 128)); o.qb = blob.push(b);
+    }
+    o.f2 = pack_fusion(true);
+  }
+  const size_t c1w = blob.push(next("classification.0.weight"), 32 * 128), c1b = blob.push(next("classification.0.bias"), 32);
+  const size_t c2w = blob.push(next("classification.2.weight"), 32 * 32), c2b = blob.push(next("classification.2.bias"), 32);
+  const size_t c3w = blob.push(next("classification.4.weight"), 32), c3b = blob.push(next("classification.4.bias"), 1);
+  if (cursor != spec.size()) return fail(GMF_ERR_STATE, "internal: weight table not fully consumed");
+
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->blob) { CU(cudaDeviceSynchronize()); cudaFree(ctx->blob); ctx->blob = nullptr; }
+  CU(cudaMalloc(&ctx->blob, blob.h.size() * sizeof(float)));
+  CU(cudaMemcpy(ctx->blob, blob.h.data(), blob.h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  const float* d = ctx->blob;
+  auto fuse = [&](const FusionOff& o) {
+    FusionW f;
+    f.pe = o.pe;
+    if (o.pe) { f.cpe_q_w = d + o.cqw; f.cpe_q_b = d + o.cqb; f.cpe_c_w = d + o.ccw; f.cpe_c_b = d + o.ccb; }
+    f.lnq_g = d + o.lqg; f.lnq_b = d + o.lqb; f.lnc_g = d + o.lcg; f.lnc_b = d + o.lcb; f.lnf_g = d + o.lfg; f.lnf_b = d + o.lfb;
+    f.wq = d + o.wq; f.wkv = d + o.wkv; f.wo = d + o.wo; f.bo = d + o.bo; f.w1 = d + o.w1; f.b1 = d + o.b1; f.w2 = d + o.w2; f.b2 = d + o.b2;
+    return f;
+  };
+  ctx->sigma = sigma; ctx->sigma_spat = sigma_spat;
+  ctx->l0_w = d + l0w; ctx->l0_b = d + l0b;
+  ctx->f1 = fuse(f1);
+  ctx->layers.resize(L);
+  for (int i = 0; i < L; ++i) {
+    LayerW& w = ctx->layers[i];
+    const LayerOff& o = lo[i];
+    w.pcn_w = d + o.pw; w.pcn_b = d + o.pb; w.qkv_w = d + o.qw; w.qkv_b = d + o.qb;
+    w.fc1_w = d + o.f1w; w.fc1_b = d + o.f1b; w.fc2_w = d + o.f2w; w.fc2_b = d + o.f2b; w.fc3_w = d + o.f3w; w.fc3_b = d + o.f3b;
+    w.f2 = fuse(o.f2);
+  }
+  ctx->cls = ClsWeights{d + c1w, d + c1b, d + c2w, d + c2b, d + c3w, d + c3b};
+  ctx->loaded = true;
+  return 0;
+}
+
+size_t gmf_workspace_bytes(const gmf_ctx* ctx, int B, int N, int T) {
+  if (!ctx || B < 1 || N < 2) return 0;
+  Work w;
+  const int Bc = std::min(B, ctx->chunk_pairs);
+  return carve(w, nullptr, Bc, N, T, std::max(num_seeds(ctx, N), 1), std::max(eff_k(ctx, N), 1)) + 1024;
+}
+
+int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
+                         int B, int N, int T, int testing, float* final_trans, float* final_labels, float* confidence, int32_t* seeds,
+                         float* feat, void* workspace, size_t workspace_bytes, void* stream) {
+  TRY(require_loaded(ctx));
+  if (B < 1 || N < 2 || T < 1) return fail(GMF_ERR_INVALID, "need B >= 1, N >= 2, T >= 1");
+  if (!corr_pos || !src || !tgt || !p_tok || !q_tok || !final_trans || !final_labels || !confidence || !seeds)
+    return fail(GMF_ERR_INVALID, "NULL tensor argument");
+  if (num_seeds(ctx, N) < 1) return fail(GMF_ERR_INVALID, "int(N * ratio) must be >= 1");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = num_seeds(ctx, N);
+  const int Bc = std::min(B, ctx->chunk_pairs);
+  Work w;
+  TRY(check_ws(ctx, w, workspace, workspace_bytes, Bc, N, T));
+  for (int b0 = 0; b0 < B; b0 += Bc) {
+    const int nb = std::min(Bc, B - b0);
+    TRY(forward_chunk(ctx, w, corr_pos + (size_t)b0 * N * 6, src + (size_t)b0 * N * 3, tgt + (size_t)b0 * N * 3,
+                      p_tok + (size_t)b0 * T * 128, q_tok + (size_t)b0 * T * 128, nb, N, T, testing, final_trans + (size_t)b0 * 16,
+                      final_labels + (size_t)b0 * N, confidence + (size_t)b0 * N, seeds + (size_t)b0 * S,
+                      feat ? feat + (size_t)b0 * N * 128 : nullptr, st));
+  }
+  return 0;
+}
+
+int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
+                              const float* q_tok, int B, int N, int T, int testing, float* final_trans, float* final_labels,
+                              float* confidence, void* stream) {
+  TRY(require_loaded(ctx));
+  if (B < 1 || N < 2 || T < 1) return fail(GMF_ERR_INVALID, "need B >= 1, N >= 2, T >= 1");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = std::max(num_seeds(ctx, N), 1);
+  const size_t ws = gmf_workspace_bytes(ctx, B, N, T);
+  Bump b{nullptr};
+  auto layout = [&](Bump& bb, float*& d_corr, float*& d_src, float*& d_tgt, float*& d_p, float*& d_q, float*& d_tr, float*& d_lab,
+                    float*& d_conf, int*& d_seeds, uint8_t*& d_ws) {
+    d_corr = bb.take<float>((size_t)B * N * 6); d_src = bb.take<float>((size_t)B * N * 3); d_tgt = bb.take<float>((size_t)B * N * 3);
+    d_p = bb.take<float>((size_t)B * T * 128); d_q = bb.take<float>((size_t)B * T * 128);
+    d_tr = bb.take<float>((size_t)B * 16); d_lab = bb.take<float>((size_t)B * N); d_conf = bb.take<float>((size_t)B * N);
+    d_seeds = bb.take<int>((size_t)B * S); d_ws = bb.take<uint8_t>(ws);
+  };
+  float *d_corr, *d_src, *d_tgt, *d_p, *d_q, *d_tr, *d_lab, *d_conf; int* d_seeds; uint8_t* d_ws;
+  layout(b, d_corr, d_src, d_tgt, d_p, d_q, d_tr, d_lab, d_conf, d_seeds, d_ws);
+  const size_t need = b.off + 2048;
+  if (need > ctx->stage_bytes) {
+    CU(cudaDeviceSynchronize());
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr; ctx->stage_bytes = 0;
+    CU(cudaMalloc(&ctx->stage, need));
+    ctx->stage_bytes = need;
+  }
+  Bump bb{(uint8_t*)(((uintptr_t)ctx->stage + 1023) & ~(uintptr_t)1023)};
+  layout(bb, d_corr, d_src, d_tgt, d_p, d_q, d_tr, d_lab, d_conf, d_seeds, d_ws);
+  CU(cudaMemcpyAsync(d_corr, corr_pos, (size_t)B * N * 6 * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_src, src, (size_t)B * N * 3 * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_tgt, tgt, (size_t)B * N * 3 * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_p, p_tok, (size_t)B * T * 128 * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_q, q_tok, (size_t)B * T * 128 * 4, cudaMemcpyHostToDevice, st));
+  TRY(gmf_pointdsc_forward(ctx, d_corr, d_src, d_tgt, d_p, d_q, B, N, T, testing, d_tr, d_lab, d_conf, d_seeds, nullptr, d_ws, ws, stream));
+  CU(cudaMemcpyAsync(final_trans, d_tr, (size_t)B * 16 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(final_labels, d_lab, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  if (confidence) CU(cudaMemcpyAsync(confidence, d_conf, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gmf_fusion_layer(gmf_ctx* ctx, int layer, const float* queries, const float* context, int B, int Lq, int Lk, float* out,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  TRY(require_loaded(ctx));
+  if (layer >= ctx->cfg.num_layers) return fail(GMF_ERR_INVALID, "layer out of range");
+  if (B > ctx->chunk_pairs) return fail(GMF_ERR_INVALID, "stage entry points take B <= chunk_pairs");
+  CU(cudaSetDevice(ctx->device));
+  Work w;
+  TRY(check_ws(ctx, w, workspace, workspace_bytes, B, std::max(Lq, 2), Lk));
+  return run_fusion(layer < 0 ? ctx->f1 : ctx->layers[layer].f2, w, queries, context, B, Lq, Lk, out, (cudaStream_t)stream);
+}
+
+int gmf_sc_attention(gmf_ctx* ctx, int layer, const float* feat, const float* src, const float* tgt, int B, int N, float* msg,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  TRY(require_loaded(ctx));
+  if (layer < 0 || layer >= ctx->cfg.num_layers) return fail(GMF_ERR_INVALID, "layer out of range");
+  if (B > ctx->chunk_pairs) return fail(GMF_ERR_INVALID, "stage entry points take B <= chunk_pairs");
+  CU(cudaSetDevice(ctx->device));
+  Work w;
+  TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, 1));
+  TRY(run_prep(w, src, tgt, B, N, (cudaStream_t)stream));
+  return run_sc_attention(ctx, ctx->layers[layer], w, feat, B, N, msg, (cudaStream_t)stream);
+}
+
+int gmf_encoder_layer(gmf_ctx* ctx, int layer, const float* feat_in, const float* src, const float* tgt, const float* image_feat, int B,
+                      int N, int T, float* feat_out, void* workspace, size_t workspace_bytes, void* stream) {
+  TRY(require_loaded(ctx));
+  if (layer < 0 || layer >= ctx->cfg.num_layers) return fail(GMF_ERR_INVALID, "layer out of range");
+  if (B > ctx->chunk_pairs) return fail(GMF_ERR_INVALID, "stage entry points take B <= chunk_pairs");
+  CU(cudaSetDevice(ctx->device));
+  Work w;
+  TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, T));
+  TRY(run_prep(w, src, tgt, B, N, (cudaStream_t)stream));
+  return run_encoder_layer(ctx, layer, w, feat_in, image_feat, B, N, T, feat_out, (cudaStream_t)stream);
+}
+
+int gmf_classify(gmf_ctx* ctx, const float* feat, int B, int N, float* normed, float* confidence, void* stream) {
+  TRY(require_loaded(ctx));
+  CU(cudaSetDevice(ctx->device));
+  return run_classify(ctx, feat, (long long)B * N, normed, confidence, (cudaStream_t)stream);
+}
+
+int gmf_pick_seeds(gmf_ctx* ctx, const float* src, const float* confidence, int B, int N, int use_nms, int32_t* seeds, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  TRY(require_loaded(ctx));
+  if (B > ctx->chunk_pairs) return fail(GMF_ERR_INVALID, "stage entry points take B <= chunk_pairs");
+  CU(cudaSetDevice(ctx->device));
+  Work w;
+  TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, 1));
+  TRY(run_prep(w, src, src, B, N, (cudaStream_t)stream));
+  return run_pick_seeds(ctx, w, confidence, B, N, num_seeds(ctx, N), use_nms, seeds, (cudaStream_t)stream);
+}
+
+int gmf_seed_hypotheses(gmf_ctx* ctx, const float* normed, const float* src, const float* tgt, const int32_t* seeds, int B, int N, int S,
+                        float* seed_trans, int32_t* knn_idx, float* seed_weight, void* workspace, size_t workspace_bytes, void* stream) {
+  TRY(require_loaded(ctx));
+  if (B > ctx->chunk_pairs) return fail(GMF_ERR_INVALID, "stage entry points take B <= chunk_pairs");
+  if (S < 1 || S > num_seeds(ctx, N)) return fail(GMF_ERR_INVALID, "S must be in [1, int(N*ratio)]");
+  CU(cudaSetDevice(ctx->device));
+  Work w;
+  TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, 1));
+  return run_seed_hypotheses(ctx, w, normed, src, tgt, seeds, B, N, S, eff_k(ctx, N), knn_idx ? knn_idx : w.knn, seed_weight,
+                             seed_trans ? seed_trans : w.seed_trans, (cudaStream_t)stream);
+}
+
+int gmf_score_hypotheses(gmf_ctx* ctx, const float* seed_trans, const float* src, const float* tgt, int B, int N, int S, int refine,
+                         float* final_trans, float* final_labels, int32_t* fitness_counts, int32_t* best, float* pre_refine, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  TRY(require_loaded(ctx));
+  if (B > ctx->chunk_pairs) return fail(GMF_ERR_INVALID, "stage entry points take B <= chunk_pairs");
+  if (S < 1 || S > num_seeds(ctx, N)) return fail(GMF_ERR_INVALID, "S must be in [1, int(N*ratio)]");
+  CU(cudaSetDevice(ctx->device));
+  Work w;
+  TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, 1));
+  TRY(run_prep(w, src, tgt, B, N, (cudaStream_t)stream));
+  return run_score(ctx, w, seed_trans, B, N, S, refine, final_trans, final_labels, fitness_counts ? fitness_counts : w.counts, best,
+                   pre_refine, (cudaStream_t)stream);
+}
+
+int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* Bp, const float* weights, int M, int k, float* T, void* stream) {
+  if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
+  if (M < 1 || k < 1) return fail(GMF_ERR_INVALID, "need M >= 1, k >= 1");
+  CU(cudaSetDevice(ctx->device));
+  rigid_transform_kernel<<<cdiv(M, 4), 128, 0, (cudaStream_t)stream>>>(A, Bp, weights, M, k, T);
+  LAUNCHED();
+  return 0;
+}
+
+int gmf_debug_linear(gmf_ctx* ctx, const float* x, const float* w_host, const float* bias_host, const float* residual, int rows, int k,
+                     int nout, int relu, float* out, void* stream) {
+  if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = nout >= 128 ? 128 : nout;
+  std::vector<float> W(w_host, w_host + (size_t)nout * k);
+  std::vector<float> packed = pack_linear(W, nout, k, k, nb);
+  float *dw = nullptr, *db = nullptr;
+  CU(cudaMalloc(&dw, packed.size() * 4));
+  CU(cudaMalloc(&db, (size_t)nout * 4));
+  CU(cudaMemcpy(dw, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(db, bias_host, (size_t)nout * 4, cudaMemcpyHostToDevice));
+  LinArgs a = lin(x, rows, dw, db);
+  a.out = out; a.residual = residual;
+  int rc = 0;
+  if (k == 128 && nout == 128 && relu && !residual) rc = run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, 1, st);
+  else if (k == 128 && nout == 64 && relu && !residual) rc = run_linear<128, 64, PRO_NONE, EPI_BIAS_RELU>(a, 1, st);
+  else if (k == 64 && nout == 64 && relu && !residual) rc = run_linear<64, 64, PRO_NONE, EPI_BIAS_RELU>(a, 1, st);
+  else if (k == 64 && nout == 128 && !relu && residual) rc = run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, 1, st);
+  else rc = fail(GMF_ERR_INVALID, "gmf_debug_linear: unsupported (k, nout, relu, residual) combination");
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(dw); cudaFree(db);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(e, "gmf_debug_linear sync");
+  return 0;
+}
+
+int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const float* v, const float* src, const float* tgt, int B, int Lq,
+                        int Lk, int D, float scale, float sigma_d, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
+  const bool sc = src && tgt;
+  if (!((D == 64 && !sc) || (D == 128 && sc && Lq == Lk))) return fail(GMF_ERR_INVALID, "gmf_debug_attention: D=64 plain or D=128 SC (Lq==Lk)");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Work w;
+  TRY(check_ws(ctx, w, workspace, workspace_bytes, B, std::max(Lq, Lk), std::max(Lq, Lk)));
+  const int qt = cdiv(Lq, 128), kt = cdiv(Lk, 128);
+  __nv_bfloat16 *Q = sc ? w.qs : w.qf, *K = sc ? w.ks : w.kf, *V = sc ? w.vts : w.vtf;
+  const long long qe = (long long)qt * 128 * D, ke = (long long)kt * 128 * D;
+  pack_tiles_kernel<<<dim3((unsigned)((qe + 255) / 256), B), 256, 0, st>>>(q, Lq, D, qt, scale * kLog2e, 0, Q); LAUNCHED();
+  pack_tiles_kernel<<<dim3((unsigned)((ke + 255) / 256), B), 256, 0, st>>>(k, Lk, D, kt, 1.f, 0, K); LAUNCHED();
+  pack_tiles_kernel<<<dim3((unsigned)((ke + 255) / 256), B), 256, 0, st>>>(v, Lk, D, kt, 1.f, 1, V); LAUNCHED();
+  AttnArgs a{};
+  a.q_t = Q; a.k_t = K; a.vt_t = V; a.out = out; a.Lq = Lq; a.Lk = Lk; a.q_tiles = qt; a.k_tiles = kt;
+  cudaError_t e;
+  if (sc) {
+    TRY(run_prep(w, src, tgt, B, Lk, st));
+    a.kpts = w.kpts; a.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
+    e = launch_attn<128, true>(a, B, st);
+  } else {
+    e = launch_attn<64, false>(a, B, st);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail_cuda(e, "attn launch");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// Token-wise linear layers of the GMF-PointDSC encoder as ONE tcgen05 (kind::tf32) kernel family with fused
+// prologues (ConvPosEnc 3-tap stencil, LayerNorm) and epilogues (bias / folded-BN / ReLU / residual / GEGLU /
+// bf16 Q,K,V^T tile emission for the flash-attention kernels).
+//
+//   out[128-row tile, NOUT] = epilogue( prologue(x)[128, K] . W[NOUT, K]^T )
+//
+// Reference ops replaced (GMF_PointDSC/models): PointCN conv+BN+ReLU PointDSC.py:104-111; projection_q/k/v
+// :56-58; fc_message :13-21,65; PreNorm/LayerNorm fusion_layer.py:32-52; to_q/to_kv/to_out :84-94;
+// FeedForward+GEGLU :54-69; ConvPosEnc :118-128.
+//
+// Structure per CTA (one 128-token tile of one pair): 8 worker warps build the A operand (prologue math, written to
+// shared memory in the 128B-swizzled K-major image), one control thread streams pre-swizzled weight chunks with
+// bulk-async copies (TMA engine) through a 2-deep mbarrier ring and issues tcgen05.mma into TMEM; the workers then
+// drain TMEM (tcgen05.ld, one thread per accumulator row) through the fused epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace gmf {
+
+enum { PRO_NONE = 0, PRO_LN = 1, PRO_CPE_LN = 2, PRO_TILED = 3 };
+enum { EPI_BIAS_RELU = 0, EPI_BIAS_RES = 1, EPI_GEGLU_TILED = 2, EPI_QKV_SC = 3, EPI_Q_FUS = 4, EPI_KV_FUS = 5, EPI_BIAS = 6 };
+
+struct LinArgs {
+  const float* x;         // PRO_TILED: tiled activation image, else [B, L, K] row-major
+  int L;                  // tokens per pair
+  int tiles;              // ceil(L / 128)
+  const float* ln_g;      // LayerNorm gamma/beta [K]
+  const float* ln_b;
+  const float* cpe_w;     // depthwise taps [K][3]
+  const float* cpe_b;     // [K]
+  float* x0_out;          // PRO_CPE_LN: x + dwconv(x) written here (residual stream), may be null
+  const float* w_packed;  // weight chunks, swizzled, in issue order
+  const float* bias;      // [NOUT] (already BN-folded / pre-scaled by the packer)
+  const float* residual;  // EPI_BIAS_RES: [B, L, NOUT]
+  float* out;             // fp32 output (row-major [B,L,NOUT] or tiled image for EPI_GEGLU_TILED)
+  __nv_bfloat16* t0;      // tiled bf16 outputs (Q / K / V^T)
+  __nv_bfloat16* t1;
+  __nv_bfloat16* t2;
+};
+
+template <int K, int NOUT, int PRO>
+struct LinCfg {
+  static constexpr int KCH = (PRO == PRO_TILED) ? 64 : K;
+  static constexpr int NKC = K / KCH;
+  static constexpr int NB = NOUT >= 128 ? 128 : NOUT;
+  static constexpr int PASSES = NOUT > 512 ? NOUT / 512 : 1;
+  static constexpr int NNB = NOUT / NB / PASSES;
+  static constexpr int PASS_COLS = NNB * NB;
+  static constexpr int TMEM_COLS = PASS_COLS <= 32 ? 32 : PASS_COLS <= 64 ? 64 : PASS_COLS <= 128 ? 128 : PASS_COLS <= 256 ? 256 : 512;
+  static constexpr int A_BYTES = 128 * KCH * 4;            // per k-chunk
+  static constexpr int A_TOTAL = (PRO == PRO_TILED) ? 2 * A_BYTES : 128 * K * 4;
+  static constexpr int B_BYTES = NB * KCH * 4;
+  static constexpr int NSTAGE = PASSES * NNB * NKC;
+  static constexpr int SMEM = 1024 + A_TOTAL + 2 * B_BYTES + 256;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int K, int NOUT, int PRO, int EPI>
+__global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
+  using Cfg = LinCfg<K, NOUT, PRO>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::A_TOTAL;
+  uint64_t* bars = (uint64_t*)(sB + 2 * Cfg::B_BYTES);
+  uint64_t* full = bars;          // [2] weights (+A chunk) landed
+  uint64_t* mma_done = bars + 2;  // [2] MMAs that read stage buffers retired
+  uint64_t* a_ready = bars + 4;   // workers finished the A operand
+  uint64_t* acc_full = bars + 5;  // accumulators of a pass complete
+  uint64_t* tmem_free = bars + 6; // workers drained TMEM of a pass
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, pair = blockIdx.y;
+  const int row0 = tile * 128;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
+    mbar_init(a_ready, 256); mbar_init(acc_full, 1); mbar_init(tmem_free, 256);
+    fence_mbar_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------- control thread: TMA + MMA issue -------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, Cfg::NB, kFmtTF32);
+      const uint8_t* wsrc = (const uint8_t*)a.w_packed;
+      const uint8_t* asrc = (const uint8_t*)a.x + (size_t)(pair * a.tiles + tile) * (size_t)(Cfg::NKC * Cfg::A_BYTES);
+      auto issue_load = [&](int it) {
+        const int buf = it & 1;
+        if (PRO == PRO_TILED) {
+          mbar_expect_tx(&full[buf], Cfg::B_BYTES + Cfg::A_BYTES);
+          bulk_g2s(sA + buf * Cfg::A_BYTES, asrc + (size_t)(it % Cfg::NKC) * Cfg::A_BYTES, Cfg::A_BYTES, &full[buf]);
+        } else {
+          mbar_expect_tx(&full[buf], Cfg::B_BYTES);
+        }
+        bulk_g2s(sB + buf * Cfg::B_BYTES, wsrc + (size_t)it * Cfg::B_BYTES, Cfg::B_BYTES, &full[buf]);
+      };
+      issue_load(0);
+      for (int it = 0; it < Cfg::NSTAGE; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < Cfg::NSTAGE) {
+          if (it >= 1) mbar_wait(&mma_done[(it + 1) & 1], ((it - 1) >> 1) & 1);
+          issue_load(it + 1);
+        }
+        const int pass = it / (Cfg::NNB * Cfg::NKC);
+        const int nbi = (it / Cfg::NKC) % Cfg::NNB;
+        const int kc = it % Cfg::NKC;
+        if (it == 0 && PRO != PRO_TILED) mbar_wait(a_ready, 0);
+        if (pass > 0 && nbi == 0 && kc == 0) mbar_wait(tmem_free, (pass - 1) & 1);
+        mbar_wait(&full[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA) + (PRO == PRO_TILED ? buf * Cfg::A_BYTES : 0);
+        const uint32_t b_base = smem_u32(sB) + buf * Cfg::B_BYTES;
+#pragma unroll
+        for (int at = 0; at < Cfg::KCH / 32; ++at) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = umma_desc_sw128(a_base + at * 16384 + ks * 32);
+            const uint64_t bd = umma_desc_sw128(b_base + at * (Cfg::NB * 128) + ks * 32);
+            tc_mma_tf32(tmem + nbi * Cfg::NB, ad, bd, idesc, (kc > 0 || at > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        tc_commit(&mma_done[buf]);
+        if (nbi == Cfg::NNB - 1 && kc == Cfg::NKC - 1) tc_commit(acc_full);
+      }
+    }
+  } else {
+    // ------------------------------- workers: A operand prologue -------------------------------
+    if (PRO != PRO_TILED) {
+      if (K == 128) {
+        const int c4 = lane * 4;  // this lane's 4 channels
+        float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 w0 = b4, w1 = b4, w2 = b4, cb = b4;
+        if (PRO == PRO_LN || PRO == PRO_CPE_LN) {
+          g4 = *reinterpret_cast<const float4*>(a.ln_g + c4);
+          b4 = *reinterpret_cast<const float4*>(a.ln_b + c4);
+        }
+        if (PRO == PRO_CPE_LN) {
+          const float* w = a.cpe_w + c4 * 3;
+          w0 = make_float4(w[0], w[3], w[6], w[9]);
+          w1 = make_float4(w[1], w[4], w[7], w[10]);
+          w2 = make_float4(w[2], w[5], w[8], w[11]);
+          cb = *reinterpret_cast<const float4*>(a.cpe_b + c4);
+        }
+        const float* xp = a.x + (size_t)pair * a.L * K;
+        for (int r = warp; r < 128; r += 8) {
+          const int gr = row0 + r;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gr < a.L) {
+            v = *reinterpret_cast<const float4*>(xp + (size_t)gr * K + c4);
+            if (PRO == PRO_CPE_LN) {
+              float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), nv = pv;
+              if (gr > 0) pv = *reinterpret_cast<const float4*>(xp + (size_t)(gr - 1) * K + c4);
+              if (gr + 1 < a.L) nv = *reinterpret_cast<const float4*>(xp + (size_t)(gr + 1) * K + c4);
+              v.x += fmaf(w0.x, pv.x, fmaf(w1.x, v.x, fmaf(w2.x, nv.x, cb.x)));
+              v.y += fmaf(w0.y, pv.y, fmaf(w1.y, v.y, fmaf(w2.y, nv.y, cb.y)));
+              v.z += fmaf(w0.z, pv.z, fmaf(w1.z, v.z, fmaf(w2.z, nv.z, cb.z)));
+              v.w += fmaf(w0.w, pv.w, fmaf(w1.w, v.w, fmaf(w2.w, nv.w, cb.w)));
+              if (a.x0_out) *reinterpret_cast<float4*>(a.x0_out + ((size_t)pair * a.L + gr) * K + c4) = v;
+            }
+            if (PRO == PRO_LN || PRO == PRO_CPE_LN) {
+              const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / 128.0f);
+              const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+              const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / 128.0f);
+              const float rs = rsqrtf(var + 1e-5f);
+              v = make_float4(fmaf(dx * rs, g4.x, b4.x), fmaf(dy * rs, g4.y, b4.y), fmaf(dz * rs, g4.z, b4.z),
+                              fmaf(dw * rs, g4.w, b4.w));
+            }
+          }
+          *reinterpret_cast<float4*>(sA + (lane >> 3) * 16384 + swz_off(r, lane & 7)) = to_tf32(v);
+        }
+      } else {  // K == 64: half a warp per row
+        const float* xp = a.x + (size_t)pair * a.L * K;
+        const int ch = lane & 15;
+        for (int r = warp * 2 + (lane >> 4); r < 128; r += 16) {
+          const int gr = row0 + r;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gr < a.L) v = *reinterpret_cast<const float4*>(xp + (size_t)gr * K + ch * 4);
+          *reinterpret_cast<float4*>(sA + (ch >> 3) * 16384 + swz_off(r, ch & 7)) = to_tf32(v);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(a_ready);
+    }
+
+    // ------------------------------- workers: epilogue -------------------------------
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    const int gr = row0 + r;
+    const bool valid = gr < a.L;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const size_t grow = (size_t)pair * a.L + gr;
+#pragma unroll 1
+    for (int pass = 0; pass < Cfg::PASSES; ++pass) {
+      mbar_wait(acc_full, pass & 1);
+      tc_fence_after();
+      constexpr int NCHUNK = (EPI == EPI_GEGLU_TILED) ? 8 : Cfg::PASS_COLS / 32;
+#pragma unroll 1
+      for (int c = half; c < NCHUNK; c += 2) {
+        uint32_t v[32];
+        tmem_ld32(trow + c * 32, v);
+        if (EPI == EPI_GEGLU_TILED) {
+          uint32_t gt[32];
+          tmem_ld32(trow + 256 + c * 32, gt);
+          tmem_ld_wait();
+          const int oc0 = pass * 256 + c * 32;       // output (value) column
+          const float* bv = a.bias + oc0;
+          const float* bg = a.bias + 512 + oc0;
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = (__uint_as_float(v[i]) + __ldg(bv + i)) * gelu_erf(__uint_as_float(gt[i]) + __ldg(bg + i));
+          // tiled image for the next GEMM (K=512 in 8 chunks of 64 = 2 atoms of 32 floats)
+          uint8_t* dst = (uint8_t*)a.out + ((size_t)(pair * a.tiles + tile) * 8 + (oc0 >> 6)) * 32768 + ((oc0 >> 5) & 1) * 16384;
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(dst + swz_off(r, j)) = to_tf32(make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+          }
+        } else {
+          tmem_ld_wait();
+          const int col0 = c * 32;
+          if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RES || EPI == EPI_BIAS) {
+            if (valid) {
+              float* op = a.out + grow * NOUT + col0;
+              const float* rp = a.residual + grow * NOUT + col0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(a.bias + col0 + 4 * j);
+                float4 o = make_float4(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y,
+                                       __uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                if (EPI == EPI_BIAS_RELU) {
+                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                if (EPI == EPI_BIAS_RES) {
+                  const float4 rr = *reinterpret_cast<const float4*>(rp + 4 * j);
+                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                }
+                *reinterpret_cast<float4*>(op + 4 * j) = o;
+              }
+            }
+          } else {
+            // bf16 tile emission for the attention kernels
+            int which, dcol0;   // which: 0 = Q-like (row-major tile), 1 = K-like, 2 = V (transposed tile)
+            int drows;          // head dim
+            if (EPI == EPI_QKV_SC) { which = col0 >> 7; dcol0 = col0 & 127; drows = 128; }
+            else if (EPI == EPI_Q_FUS) { which = 0; dcol0 = col0; drows = 64; }
+            else { which = 1 + (col0 >> 6); dcol0 = col0 & 63; drows = 64; }
+            const float* bp = a.bias + col0;
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = valid ? __uint_as_float(v[i]) + (a.bias ? __ldg(bp + i) : 0.f) : 0.f;
+            const size_t tile_elems = (size_t)128 * drows;
+            if (which < 2) {
+              __nv_bfloat16* base = (which == 0 ? a.t0 : a.t1) + (size_t)(pair * a.tiles + tile) * tile_elems;
+              uint8_t* dst = (uint8_t*)base + (dcol0 >> 6) * 16384;
+              const int cc0 = (dcol0 & 63) >> 3;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 pk;
+                pk.x = pack_bf16(o[8 * j], o[8 * j + 1]); pk.y = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
+                pk.z = pack_bf16(o[8 * j + 4], o[8 * j + 5]); pk.w = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
+                *reinterpret_cast<uint4*>(dst + swz_off(r, cc0 + j)) = pk;
+              }
+            } else {
+              __nv_bfloat16* base = a.t2 + (size_t)(pair * a.tiles + tile) * tile_elems;
+              uint8_t* dst = (uint8_t*)base + (r >> 6) * (drows * 128) + (r & 7) * 2;
+              const int kchunk = (r & 63) >> 3;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int d = dcol0 + i;
+                *reinterpret_cast<__nv_bfloat16*>(dst + swz_off(d, kchunk)) = __float2bfloat16_rn(o[i]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, Cfg::TMEM_COLS);
+}
+
+template <int K, int NOUT, int PRO, int EPI>
+inline cudaError_t launch_linear(const LinArgs& a, int pairs, cudaStream_t st) {
+  using Cfg = LinCfg<K, NOUT, PRO>;
+  static bool configured = false;
+  auto kern = linear_tc_kernel<K, NOUT, PRO, EPI>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<dim3(a.tiles, pairs), 288, Cfg::SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gmf

@@ -1,0 +1,131 @@
+/*
+ * gmf_b200 — C ABI of the B200-native GMF-PointDSC correspondence outlier-rejection forward path.
+ *
+ * The reference (XiaoshuiHuang/GMF, GMF_PointDSC/) has no FFI: its boundary is the Python nn.Module
+ * `PointDSC.forward(data) -> dict` (models/PointDSC.py:146-266).  This header is the boundary a
+ * maintainer binds instead (ctypes stub in INTEGRATION.md; `gmf_b200/module.py` is that binding):
+ * everything between "image tokens exist" (PointDSC.py:135) and the returned dict (:261-266) runs
+ * behind `gmf_pointdsc_forward`, and each reference method on the path has a per-stage entry point so
+ * that parity can be checked stage by stage with teacher forcing.
+ *
+ * Conventions: plain pointers and sizes only.  Unless a function says "host", every data pointer is
+ * a DEVICE pointer owned by the caller; tensors are dense row-major fp32 (indices int32).  All
+ * functions return 0 on success or a negative gmf_status; the message is available from
+ * gmf_last_error() (thread local).  Work is enqueued asynchronously on `stream` (a cudaStream_t
+ * passed as void*; NULL = default stream); nothing synchronises the device unless stated.  A context
+ * is bound to one device and may be used from one thread at a time; distinct contexts are
+ * independent (one process / context per GPU when sharding pairs).
+ */
+#ifndef GMF_B200_H
+#define GMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmf_ctx gmf_ctx;
+
+enum gmf_status {
+  GMF_OK = 0,
+  GMF_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  GMF_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  GMF_ERR_STATE = -3,     /* weights not loaded, workspace too small, ... */
+};
+
+/* Hyper-parameters of PointDSC.__init__ (models/PointDSC.py:147-167). */
+typedef struct gmf_config {
+  int32_t num_layers;       /* 12 */
+  int32_t num_iterations;   /* 10, power iteration cap (:160) */
+  int32_t k;                /* 40, seed neighbourhood (:166), <= 40 */
+  float ratio;              /* 0.1, seeds = int(N * ratio) (:161) */
+  float inlier_threshold;   /* 0.10 (3DMatch) / 1.2 (KITTI) (:163) */
+  float nms_radius;         /* (:167) */
+} gmf_config;
+
+const char* gmf_last_error(void);
+const char* gmf_version(void);
+
+/* ---- context & weights ------------------------------------------------------------------- */
+int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg);
+void gmf_destroy(gmf_ctx* ctx);
+
+/* The hot-path tensors of the reference state_dict, in canonical order (gmf_b200/weights.py mirrors
+ * this table).  gmf_weight_spec writes the state_dict key into name[cap] and the element count. */
+int gmf_weight_count(int num_layers);
+int gmf_weight_spec(int num_layers, int index, char* name, int cap, int64_t* numel);
+/* host pointer: all tensors concatenated in that order (fp32).  Folds eval-mode BatchNorm into the
+ * preceding 1x1 conv, folds the softmax scales into the query projections, rounds GEMM weights to
+ * TF32 and uploads them as pre-swizzled UMMA tile images.  May be called again after an update. */
+int gmf_load_weights(gmf_ctx* ctx, const float* host_flat, int64_t numel);
+
+/* ---- whole path --------------------------------------------------------------------------- */
+size_t gmf_workspace_bytes(const gmf_ctx* ctx, int B, int N, int T);
+
+/* PointDSC.forward after the image backbone (PointDSC.py:137-266), testing-mode semantics per pair
+ * (B > 1 == the reference looped over pairs: it asserts bs == 1, :279,:504).
+ *   corr_pos [B,N,6]  src,tgt [B,N,3]  p_tok,q_tok [B,T,128] (backbone tokens, PointDSC.py:129-135)
+ * outputs: final_trans [B,4,4], final_labels [B,N] (0/1), confidence [B,N] (classifier logits),
+ *          seeds [B,int(N*ratio)] int32; optional (may be NULL): feat [B,N,128] un-normalised encoder
+ *          features.  testing == 0 gives the training-mode selections (top-S seeds without NMS, no
+ *          post-refinement, :246,:256) — final_labels stay 0/1 from the best hypothesis. */
+int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
+                         const float* q_tok, int B, int N, int T, int testing, float* final_trans, float* final_labels,
+                         float* confidence, int32_t* seeds, float* feat, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D of the inputs, the forward, D2H of
+ * final_trans / final_labels / confidence, then a stream synchronise.  Uses context-owned device
+ * staging (grown on demand). */
+int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
+                              const float* q_tok, int B, int N, int T, int testing, float* final_trans,
+                              float* final_labels, float* confidence, void* stream);
+
+/* ---- per-stage entry points (teacher-forced parity) ---------------------------------------- */
+/* FusionLayer.forward (models/fusion_layer.py:172-201), depth 0.  layer < 0: encoder.fusion_layer_1 (pe=False);
+ * layer >= 0: NonLocal_layer_{layer}.fusion_layer_2 (pe=True).  queries [B,Lq,128], context [B,Lk,128] -> out [B,Lq,128]. */
+int gmf_fusion_layer(gmf_ctx* ctx, int layer, const float* queries, const float* context, int B, int Lq, int Lk, float* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* SC-guided non-local attention core (PointDSC.py:56-64): Q/K/V projections + softmax(compat * QK^T/sqrt(C)) V,
+ * compat recomputed on the fly from src/tgt.  feat [B,N,128] (PointCN output, token-major) -> msg [B,N,128]. */
+int gmf_sc_attention(gmf_ctx* ctx, int layer, const float* feat, const float* src, const float* tgt, int B, int N, float* msg,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* One encoder layer = PointCN_layer_i + NonLocal_layer_i (PointDSC.py:140-142, 40-74).  feat_in/out [B,N,128] token-major. */
+int gmf_encoder_layer(gmf_ctx* ctx, int layer, const float* feat_in, const float* src, const float* tgt, const float* image_feat,
+                      int B, int N, int T, float* feat_out, void* workspace, size_t workspace_bytes, void* stream);
+/* F.normalize + classification MLP (PointDSC.py:229,241).  feat [B,N,128] -> normed [B,N,128], confidence [B,N]. */
+int gmf_classify(gmf_ctx* ctx, const float* feat, int B, int N, float* normed, float* confidence, void* stream);
+/* pick_seeds (PointDSC.py:268-286) when use_nms != 0, else argsort(confidence, descending)[:S] (:246). */
+int gmf_pick_seeds(gmf_ctx* ctx, const float* src, const float* confidence, int B, int N, int use_nms, int32_t* seeds,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* cal_seed_trans up to the per-seed transforms (PointDSC.py:323-407): kNN, 40x40 compat, power iteration with the
+ * reference's global allclose exit, weighted Kabsch.  Optional outputs may be NULL. */
+int gmf_seed_hypotheses(gmf_ctx* ctx, const float* normed, const float* src, const float* tgt, const int32_t* seeds, int B, int N,
+                        int S, float* seed_trans /*[B,S,4,4]*/, int32_t* knn_idx /*[B,S,k]*/, float* seed_weight /*[B,S,k]*/,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* Hypothesis scoring (PointDSC.py:413-427) + post_refinement (:493-528, when refine != 0).  fitness_counts [B,S] int32,
+ * best [B] int32 and pre_refine [B,4,4] are optional. */
+int gmf_score_hypotheses(gmf_ctx* ctx, const float* seed_trans, const float* src, const float* tgt, int B, int N, int S, int refine,
+                         float* final_trans, float* final_labels, int32_t* fitness_counts, int32_t* best, float* pre_refine,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* rigid_transform_3d (models/common.py:10-50): A,B [M,k,3], weights [M,k] or NULL -> T [M,4,4]. */
+int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* B, const float* weights, int M, int k, float* T, void* stream);
+
+/* ---- introspection / debugging ------------------------------------------------------------- */
+/* number of gmf kernels launched by this process since the last reset (bench.py's gpu_launches) */
+int64_t gmf_launch_count(int reset);
+/* out[rows,nout] = act(x[rows,k] . W[nout,k]^T + bias) (+ residual) through the tcgen05 TF32 linear kernel.
+ * W, bias are HOST pointers (packed on the fly); x/residual/out device.  (k,nout) in {(128,128),(128,64),(64,64),(64,128)}. */
+int gmf_debug_linear(gmf_ctx* ctx, const float* x, const float* w_host, const float* bias_host, const float* residual, int rows, int k,
+                     int nout, int relu, float* out, void* stream);
+/* out[B,Lq,D] = softmax(q k^T * scale [* compat]) v through the tcgen05 attention kernel; q,k,v row-major fp32 device
+ * [B,L,D], D in {64,128}; src/tgt non-NULL (with D == 128, Lq == Lk) switches the SC-guided variant on. */
+int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const float* v, const float* src, const float* tgt, int B, int Lq,
+                        int Lk, int D, float scale, float sigma_d, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMF_B200_H */
