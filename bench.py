@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""Headline benchmark: fragment pairs/s of the GMF-PointDSC forward hot path at 5k correspondences.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm's CPU path (oracle port)
+
+A "step" is one pass of the hot path (Fusion-1 ... post-refinement, everything after the image tokens exist) over one
+batch of synthetic fragment pairs per GPU.  Workload = BASELINE.json configs[1]: 5000 correspondences/pair, 64 pairs per
+GPU, 480x640 images -> 4800 image tokens, 12 layers, testing mode, random-init weights.  Pairs are independent, so N GPUs
+run N independent shards (weak scaling, no data-path collective); rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fragment pairs/sec, GMF-PointDSC fwd @5k corr"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gmf_b200", choices=["gmf_b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=64, help="pairs per GPU per step (cfg#2: 64)")
+    ap.add_argument("--corr", type=int, default=5000)
+    ap.add_argument("--tokens", type=int, default=4800)
+    ap.add_argument("--layers", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"cfg#2 GMF-PointDSC 3DMatch/FCGF shape: {a.corr} correspondences/pair, {a.pairs} pairs/GPU/step, "
+            f"{a.tokens} image tokens/fragment (480x640), {a.layers} layers, testing mode, random-init weights")
+
+
+def flops_per_pair(n, t, layers):
+    """Algorithmic FLOPs of the timed path (SURVEY.md §8a/§8d formulas)."""
+    c, d1 = 128, 64
+    def fusion(nq, tk):
+        return 2 * nq * c * d1 + 2 * tk * c * 2 * d1 + 4 * nq * tk * d1 + 2 * nq * d1 * c + 2 * nq * c * 1024 + 2 * nq * 512 * c
+    per_layer = 2 * n * c * c + 6 * n * c * c + 4 * n * n * c + 2 * n * (c * 64 + 64 * 64 + 64 * c) + fusion(n, t)
+    return fusion(t, t) + 2 * n * 6 * c + layers * per_layer + 2 * n * (c * 32 + 32 * 32 + 32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 2:] if len(sm) > 3 else sm          # upper half == samples under load
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1391.3), d.get("hbm_gbs", 6548.2), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs(a, rank):
+    from gmf_b200.synth import synth_pairs, synth_tokens
+    pr = synth_pairs(a.pairs, a.corr, seed=2000 + rank, extent=3.0, inlier_ratio=0.30, noise=0.002)
+    p_tok = synth_tokens(a.pairs, a.tokens, seed=10 + rank)
+    q_tok = synth_tokens(a.pairs, a.tokens, seed=20 + rank)
+    return pr, p_tok, q_tok
+
+
+def synth_weights(layers):
+    from gmf_b200.synth import synth_state_dict
+    from gmf_b200.weights import hot_path_spec
+    return synth_state_dict(hot_path_spec(layers), seed=0, plain_init=True)
+
+
+def cpu_reference_pairs_per_s(a, steps, warmup, sample_pairs=1):
+    """The reference algorithm on the host cores (oracle port of the reference's PyTorch CPU path), bs=1 loop."""
+    from oracle import pointdsc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth_weights(a.layers)
+    cfg = dict(O.DEFAULT_CFG, num_layers=a.layers)
+    a1 = argparse.Namespace(**{**vars(a), "pairs": sample_pairs})
+    pr, p_tok, q_tok = make_inputs(a1, 0)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.forward_testing(sd, cfg, pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    return sample_pairs * len(times) / tot, cores, 1000.0 * tot / len(times)
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    v, cores, ms = cpu_reference_pairs_per_s(a, a.steps, a.warmup)
+    sample = f"1 pair/step of the same workload (N={a.corr}, T={a.tokens}, {a.layers} layers), {a.steps} timed steps after {a.warmup} warm-ups"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "reference algorithm on host CPU cores (oracle port of the reference's "
+                       "PyTorch fp32 path; the Python reference tree does not travel to the GPU box); step = 1 pair"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    import torch.distributed as dist
+    from gmf_b200.engine import Engine
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(num_layers=a.layers, device=dev)
+    eng.load_state_dict(synth_weights(a.layers))
+    pr, p_tok, q_tok = make_inputs(a, rank)
+    host = [pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok]
+    host = [t.contiguous().pin_memory() for t in host]
+    devt = [t.to(dev, non_blocking=True) for t in host]
+    h_trans = torch.empty(a.pairs, 4, 4).pin_memory()
+    h_lab = torch.empty(a.pairs, a.corr).pin_memory()
+    h_conf = torch.empty(a.pairs, a.corr).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    step_dev = lambda: eng.forward(*devt, testing=True)                                    # noqa: E731
+    step_host = lambda: eng.forward_host(*host, h_trans, h_lab, h_conf, testing=True)      # noqa: E731
+
+    for _ in range(max(a.warmup, 3)):
+        out = step_dev()
+    torch.cuda.synchronize()
+    eng.launch_count(reset=True)
+    with ClockSampler(local) as cs:
+        ms = timed(step_dev, a.steps)
+    launches = eng.launch_count(reset=True)
+    clocks = cs.summary()
+    value = world * a.pairs * a.steps / (ms / 1000.0)
+
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(2):
+            step_host()
+        ms_h = timed(step_host, a.steps)
+        h2d = sum(t.numel() * 4 for t in host)
+        d2h = (h_trans.numel() + h_lab.numel() + h_conf.numel()) * 4
+        e2e = {"value": world * a.pairs * a.steps / (ms_h / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_h / a.steps, "api": "gmf_pointdsc_forward_host (C ABI, pinned host buffers in/out, stream-synchronised)"}
+
+    roof = None
+    prof_table = None
+    if rank == 0 and not a.no_roofline:
+        peak_tf, hbm, how = measured_peaks()
+        eng.profile(True)
+        for _ in range(a.steps):
+            step_dev()
+        prof = eng.profile_read()
+        eng.profile(False)
+        tot_ms = sum(v[0] for v in prof.values())
+        prof_table = {k: {"ms_per_step": v[0] / a.steps, "launches_per_step": v[1] / a.steps, "share": v[0] / tot_ms} for k, v in prof.items()}
+        sc_ms, sc_n = prof["attn_sc"]
+        sc_flops = 4.0 * a.corr * a.corr * 128 * a.pairs * a.layers * a.steps           # 4 N^2 C per pair-layer
+        ach = sc_flops / (sc_ms / 1000.0) / 1e12
+        roof = {"kernel": "attn_tc_kernel<128,SC> (SC-guided non-local flash attention, compat on the fly)", "bound": "tensor",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": how, "avg_launch_ms": sc_ms / max(sc_n, 1), "launches": sc_n,
+                "algorithmic_flops_per_launch": sc_flops / max(sc_n, 1),
+                "whole_path": {"flops_per_pair": flops_per_pair(a.corr, a.tokens, a.layers),
+                               "achieved_tflops": flops_per_pair(a.corr, a.tokens, a.layers) * value / world / 1e12,
+                               "frac_of_tensor_peak": flops_per_pair(a.corr, a.tokens, a.layers) * value / world / 1e12 / peak_tf}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, cores, msp = cpu_reference_pairs_per_s(a, steps=1, warmup=0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 pair of the same workload (N={a.corr}, T={a.tokens}, {a.layers} layers), single timed pass, {msp / 1000:.1f} s"}
+
+    # sanity on the last device result: poses must be finite and close to the synthetic ground truth
+    tr = out["final_trans"].float().cpu()
+    gt = pr["gt_trans"]
+    te_mm = float((tr[:, :3, 3] - gt[:, :3, 3]).norm(dim=-1).max() * 1000)
+    if rank == 0:
+        ws_gb = eng.workspace(a.pairs, a.corr, a.tokens)[1] / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 attention operands + tf32 linear layers, fp32 accumulate/softmax/classifier", "data": "synthetic",
+                "config": {"workload": workload_name(a), "parallelism": f"pair-sharded replicas x{world}, no collective on the data path",
+                           "cache": f"per-step inputs ({sum(t.numel() * 4 for t in host) / 1e6:.0f} MB) + workspace ({ws_gb:.1f} GB) exceed the 126 MB L2",
+                           "max_translation_error_vs_gt_mm": te_mm},
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernel_profile": prof_table}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

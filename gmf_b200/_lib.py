@@ -16,7 +16,7 @@ EXPORTS = [
     "gmf_load_weights", "gmf_workspace_bytes", "gmf_pointdsc_forward", "gmf_pointdsc_forward_host",
     "gmf_fusion_layer", "gmf_sc_attention", "gmf_encoder_layer", "gmf_classify", "gmf_pick_seeds",
     "gmf_seed_hypotheses", "gmf_score_hypotheses", "gmf_rigid_transform_3d", "gmf_launch_count",
-    "gmf_debug_linear", "gmf_debug_attention",
+    "gmf_debug_linear", "gmf_debug_attention", "gmf_profile_enable", "gmf_profile_read",
 ]
 
 
@@ -66,6 +66,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.gmf_rigid_transform_3d.argtypes = [vp, vp, vp, vp, i, i, vp, vp]
     lib.gmf_debug_linear.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp, vp]
     lib.gmf_debug_attention.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, vp, vp, sz, vp]
+    lib.gmf_profile_enable.argtypes = [vp, i]
+    lib.gmf_profile_read.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 

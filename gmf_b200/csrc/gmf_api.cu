@@ -20,6 +20,34 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 
+// optional per-launch CUDA-event profiler (bench.py's roofline leg); categories are listed in include/gmf_b200.h
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;     // pairs (start, stop)
+  std::vector<int> cat;
+  size_t used = 0;                 // events handed out
+};
+thread_local Prof* g_prof = nullptr;
+struct ProfScope {
+  cudaStream_t st; cudaEvent_t stop = nullptr;
+  ProfScope(int category, cudaStream_t s) : st(s) {
+    Prof* p = g_prof;
+    if (!p || !p->on) return;
+    if (p->used + 2 > p->ev.size()) {
+      const size_t old = p->ev.size();
+      p->ev.resize(old + 512);
+      for (size_t i = old; i < p->ev.size(); ++i) cudaEventCreate(&p->ev[i]);
+    }
+    cudaEventRecord(p->ev[p->used], st);
+    stop = p->ev[p->used + 1];
+    p->cat.push_back(category);
+    p->used += 2;
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+};
+enum { CAT_PCN = 0, CAT_QKV, CAT_FC12, CAT_QFUS, CAT_KVFUS, CAT_OUT64, CAT_FFN1, CAT_FFN2, CAT_ATTN_FUS, CAT_ATTN_SC, CAT_PREP,
+       CAT_CLASSIFY, CAT_SEEDS, CAT_KNN, CAT_SPECTRAL, CAT_SCORE, CAT_COUNT };
+
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -168,6 +196,7 @@ struct gmf_ctx {
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
+  Prof prof;
 };
 
 namespace {
@@ -235,7 +264,8 @@ int check_ws(const gmf_ctx* ctx, Work& w, void* ws, size_t bytes, int B, int N, 
 // launch schedule
 // ------------------------------------------------------------------------------------------------
 template <int K, int NOUT, int PRO, int EPI>
-int run_linear(const LinArgs& a, int pairs, cudaStream_t st) {
+int run_linear(const LinArgs& a, int pairs, cudaStream_t st, int category = CAT_FC12) {
+  ProfScope ps(category, st);
   cudaError_t e = launch_linear<K, NOUT, PRO, EPI>(a, pairs, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail_cuda(e, "linear_tc launch");
@@ -256,9 +286,9 @@ int run_fusion(const FusionW& f, Work& w, const float* xq, const float* ctxk, in
     a.ln_g = f.lnq_g; a.ln_b = f.lnq_b; a.t0 = w.qf;
     if (f.pe) {
       a.cpe_w = f.cpe_q_w; a.cpe_b = f.cpe_q_b; a.x0_out = w.x0; resid0 = w.x0;
-      TRY((run_linear<128, 64, PRO_CPE_LN, EPI_Q_FUS>(a, B, st)));
+      TRY((run_linear<128, 64, PRO_CPE_LN, EPI_Q_FUS>(a, B, st, CAT_QFUS)));
     } else {
-      TRY((run_linear<128, 64, PRO_LN, EPI_Q_FUS>(a, B, st)));
+      TRY((run_linear<128, 64, PRO_LN, EPI_Q_FUS>(a, B, st, CAT_QFUS)));
     }
   }
   {  // context: (CPE) -> LN_ctx -> to_kv => bf16 K tiles, V^T tiles
@@ -266,15 +296,16 @@ int run_fusion(const FusionW& f, Work& w, const float* xq, const float* ctxk, in
     a.ln_g = f.lnc_g; a.ln_b = f.lnc_b; a.t1 = w.kf; a.t2 = w.vtf;
     if (f.pe) {
       a.cpe_w = f.cpe_c_w; a.cpe_b = f.cpe_c_b; a.x0_out = nullptr;
-      TRY((run_linear<128, 128, PRO_CPE_LN, EPI_KV_FUS>(a, B, st)));
+      TRY((run_linear<128, 128, PRO_CPE_LN, EPI_KV_FUS>(a, B, st, CAT_KVFUS)));
     } else {
-      TRY((run_linear<128, 128, PRO_LN, EPI_KV_FUS>(a, B, st)));
+      TRY((run_linear<128, 128, PRO_LN, EPI_KV_FUS>(a, B, st, CAT_KVFUS)));
     }
   }
   {
     AttnArgs a{};
     a.q_t = w.qf; a.k_t = w.kf; a.vt_t = w.vtf; a.out = w.of;
     a.Lq = Lq; a.Lk = Lk; a.q_tiles = cdiv(Lq, 128); a.k_tiles = cdiv(Lk, 128);
+    ProfScope ps(CAT_ATTN_FUS, st);
     cudaError_t e = launch_attn<64, false>(a, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "attn_tc<64> launch");
@@ -282,22 +313,23 @@ int run_fusion(const FusionW& f, Work& w, const float* xq, const float* ctxk, in
   {  // to_out + bias + residual
     LinArgs a = lin(w.of, Lq, f.wo, f.bo);
     a.residual = resid0; a.out = w.x1;
-    TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st)));
+    TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st, CAT_OUT64)));
   }
   {  // LN -> Linear(128,1024) -> GEGLU => tiled activation image
     LinArgs a = lin(w.x1, Lq, f.w1, f.b1);
     a.ln_g = f.lnf_g; a.ln_b = f.lnf_b; a.out = w.g_t;
-    TRY((run_linear<128, 1024, PRO_LN, EPI_GEGLU_TILED>(a, B, st)));
+    TRY((run_linear<128, 1024, PRO_LN, EPI_GEGLU_TILED>(a, B, st, CAT_FFN1)));
   }
   {  // Linear(512,128) + bias + residual
     LinArgs a = lin(w.g_t, Lq, f.w2, f.b2);
     a.residual = w.x1; a.out = out;
-    TRY((run_linear<512, 128, PRO_TILED, EPI_BIAS_RES>(a, B, st)));
+    TRY((run_linear<512, 128, PRO_TILED, EPI_BIAS_RES>(a, B, st, CAT_FFN2)));
   }
   return 0;
 }
 
 int run_prep(Work& w, const float* src, const float* tgt, int B, int N, cudaStream_t st) {
+  ProfScope ps(CAT_PREP, st);
   prep_points_kernel<<<B, 256, 0, st>>>(src, tgt, N, cdiv(N, 128) * 128, w.kpts, w.src4, w.tgt4);
   LAUNCHED();
   return 0;
@@ -308,12 +340,13 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
   {
     LinArgs a = lin(feat1, N, lw.qkv_w, lw.qkv_b);
     a.t0 = w.qs; a.t1 = w.ks; a.t2 = w.vts;
-    TRY((run_linear<128, 384, PRO_NONE, EPI_QKV_SC>(a, B, st)));
+    TRY((run_linear<128, 384, PRO_NONE, EPI_QKV_SC>(a, B, st, CAT_QKV)));
   }
   AttnArgs a{};
   a.q_t = w.qs; a.k_t = w.ks; a.vt_t = w.vts; a.kpts = w.kpts; a.out = msg;
   a.Lq = N; a.Lk = N; a.q_tiles = a.k_tiles = cdiv(N, 128);
   a.neg_inv_sigma2 = -1.0f / (ctx->sigma_spat * ctx->sigma_spat);
+  ProfScope ps(CAT_ATTN_SC, st);
   cudaError_t e = launch_attn<128, true>(a, B, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail_cuda(e, "attn_tc<128,SC> launch");
@@ -327,7 +360,7 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
   {
     LinArgs a = lin(feat_in, N, lw.pcn_w, lw.pcn_b);
     a.out = w.feat1;
-    TRY((run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
+    TRY((run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, B, st, CAT_PCN)));
   }
   TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st));
   {
@@ -344,7 +377,7 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
   {
     LinArgs a = lin(w.m2, N, lw.fc3_w, lw.fc3_b);
     a.residual = w.x2; a.out = feat_out;
-    TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st)));
+    TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st, CAT_OUT64)));
   }
   return 0;
 }
@@ -355,6 +388,7 @@ int run_classify(const gmf_ctx* ctx, const float* feat, long long rows, float* n
     CU(cudaFuncSetAttribute(classify_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClsSmem));
     configured = true;
   }
+  ProfScope ps(CAT_CLASSIFY, st);
   classify_normalize_kernel<<<(unsigned)((rows + 63) / 64), 256, kClsSmem, st>>>(feat, rows, ctx->cls, normed, conf);
   LAUNCHED();
   return 0;
@@ -364,6 +398,7 @@ int run_pick_seeds(const gmf_ctx* ctx, Work& w, const float* conf, int B, int N,
   int np2 = 1;
   while (np2 < N) np2 <<= 1;
   if (np2 > 16384) return fail(GMF_ERR_INVALID, "pick_seeds supports N <= 16384");
+  ProfScope ps(CAT_SEEDS, st);
   nms_key_kernel<<<dim3(cdiv(N, 256), B), 256, 0, st>>>(w.src4, conf, N, ctx->cfg.nms_radius, use_nms, w.key);
   LAUNCHED();
   static bool configured = false;
@@ -384,6 +419,7 @@ int launch_knn(const float* normed, const int* seeds, int B, int N, int S, int k
     CU(cudaFuncSetAttribute(seed_knn_kernel<SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  ProfScope ps(CAT_KNN, st);
   seed_knn_kernel<SPC><<<dim3(cdiv(S, SPC), B), 256, smem, st>>>(normed, seeds, N, S, k, knn);
   LAUNCHED();
   return 0;
@@ -398,6 +434,7 @@ int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const 
   else if ((size_t)2 * (128 + N) * 4 <= budget) TRY(launch_knn<2>(normed, seeds, B, N, S, k, knn, st));
   else if ((size_t)(128 + N) * 4 <= budget) TRY(launch_knn<1>(normed, seeds, B, N, S, k, knn, st));
   else return fail(GMF_ERR_INVALID, "seed kNN supports N <= ~37000");
+  ProfScope ps(CAT_SPECTRAL, st);
   CU(cudaMemsetAsync(w.pair_mask, 0xff, (size_t)B * sizeof(unsigned), st));
   seed_spectral_kernel<0><<<dim3(S, B), 128, 0, st>>>(normed, src, tgt, knn, N, S, k, ctx->sigma, ctx->sigma_spat,
                                                      ctx->cfg.num_iterations, w.pair_mask, nullptr, nullptr);
@@ -410,6 +447,7 @@ int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const 
 
 int run_score(const gmf_ctx* ctx, Work& w, const float* seed_trans, int B, int N, int S, int refine, float* final_trans, float* labels,
               int* counts, int* best, float* pre_refine, cudaStream_t st) {
+  ProfScope ps(CAT_SCORE, st);
   CU(cudaMemsetAsync(counts, 0, (size_t)B * S * sizeof(int), st));
   score_kernel<<<dim3(cdiv(S, kScoreSeeds), cdiv(N, 256 * kScorePPT), B), 256, 0, st>>>(w.src4, w.tgt4, seed_trans, N, S, ctx->cfg.inlier_threshold, counts);
   LAUNCHED();
@@ -426,6 +464,7 @@ int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, co
   const int S = num_seeds(ctx, N), k = eff_k(ctx, N);
   TRY(run_prep(w, src, tgt, B, N, st));
   {
+    ProfScope ps(CAT_PREP, st);
     const long long rows = (long long)B * N;
     layer0_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(corr, ctx->l0_w, ctx->l0_b, w.featA, rows, 6);
     LAUNCHED();
@@ -444,6 +483,7 @@ int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, co
 int require_loaded(const gmf_ctx* ctx) {
   if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
   if (!ctx->loaded) return fail(GMF_ERR_STATE, "weights not loaded (gmf_load_weights)");
+  g_prof = const_cast<Prof*>(&ctx->prof);
   return 0;
 }
 
@@ -478,6 +518,33 @@ int64_t gmf_launch_count(int reset) {
   const long long v = g_launches.load();
   if (reset) g_launches.store(0);
   return v;
+}
+
+int gmf_profile_enable(gmf_ctx* ctx, int enable) {
+  if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  ctx->prof.on = enable != 0;
+  ctx->prof.used = 0;
+  ctx->prof.cat.clear();
+  return 0;
+}
+
+int gmf_profile_read(gmf_ctx* ctx, int category, double* total_ms, int64_t* launches) {
+  if (!ctx || category < 0 || category >= CAT_COUNT) return fail(GMF_ERR_INVALID, "bad profile category");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  double ms = 0;
+  int64_t n = 0;
+  for (size_t i = 0; i < ctx->prof.cat.size(); ++i)
+    if (ctx->prof.cat[i] == category) {
+      float t = 0;
+      CU(cudaEventElapsedTime(&t, ctx->prof.ev[2 * i], ctx->prof.ev[2 * i + 1]));
+      ms += t; ++n;
+    }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  return 0;
 }
 
 int gmf_weight_count(int num_layers) { return (int)build_spec(num_layers).size(); }
@@ -516,6 +583,8 @@ void gmf_destroy(gmf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->blob) cudaFree(ctx->blob);
   if (ctx->stage) cudaFree(ctx->stage);
+  for (auto e : ctx->prof.ev) cudaEventDestroy(e);
+  if (g_prof == &ctx->prof) g_prof = nullptr;
   delete ctx;
 }
 

@@ -209,5 +209,21 @@ class Engine:
                                                 _ptr(out), _ptr(ws), nb, self._stream()))
         return out
 
+    PROFILE_CATEGORIES = ["pointcn", "qkv_proj", "fc_message_12", "fusion_q_proj", "fusion_kv_proj", "gemm_64_128", "ffn_geglu",
+                          "ffn_out", "attn_fusion", "attn_sc", "prep_layer0", "classify", "pick_seeds", "seed_knn",
+                          "spectral_kabsch", "score_refine"]
+
+    def profile(self, enable: bool):
+        _lib.check(self.lib.gmf_profile_enable(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> {category: (total_ms, launches)} since profile(True)."""
+        out = {}
+        for i, name in enumerate(self.PROFILE_CATEGORIES):
+            ms, n = C.c_double(), C.c_int64()
+            _lib.check(self.lib.gmf_profile_read(self.h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     def launch_count(self, reset=False) -> int:
         return int(self.lib.gmf_launch_count(1 if reset else 0))

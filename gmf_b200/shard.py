@@ -1,0 +1,28 @@
+"""Pair sharding across ranks: fragment pairs are independent, so each rank owns a contiguous slice of the
+batch and the only cross-rank step is the final host gather of [B,4,4] poses (+ labels).  No collective on the data path."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+
+
+def shard_range(num_pairs: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split: the first (num_pairs % world) ranks get one extra pair."""
+    base, rem = divmod(num_pairs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_poses(local_trans: torch.Tensor, num_pairs: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """Host gather of the per-rank [b,4,4] results into [num_pairs,4,4] on every rank (CPU tensors; gloo or nccl group)."""
+    import torch.distributed as dist
+    if world == 1:
+        return local_trans.cpu()
+    sizes = [shard_range(num_pairs, r, world) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    buf = torch.zeros(mx, 4, 4, dtype=torch.float32, device=local_trans.device)
+    buf[: local_trans.shape[0]] = local_trans
+    outs: List[torch.Tensor] = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)]).cpu()

@@ -114,6 +114,15 @@ int gmf_score_hypotheses(gmf_ctx* ctx, const float* seed_trans, const float* src
 int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* B, const float* weights, int M, int k, float* T, void* stream);
 
 /* ---- introspection / debugging ------------------------------------------------------------- */
+/* Per-launch CUDA-event timing (bench.py's roofline leg).  While enabled every kernel launch is bracketed by events on
+ * the launching stream; gmf_profile_read synchronises the device and returns the summed device time and launch count
+ * of one category since the last gmf_profile_enable call.  Categories: 0 PointCN GEMM, 1 QKV projection, 2 fc_message
+ * 128->64/64->64, 3 fusion Q projection, 4 fusion KV projection, 5 64->128 GEMMs (to_out, fc_message.6), 6 FFN GEGLU GEMM,
+ * 7 FFN output GEMM, 8 fusion flash attention, 9 SC-guided flash attention, 10 prep+layer0, 11 classifier, 12 seed
+ * picking, 13 seed kNN, 14 spectral+Kabsch, 15 scoring+refinement. */
+#define GMF_PROFILE_CATEGORIES 16
+int gmf_profile_enable(gmf_ctx* ctx, int enable);
+int gmf_profile_read(gmf_ctx* ctx, int category, double* total_ms, int64_t* launches);
 /* number of gmf kernels launched by this process since the last reset (bench.py's gpu_launches) */
 int64_t gmf_launch_count(int reset);
 /* out[rows,nout] = act(x[rows,k] . W[nout,k]^T + bias) (+ residual) through the tcgen05 TF32 linear kernel.
