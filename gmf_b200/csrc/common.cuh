@@ -90,6 +90,18 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                : "memory");
 }
 
+// One lane of a converged warp (the canonical way to issue tcgen05.mma / TMA from warp-uniform code: the compiler
+// predicates the async instruction instead of wrapping it in a per-lane serialisation loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B, 8-row group stride 1024 B (cute::UMMA::SmemDescriptor:
 // start>>4 @[0,14), LBO>>4 @[16,30), SBO>>4 @[32,46), version=1 @[46,48), layout=2 (SW128) @[61,64)).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_byte_addr) {
@@ -104,6 +116,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_byte_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int fmt) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// advance a descriptor's start address by a byte offset (multiple of 16; no carry out of the 14-bit field in our layouts)
+__device__ __forceinline__ uint64_t umma_desc_adv(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 constexpr int kFmtBF16 = 1;
 constexpr int kFmtTF32 = 2;
 
@@ -120,6 +134,43 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// Predicated single-lane variants for warp-converged role code: every lane executes the call, only the lane with
+// `on != 0` (from elect_one()) issues.  Keeping the call site convergent lets the compiler keep the descriptors in uniform
+// registers instead of emitting a per-lane serialisation loop around every UTCHMMA.
+__device__ __forceinline__ void tc_mma_bf16_p(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_p(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_p(uint64_t* bar, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_p(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint64_t* bar, uint32_t bytes, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes), "r"(on)
       : "memory");
 }
 

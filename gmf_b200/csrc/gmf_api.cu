@@ -192,7 +192,7 @@ struct gmf_ctx {
   FusionW f1;
   std::vector<LayerW> layers;
   ClsWeights cls{};
-  int chunk_pairs = 16;
+  int chunk_pairs = 64;
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;

@@ -51,7 +51,11 @@ struct LinCfg {
   static constexpr int A_TOTAL = (PRO == PRO_TILED) ? 2 * A_BYTES : 128 * K * 4;
   static constexpr int B_BYTES = NB * KCH * 4;
   static constexpr int NSTAGE = PASSES * NNB * NKC;
-  static constexpr int SMEM = 1024 + A_TOTAL + 2 * B_BYTES + 256;
+  // per-warp 32x32 fp32 transpose staging for coalesced row-major epilogue I/O: aliases the idle second weight buffer
+  // when the kernel streams a single weight chunk, else lives behind the barriers
+  static constexpr bool STG_ALIAS = (NSTAGE == 1) && (B_BYTES >= 32768);
+  static constexpr int STG_BYTES = 8 * 32 * 32 * 4;
+  static constexpr int SMEM = 1024 + A_TOTAL + 2 * B_BYTES + 256 + (STG_ALIAS ? 0 : STG_BYTES);
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -59,8 +63,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 template <int K, int NOUT, int PRO, int EPI>
 __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
   using Cfg = LinCfg<K, NOUT, PRO>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::A_TOTAL;
   uint64_t* bars = (uint64_t*)(sB + 2 * Cfg::B_BYTES);
@@ -70,6 +74,7 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
   uint64_t* acc_full = bars + 5;  // accumulators of a pass complete
   uint64_t* tmem_free = bars + 6; // workers drained TMEM of a pass
   uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  float* sStg = Cfg::STG_ALIAS ? (float*)(sB + Cfg::B_BYTES) : (float*)(sB + 2 * Cfg::B_BYTES + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, pair = blockIdx.y;
@@ -88,49 +93,48 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 8) {
-    // ------------------------------- control thread: TMA + MMA issue -------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, Cfg::NB, kFmtTF32);
-      const uint8_t* wsrc = (const uint8_t*)a.w_packed;
-      const uint8_t* asrc = (const uint8_t*)a.x + (size_t)(pair * a.tiles + tile) * (size_t)(Cfg::NKC * Cfg::A_BYTES);
-      auto issue_load = [&](int it) {
-        const int buf = it & 1;
-        if (PRO == PRO_TILED) {
-          mbar_expect_tx(&full[buf], Cfg::B_BYTES + Cfg::A_BYTES);
-          bulk_g2s(sA + buf * Cfg::A_BYTES, asrc + (size_t)(it % Cfg::NKC) * Cfg::A_BYTES, Cfg::A_BYTES, &full[buf]);
-        } else {
-          mbar_expect_tx(&full[buf], Cfg::B_BYTES);
-        }
-        bulk_g2s(sB + buf * Cfg::B_BYTES, wsrc + (size_t)it * Cfg::B_BYTES, Cfg::B_BYTES, &full[buf]);
-      };
-      issue_load(0);
-      for (int it = 0; it < Cfg::NSTAGE; ++it) {
-        const int buf = it & 1;
-        if (it + 1 < Cfg::NSTAGE) {
-          if (it >= 1) mbar_wait(&mma_done[(it + 1) & 1], ((it - 1) >> 1) & 1);
-          issue_load(it + 1);
-        }
-        const int pass = it / (Cfg::NNB * Cfg::NKC);
-        const int nbi = (it / Cfg::NKC) % Cfg::NNB;
-        const int kc = it % Cfg::NKC;
-        if (it == 0 && PRO != PRO_TILED) mbar_wait(a_ready, 0);
-        if (pass > 0 && nbi == 0 && kc == 0) mbar_wait(tmem_free, (pass - 1) & 1);
-        mbar_wait(&full[buf], (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(sA) + (PRO == PRO_TILED ? buf * Cfg::A_BYTES : 0);
-        const uint32_t b_base = smem_u32(sB) + buf * Cfg::B_BYTES;
-#pragma unroll
-        for (int at = 0; at < Cfg::KCH / 32; ++at) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = umma_desc_sw128(a_base + at * 16384 + ks * 32);
-            const uint64_t bd = umma_desc_sw128(b_base + at * (Cfg::NB * 128) + ks * 32);
-            tc_mma_tf32(tmem + nbi * Cfg::NB, ad, bd, idesc, (kc > 0 || at > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        tc_commit(&mma_done[buf]);
-        if (nbi == Cfg::NNB - 1 && kc == Cfg::NKC - 1) tc_commit(acc_full);
+    // ------------------------------- control warp (converged; one elected lane issues TMA + MMA) ---------------
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t idesc = umma_idesc(128, Cfg::NB, kFmtTF32);
+    const uint8_t* wsrc = (const uint8_t*)a.w_packed;
+    const uint8_t* asrc = (const uint8_t*)a.x + (size_t)(pair * a.tiles + tile) * (size_t)(Cfg::NKC * Cfg::A_BYTES);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
+    auto issue_load = [&](int it) {
+      const int buf = it & 1;
+      if (PRO == PRO_TILED) {
+        mbar_expect_tx_p(&full[buf], Cfg::B_BYTES + Cfg::A_BYTES, leader);
+        bulk_g2s_p(sA + buf * Cfg::A_BYTES, asrc + (size_t)(it % Cfg::NKC) * Cfg::A_BYTES, Cfg::A_BYTES, &full[buf], leader);
+      } else {
+        mbar_expect_tx_p(&full[buf], Cfg::B_BYTES, leader);
       }
+      bulk_g2s_p(sB + buf * Cfg::B_BYTES, wsrc + (size_t)it * Cfg::B_BYTES, Cfg::B_BYTES, &full[buf], leader);
+    };
+    issue_load(0);
+    for (int it = 0; it < Cfg::NSTAGE; ++it) {
+      const int buf = it & 1;
+      if (it + 1 < Cfg::NSTAGE) {
+        if (it >= 1) mbar_wait(&mma_done[(it + 1) & 1], ((it - 1) >> 1) & 1);
+        issue_load(it + 1);
+      }
+      const int pass = it / (Cfg::NNB * Cfg::NKC);
+      const int nbi = (it / Cfg::NKC) % Cfg::NNB;
+      const int kc = it % Cfg::NKC;
+      if (it == 0 && PRO != PRO_TILED) mbar_wait(a_ready, 0);
+      if (pass > 0 && nbi == 0 && kc == 0) mbar_wait(tmem_free, (pass - 1) & 1);
+      mbar_wait(&full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint64_t ad = umma_desc_adv(a_desc0, PRO == PRO_TILED ? buf * Cfg::A_BYTES : 0);
+      const uint64_t bd = umma_desc_adv(b_desc0, buf * Cfg::B_BYTES);
+#pragma unroll
+      for (int at = 0; at < Cfg::KCH / 32; ++at) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          tc_mma_tf32_p(tmem + nbi * Cfg::NB, umma_desc_adv(ad, at * 16384 + ks * 32), umma_desc_adv(bd, at * (Cfg::NB * 128) + ks * 32),
+                        idesc, (kc > 0 || at > 0 || ks > 0) ? 1u : 0u, leader);
+      }
+      tc_commit_p(&mma_done[buf], leader);
+      if (nbi == Cfg::NNB - 1 && kc == Cfg::NKC - 1) tc_commit_p(acc_full, leader);
     }
   } else {
     // ------------------------------- workers: A operand prologue -------------------------------
@@ -151,15 +155,26 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
           cb = *reinterpret_cast<const float4*>(a.cpe_b + c4);
         }
         const float* xp = a.x + (size_t)pair * a.L * K;
-        for (int r = warp; r < 128; r += 8) {
+        // warp w owns rows [16w, 16w+16): all global loads (plus the two CPE halo rows) are issued before any use so
+        // that 16-18 independent 512-byte row reads are in flight per warp
+        constexpr int RPW = 16;
+        const int rbase = warp * RPW;
+        float4 rv[RPW + 2];
+#pragma unroll
+        for (int i = 0; i < RPW + 2; ++i) {
+          const int gr = row0 + rbase + i - 1;
+          const bool want = (PRO == PRO_CPE_LN) ? true : (i >= 1 && i <= RPW);
+          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (want && gr >= 0 && gr < a.L) rv[i] = *reinterpret_cast<const float4*>(xp + (size_t)gr * K + c4);
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const int r = rbase + i;
           const int gr = row0 + r;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v = rv[i + 1];
           if (gr < a.L) {
-            v = *reinterpret_cast<const float4*>(xp + (size_t)gr * K + c4);
             if (PRO == PRO_CPE_LN) {
-              float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), nv = pv;
-              if (gr > 0) pv = *reinterpret_cast<const float4*>(xp + (size_t)(gr - 1) * K + c4);
-              if (gr + 1 < a.L) nv = *reinterpret_cast<const float4*>(xp + (size_t)(gr + 1) * K + c4);
+              const float4 pv = rv[i], nv = rv[i + 2];
               v.x += fmaf(w0.x, pv.x, fmaf(w1.x, v.x, fmaf(w2.x, nv.x, cb.x)));
               v.y += fmaf(w0.y, pv.y, fmaf(w1.y, v.y, fmaf(w2.y, nv.y, cb.y)));
               v.z += fmaf(w0.z, pv.z, fmaf(w1.z, v.z, fmaf(w2.z, nv.z, cb.z)));
@@ -180,11 +195,17 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
       } else {  // K == 64: half a warp per row
         const float* xp = a.x + (size_t)pair * a.L * K;
         const int ch = lane & 15;
-        for (int r = warp * 2 + (lane >> 4); r < 128; r += 16) {
-          const int gr = row0 + r;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gr < a.L) v = *reinterpret_cast<const float4*>(xp + (size_t)gr * K + ch * 4);
-          *reinterpret_cast<float4*>(sA + (ch >> 3) * 16384 + swz_off(r, ch & 7)) = to_tf32(v);
+        float4 rv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int gr = row0 + warp * 16 + i * 2 + (lane >> 4);
+          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gr < a.L) rv[i] = *reinterpret_cast<const float4*>(xp + (size_t)gr * K + ch * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = warp * 16 + i * 2 + (lane >> 4);
+          *reinterpret_cast<float4*>(sA + (ch >> 3) * 16384 + swz_off(r, ch & 7)) = to_tf32(rv[i]);
         }
       }
       fence_proxy_async();
@@ -228,24 +249,50 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
           tmem_ld_wait();
           const int col0 = c * 32;
           if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RES || EPI == EPI_BIAS) {
-            if (valid) {
-              float* op = a.out + grow * NOUT + col0;
-              const float* rp = a.residual + grow * NOUT + col0;
+            // coalesced I/O through a per-warp XOR-swizzled 32x32 staging tile: global accesses touch 4 rows x 128 B per
+            // instruction instead of 32 rows x 16 B
+            float* stg = sStg + warp * 1024;
+            const int srow = lane >> 3, sj = lane & 7;
+            const size_t gbase = ((size_t)pair * a.L + row0 + q * 32) * NOUT + col0;
+            if (EPI == EPI_BIAS_RES) {
+              float4 rr[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bb = *reinterpret_cast<const float4*>(a.bias + col0 + 4 * j);
-                float4 o = make_float4(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y,
-                                       __uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
-                if (EPI == EPI_BIAS_RELU) {
-                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                }
-                if (EPI == EPI_BIAS_RES) {
-                  const float4 rr = *reinterpret_cast<const float4*>(rp + 4 * j);
-                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                }
-                *reinterpret_cast<float4*>(op + 4 * j) = o;
+              for (int i = 0; i < 8; ++i) {
+                const int rw = i * 4 + srow;
+                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + q * 32 + rw < a.L) rr[i] = *reinterpret_cast<const float4*>(a.residual + gbase + (size_t)rw * NOUT + sj * 4);
               }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rw = i * 4 + srow;
+                *reinterpret_cast<float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2)) = rr[i];
+              }
+              __syncwarp();
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = *reinterpret_cast<const float4*>(a.bias + col0 + 4 * j);
+              float4 o = make_float4(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y,
+                                     __uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+              if (EPI == EPI_BIAS_RELU) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              }
+              float4* slot = reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2));
+              if (EPI == EPI_BIAS_RES) {
+                const float4 rr = *slot;
+                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              }
+              *slot = o;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rw = i * 4 + srow;
+              if (row0 + q * 32 + rw < a.L)
+                *reinterpret_cast<float4*>(a.out + gbase + (size_t)rw * NOUT + sj * 4) =
+                    *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
+            }
+            __syncwarp();
           } else {
             // bf16 tile emission for the attention kernels
             int which, dcol0;   // which: 0 = Q-like (row-major tile), 1 = K-like, 2 = V (transposed tile)
