@@ -208,7 +208,7 @@ struct Work {
   float *kpts; float4 *src4, *tgt4;
   float *imgfeat, *featA, *feat1, *x0, *x1, *x2, *of, *g_t, *msg, *m1, *m2;
   __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts;
-  float *normed, *conf, *key, *seed_w, *seed_trans, *pre_refine;
+  float *normed, *conf, *key, *seed_w, *seed_trans, *pre_refine, *dist, *seedM;
   int *seeds, *knn, *counts, *best;
   unsigned* pair_mask;
 };
@@ -242,6 +242,8 @@ size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k) {
   w.normed = b.take<float>((size_t)B * N * 128); w.conf = b.take<float>((size_t)B * N); w.key = b.take<float>((size_t)B * N);
   w.seed_w = b.take<float>((size_t)B * S * k); w.seed_trans = b.take<float>((size_t)B * S * 16);
   w.pre_refine = b.take<float>((size_t)B * 16);
+  w.dist = b.take<float>((size_t)B * S * N);
+  w.seedM = b.take<float>((size_t)B * S * 1600);
   w.seeds = b.take<int>((size_t)B * S); w.knn = b.take<int>((size_t)B * S * k); w.counts = b.take<int>((size_t)B * S);
   w.best = b.take<int>(B); w.pair_mask = b.take<unsigned>(B);
   return b.off + 1024;
@@ -412,15 +414,14 @@ int run_pick_seeds(const gmf_ctx* ctx, Work& w, const float* conf, int B, int N,
 }
 
 template <int SPC>
-int launch_knn(const float* normed, const int* seeds, int B, int N, int S, int k, int* knn, cudaStream_t st) {
-  const size_t smem = (size_t)(64 * 132 + SPC * 128 + (size_t)SPC * N) * 4;
+int launch_select(const float* dist, int B, int N, int S, int k, int* knn, cudaStream_t st) {
+  const size_t smem = (size_t)SPC * N * 4;
   static size_t configured = 0;
   if (smem > configured) {
-    CU(cudaFuncSetAttribute(seed_knn_kernel<SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(seed_select_kernel<SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  ProfScope ps(CAT_KNN, st);
-  seed_knn_kernel<SPC><<<dim3(cdiv(S, SPC), B), 256, smem, st>>>(normed, seeds, N, S, k, knn);
+  seed_select_kernel<SPC><<<dim3(cdiv(S, SPC), B), SPC * 32, smem, st>>>(dist, N, S, k, knn);
   LAUNCHED();
   return 0;
 }
@@ -428,19 +429,24 @@ int launch_knn(const float* normed, const int* seeds, int B, int N, int S, int k
 int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const float* src, const float* tgt, const int* seeds, int B,
                         int N, int S, int k, int* knn, float* seed_w, float* seed_trans, cudaStream_t st) {
   if (k < 1 || k > 40) return fail(GMF_ERR_INVALID, "k must be in [1, 40]");
-  const size_t budget = 180 * 1024 - 64 * 132 * 4;
-  if ((size_t)8 * (128 + N) * 4 <= budget) TRY(launch_knn<8>(normed, seeds, B, N, S, k, knn, st));
-  else if ((size_t)4 * (128 + N) * 4 <= budget) TRY(launch_knn<4>(normed, seeds, B, N, S, k, knn, st));
-  else if ((size_t)2 * (128 + N) * 4 <= budget) TRY(launch_knn<2>(normed, seeds, B, N, S, k, knn, st));
-  else if ((size_t)(128 + N) * 4 <= budget) TRY(launch_knn<1>(normed, seeds, B, N, S, k, knn, st));
-  else return fail(GMF_ERR_INVALID, "seed kNN supports N <= ~37000");
+  {
+    ProfScope ps(CAT_KNN, st);
+    seed_dist_kernel<<<dim3(cdiv(N, 64), cdiv(S, 64), B), 256, 0, st>>>(normed, seeds, N, S, w.dist);
+    LAUNCHED();
+    const size_t budget = 200 * 1024;
+    if ((size_t)8 * N * 4 <= budget) TRY(launch_select<8>(w.dist, B, N, S, k, knn, st));
+    else if ((size_t)4 * N * 4 <= budget) TRY(launch_select<4>(w.dist, B, N, S, k, knn, st));
+    else if ((size_t)2 * N * 4 <= budget) TRY(launch_select<2>(w.dist, B, N, S, k, knn, st));
+    else if ((size_t)N * 4 <= budget) TRY(launch_select<1>(w.dist, B, N, S, k, knn, st));
+    else return fail(GMF_ERR_INVALID, "seed kNN supports N <= 51200");
+  }
   ProfScope ps(CAT_SPECTRAL, st);
   CU(cudaMemsetAsync(w.pair_mask, 0xff, (size_t)B * sizeof(unsigned), st));
   seed_spectral_kernel<0><<<dim3(S, B), 128, 0, st>>>(normed, src, tgt, knn, N, S, k, ctx->sigma, ctx->sigma_spat,
-                                                     ctx->cfg.num_iterations, w.pair_mask, nullptr, nullptr);
+                                                     ctx->cfg.num_iterations, w.pair_mask, nullptr, nullptr, w.seedM);
   LAUNCHED();
   seed_spectral_kernel<1><<<dim3(S, B), 128, 0, st>>>(normed, src, tgt, knn, N, S, k, ctx->sigma, ctx->sigma_spat,
-                                                     ctx->cfg.num_iterations, w.pair_mask, seed_w, seed_trans);
+                                                     ctx->cfg.num_iterations, w.pair_mask, seed_w, seed_trans, w.seedM);
   LAUNCHED();
   return 0;
 }

@@ -291,78 +291,90 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(const float* __restrict
 // seed kNN in feature space (common.py:53-75 restricted to the seed rows; PointDSC.py:325-329):
 // d_j = 2 - 2 <f_seed, f_j>, (k+1) smallest, rank 0 dropped.  Ties -> lower index first.
 // ------------------------------------------------------------------------------------------------
-template <int SPC>   // seeds per CTA
-__global__ void __launch_bounds__(256) seed_knn_kernel(const float* __restrict__ normed, const int* __restrict__ seeds, int N, int S,
-                                                       int k, int* __restrict__ knn_idx) {
-  extern __shared__ float sm[];
-  float* tile = sm;                       // [64][132]
-  float* sf = tile + 64 * 132;            // [SPC][128]
-  float* dist = sf + SPC * 128;           // [SPC][N]
-  const int pair = blockIdx.y, s0 = blockIdx.x * SPC, tid = threadIdx.x;
+// Kernel 1: D[seed][j] = 2 - 2 <f_seed, f_j> as a register-blocked fp32 SGEMM (64 seeds x 64 points per CTA, 4x4 per thread).
+__global__ void __launch_bounds__(256) seed_dist_kernel(const float* __restrict__ normed, const int* __restrict__ seeds, int N, int S,
+                                                        float* __restrict__ dist) {
+  __shared__ __align__(16) float As[16][68];
+  __shared__ __align__(16) float Bs[16][68];
+  __shared__ int sidx[64];
+  const int pair = blockIdx.z, m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, tid = threadIdx.x;
   const float* F = normed + (size_t)pair * N * 128;
-  for (int i = tid; i < SPC * 32; i += 256) {
-    const int s = i >> 5, c4 = (i & 31) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s0 + s < S) v = *reinterpret_cast<const float4*>(F + (size_t)seeds[(size_t)pair * S + s0 + s] * 128 + c4);
-    *reinterpret_cast<float4*>(sf + s * 128 + c4) = v;
-  }
-  constexpr int SPT = (SPC + 3) / 4;      // seeds per thread
-  const int p = tid & 63, sg = tid >> 6;
-  for (int j0 = 0; j0 < N; j0 += 64) {
-    __syncthreads();
-    for (int i = tid; i < 64 * 32; i += 256) {
-      const int r = i >> 5, c4 = (i & 31) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + r < N) v = *reinterpret_cast<const float4*>(F + (size_t)(j0 + r) * 128 + c4);
-      *reinterpret_cast<float4*>(tile + r * 132 + c4) = v;
-    }
-    __syncthreads();
-    float acc[SPT];
-#pragma unroll
-    for (int u = 0; u < SPT; ++u) acc[u] = 0.f;
-#pragma unroll 8
-    for (int c4 = 0; c4 < 128; c4 += 4) {
-      const float4 f = *reinterpret_cast<const float4*>(tile + p * 132 + c4);
-#pragma unroll
-      for (int u = 0; u < SPT; ++u) {
-        const int s = sg * SPT + u;
-        if (s < SPC) {
-          const float4 q = *reinterpret_cast<const float4*>(sf + s * 128 + c4);
-          acc[u] = fmaf(f.x, q.x, fmaf(f.y, q.y, fmaf(f.z, q.z, fmaf(f.w, q.w, acc[u]))));
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < SPT; ++u) {
-      const int s = sg * SPT + u;
-      if (s < SPC && j0 + p < N) dist[(size_t)s * N + j0 + p] = 2.0f - 2.0f * acc[u];
-    }
-  }
+  if (tid < 64) sidx[tid] = (m0 + tid < S) ? seeds[(size_t)pair * S + m0 + tid] : -1;
   __syncthreads();
-  // selection: warp w extracts the k+1 smallest of seed w by repeated (value, index) arg-min
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int s = warp; s < SPC; s += 8) {
-    if (s0 + s >= S) continue;
-    float* d = dist + (size_t)s * N;
-    for (int rnk = 0; rnk <= k; ++rnk) {
-      float bv = INFINITY;
-      int bi = 0x7fffffff;
-      for (int j = lane; j < N; j += 32) {
-        const float v = d[j];
-        if (v < bv) { bv = v; bi = j; }
-      }
+  const int lr = tid >> 2, lk = (tid & 3) * 4;            // loader: row within tile, k offset
+  const int arow = sidx[lr];
+  const int brow = (n0 + lr < N) ? n0 + lr : -1;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (lane == 0) {
-        if (bi < N) d[bi] = INFINITY;
-        if (rnk > 0) knn_idx[((size_t)pair * S + s0 + s) * k + rnk - 1] = bi < N ? bi : 0;
-      }
-      __syncwarp();
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+  if (arow >= 0) av = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + lk);
+  if (brow >= 0) bv = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + lk);
+  for (int k0 = 0; k0 < 128; k0 += 16) {
+    As[lk][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
+    Bs[lk][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
+    __syncthreads();
+    if (k0 + 16 < 128) {                                   // prefetch the next k-slab while computing this one
+      av = make_float4(0.f, 0.f, 0.f, 0.f); bv = av;
+      if (arow >= 0) av = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + k0 + 16 + lk);
+      if (brow >= 0) bv = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + k0 + 16 + lk);
     }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= S) continue;
+    float* d = dist + ((size_t)pair * S + m) * N + n0 + tx * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n0 + tx * 4 + j < N) d[j] = 2.0f - 2.0f * acc[i][j];
+  }
+}
+
+// Kernel 2: per seed, the (k+1) smallest distances in ascending order (ties -> lower index), rank 0 dropped.
+// One warp per seed; the seed's distance row lives in shared memory and is consumed by repeated (value, index) arg-min.
+template <int SPC>   // seeds (warps) per CTA
+__global__ void __launch_bounds__(SPC * 32) seed_select_kernel(const float* __restrict__ dist, int N, int S, int k, int* __restrict__ knn_idx) {
+  extern __shared__ float sm[];
+  const int pair = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * SPC + warp;
+  if (s >= S) return;
+  float* d = sm + (size_t)warp * N;
+  const float* src = dist + ((size_t)pair * S + s) * N;
+  for (int j = lane; j < N; j += 32) d[j] = src[j];
+  __syncwarp();
+  for (int rnk = 0; rnk <= k; ++rnk) {
+    float bv = INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < N; j += 32) {
+      const float v = d[j];
+      if (v < bv) { bv = v; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      if (bi < N) d[bi] = INFINITY;
+      if (rnk > 0) knn_idx[((size_t)pair * S + s) * k + rnk - 1] = bi < N ? bi : 0;
+    }
+    __syncwarp();
   }
 }
 
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(128) seed_spectral_kernel(const float* __restr
                                                             const float* __restrict__ tgt, const int* __restrict__ knn_idx, int N, int S,
                                                             int k, float sigma, float sigma_spat, int iters,
                                                             unsigned* __restrict__ pair_mask, float* __restrict__ seed_w,
-                                                            float* __restrict__ seed_trans) {
+                                                            float* __restrict__ seed_trans, float* __restrict__ seedM) {
   constexpr int KM = 40;
   __shared__ float kf[KM][129];
   __shared__ float ks[KM][3], kt[KM][3];
@@ -389,29 +401,47 @@ __global__ void __launch_bounds__(128) seed_spectral_kernel(const float* __restr
   const size_t sg = (size_t)pair * S + sidx;
   if (tid < k) idx[tid] = knn_idx[sg * k + tid];
   __syncthreads();
-  const float* F = normed + (size_t)pair * N * 128;
-  for (int r = warp; r < k; r += 4) {
-    const float4 f = *reinterpret_cast<const float4*>(F + (size_t)idx[r] * 128 + lane * 4);
-    kf[r][lane * 4] = f.x; kf[r][lane * 4 + 1] = f.y; kf[r][lane * 4 + 2] = f.z; kf[r][lane * 4 + 3] = f.w;
-  }
   if (tid < k * 3) {
     const int r = tid / 3, c = tid % 3;
     ks[r][c] = src[((size_t)pair * N + idx[r]) * 3 + c];
     kt[r][c] = tgt[((size_t)pair * N + idx[r]) * 3 + c];
   }
-  __syncthreads();
-  const float inv_s2 = 1.0f / (sigma * sigma), inv_d2 = 1.0f / (sigma_spat * sigma_spat);
-  for (int e = tid; e < k * k; e += 128) {
-    const int i = e / k, j = e % k;
-    float dot = 0.f;
+  float* Mg = seedM + sg * (KM * KM);                   // pass 0 publishes M, pass 1 reloads it (L2) instead of recomputing
+  if (PASS == 0) {
+    const float* F = normed + (size_t)pair * N * 128;
+    for (int r = warp; r < k; r += 4) {
+      const float4 f = *reinterpret_cast<const float4*>(F + (size_t)idx[r] * 128 + lane * 4);
+      kf[r][lane * 4] = f.x; kf[r][lane * 4 + 1] = f.y; kf[r][lane * 4 + 2] = f.z; kf[r][lane * 4 + 3] = f.w;
+    }
+    __syncthreads();
+    const float inv_s2 = 1.0f / (sigma * sigma), inv_d2 = 1.0f / (sigma_spat * sigma_spat);
+    const int kq = (k + 3) >> 2;                        // 1 x 4 register blocking: one kf[i] load feeds four dot products
+    for (int e = tid; e < k * kq; e += 128) {
+      const int i = e / kq, j0 = (e % kq) * 4;
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
+      const int j1 = min(j0 + 1, k - 1), j2 = min(j0 + 2, k - 1), j3 = min(j0 + 3, k - 1);
 #pragma unroll 8
-    for (int c = 0; c < 128; ++c) dot = fmaf(kf[i][c], kf[j][c], dot);
-    const float mf = fmaxf(1.0f - (1.0f - dot) * inv_s2, 0.f);                       // PointDSC.py:338
-    const float ax = ks[i][0] - ks[j][0], ay = ks[i][1] - ks[j][1], az = ks[i][2] - ks[j][2];
-    const float bx = kt[i][0] - kt[j][0], by = kt[i][1] - kt[j][1], bz = kt[i][2] - kt[j][2];
-    const float dd = sqrtf(ax * ax + ay * ay + az * az) - sqrtf(bx * bx + by * by + bz * bz);
-    const float ms = fmaxf(1.0f - dd * dd * inv_d2, 0.f);                            // :351
-    M[i][j] = (i == j) ? 0.f : mf * ms;                                              // :360-361
+      for (int c = 0; c < 128; ++c) {
+        const float a = kf[i][c];
+        dot[0] = fmaf(a, kf[j0][c], dot[0]); dot[1] = fmaf(a, kf[j1][c], dot[1]);
+        dot[2] = fmaf(a, kf[j2][c], dot[2]); dot[3] = fmaf(a, kf[j3][c], dot[3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        if (j >= k) break;
+        const float mf = fmaxf(1.0f - (1.0f - dot[u]) * inv_s2, 0.f);                   // PointDSC.py:338
+        const float ax = ks[i][0] - ks[j][0], ay = ks[i][1] - ks[j][1], az = ks[i][2] - ks[j][2];
+        const float bx = kt[i][0] - kt[j][0], by = kt[i][1] - kt[j][1], bz = kt[i][2] - kt[j][2];
+        const float dd = sqrtf(ax * ax + ay * ay + az * az) - sqrtf(bx * bx + by * by + bz * bz);
+        const float ms = fmaxf(1.0f - dd * dd * inv_d2, 0.f);                          // :351
+        const float m = (i == j) ? 0.f : mf * ms;                                      // :360-361
+        M[i][j] = m;
+        Mg[i * KM + j] = m;
+      }
+    }
+  } else {
+    for (int e = tid; e < k * k; e += 128) M[e / k][e % k] = Mg[(e / k) * KM + (e % k)];
   }
   if (tid < k) v[tid] = 1.0f;
   __syncthreads();
