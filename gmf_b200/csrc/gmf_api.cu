@@ -632,13 +632,11 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     o.wo = blob.push(pack_linear(vec(next("to_out.weight"), 128 * 64), 128, 64, 64, 128));
     o.bo = blob.push(next("to_out.bias"), 128);
     o.lfg = blob.push(next("1.norm.weight"), 128); o.lfb = blob.push(next("1.norm.bias"), 128);
-    std::vector<int> rowmap(1024);
-    for (int p = 0; p < 2; ++p)
-      for (int nbi = 0; nbi < 4; ++nbi) {
-        const int base = nbi < 2 ? (2 * p + nbi) * 128 : 512 + (2 * p + nbi - 2) * 128;
-        for (int n = 0; n < 128; ++n) rowmap[(p * 4 + nbi) * 128 + n] = base + n;
-      }
-    o.w1 = blob.push(pack_linear(vec(next("net.0.weight"), 1024 * 128), 1024, 128, 128, 128, &rowmap));
+    std::vector<int> rowmap(1024);      // TMEM column order: pass p = [value rows 128p.., gate rows 512+128p..]
+    for (int p = 0; p < 4; ++p)
+      for (int nbi = 0; nbi < 2; ++nbi)
+        for (int n = 0; n < 128; ++n) rowmap[(p * 2 + nbi) * 128 + n] = (nbi ? 512 : 0) + p * 128 + n;
+    o.w1 = blob.push(pack_linear(vec(next("net.0.weight"), 1024 * 128), 1024, 128, 64, 128, &rowmap));
     o.b1 = blob.push(next("net.0.bias"), 1024);
     o.w2 = blob.push(pack_linear(vec(next("net.2.weight"), 128 * 512), 128, 512, 64, 128));
     o.b2 = blob.push(next("net.2.bias"), 128);
@@ -694,7 +692,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
         for (int j = 0; j < 128 * 128; ++j) W[(size_t)q * 128 * 128 + j] = wq[j] * s;
         for (int j = 0; j < 128; ++j) b[q * 128 + j] = bq[j] * s;
       }
-      o.qw = blob.push(pack_linear(W, 384, 128, 128, 128)); o.qb = blob.push(b);
+      o.qw = blob.push(pack_linear(W, 384, 128, 64, 128)); o.qb = blob.push(b);
     }
     o.f2 = pack_fusion(true);
   }

@@ -40,25 +40,41 @@ struct LinArgs {
 
 template <int K, int NOUT, int PRO>
 struct LinCfg {
-  static constexpr int KCH = (PRO == PRO_TILED) ? 64 : K;
+  static constexpr bool STREAM = (PRO == PRO_TILED) || (NOUT > 128);   // weights arrive as a stream of chunks
+  static constexpr int KCH = STREAM ? 64 : K;                           // K extent of one weight chunk
   static constexpr int NKC = K / KCH;
-  static constexpr int NB = NOUT >= 128 ? 128 : NOUT;
-  static constexpr int PASSES = NOUT > 512 ? NOUT / 512 : 1;
+  static constexpr int NB = NOUT >= 128 ? 128 : NOUT;                   // MMA N = rows of one weight chunk
+  static constexpr int PASSES = NOUT > 512 ? NOUT / 256 : 1;       // GEGLU: 4 passes of (128 value | 128 gate) columns
   static constexpr int NNB = NOUT / NB / PASSES;
   static constexpr int PASS_COLS = NNB * NB;
-  static constexpr int TMEM_COLS = PASS_COLS <= 32 ? 32 : PASS_COLS <= 64 ? 64 : PASS_COLS <= 128 ? 128 : PASS_COLS <= 256 ? 256 : 512;
+  static constexpr int TBUF = (PASSES > 1 && 2 * PASS_COLS <= 512) ? 2 : 1;   // double-buffered accumulators: MMAs of pass p+1
+  static constexpr int TCOLS_RAW = TBUF * PASS_COLS;                          // overlap the epilogue of pass p
+  static constexpr int TMEM_COLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
+  static constexpr int NBUF = STREAM ? (PRO == PRO_TILED ? 3 : 4) : 2;  // weight ring depth (TMA latency > one chunk of MMAs)
   static constexpr int A_BYTES = 128 * KCH * 4;            // per k-chunk
-  static constexpr int A_TOTAL = (PRO == PRO_TILED) ? 2 * A_BYTES : 128 * K * 4;
+  static constexpr int A_TOTAL = (PRO == PRO_TILED) ? NBUF * A_BYTES : 128 * K * 4;
   static constexpr int B_BYTES = NB * KCH * 4;
   static constexpr int NSTAGE = PASSES * NNB * NKC;
   // per-warp 32x32 fp32 transpose staging for coalesced row-major epilogue I/O: aliases the idle second weight buffer
   // when the kernel streams a single weight chunk, else lives behind the barriers
   static constexpr bool STG_ALIAS = (NSTAGE == 1) && (B_BYTES >= 32768);
   static constexpr int STG_BYTES = 8 * 32 * 32 * 4;
-  static constexpr int SMEM = 1024 + A_TOTAL + 2 * B_BYTES + 256 + (STG_ALIAS ? 0 : STG_BYTES);
+  static constexpr int SMEM = 1024 + A_TOTAL + NBUF * B_BYTES + 256 + (STG_ALIAS ? 0 : STG_BYTES);
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one RCP + one EX2 + 7 FMA instead of erff's
+// ~30-instruction branchy polynomial.  F.gelu default in the reference (fusion_layer.py:57).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // MUFU.RCP (1 ulp) instead of IEEE refinement
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * ex2_approx(-z * z * 1.4426950408889634f);   // erf(|x|/sqrt2)
+  return 0.5f * x + 0.5f * fabsf(x) * e;                                     // x/2 (1 + sign(x) erf)
+}
 
 template <int K, int NOUT, int PRO, int EPI>
 __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
@@ -67,23 +83,23 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::A_TOTAL;
-  uint64_t* bars = (uint64_t*)(sB + 2 * Cfg::B_BYTES);
-  uint64_t* full = bars;          // [2] weights (+A chunk) landed
-  uint64_t* mma_done = bars + 2;  // [2] MMAs that read stage buffers retired
-  uint64_t* a_ready = bars + 4;   // workers finished the A operand
-  uint64_t* acc_full = bars + 5;  // accumulators of a pass complete
-  uint64_t* tmem_free = bars + 6; // workers drained TMEM of a pass
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
-  float* sStg = Cfg::STG_ALIAS ? (float*)(sB + Cfg::B_BYTES) : (float*)(sB + 2 * Cfg::B_BYTES + 256);
+  uint64_t* bars = (uint64_t*)(sB + Cfg::NBUF * Cfg::B_BYTES);
+  uint64_t* full = bars;          // [4] weights (+A chunk) landed
+  uint64_t* mma_done = bars + 4;  // [4] MMAs that read stage buffers retired
+  uint64_t* a_ready = bars + 8;   // workers finished the A operand
+  uint64_t* acc_full = bars + 9;  // [2] accumulators of a pass complete (per TMEM buffer)
+  uint64_t* tmem_free = bars + 11; // [2] workers drained the TMEM buffer of a pass
+  uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+  float* sStg = Cfg::STG_ALIAS ? (float*)(sB + Cfg::B_BYTES) : (float*)(sB + Cfg::NBUF * Cfg::B_BYTES + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, pair = blockIdx.y;
   const int row0 = tile * 128;
 
   if (tid == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
-    mbar_init(a_ready, 256); mbar_init(acc_full, 1); mbar_init(tmem_free, 256);
+    for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&mma_done[i], 1); }
+    mbar_init(a_ready, 256);
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1); mbar_init(&tmem_free[0], 256); mbar_init(&tmem_free[1], 256);
     fence_mbar_init();
   }
   if (warp == 8) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -101,7 +117,7 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
     const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
     const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
     auto issue_load = [&](int it) {
-      const int buf = it & 1;
+      const int buf = it % Cfg::NBUF;
       if (PRO == PRO_TILED) {
         mbar_expect_tx_p(&full[buf], Cfg::B_BYTES + Cfg::A_BYTES, leader);
         bulk_g2s_p(sA + buf * Cfg::A_BYTES, asrc + (size_t)(it % Cfg::NKC) * Cfg::A_BYTES, Cfg::A_BYTES, &full[buf], leader);
@@ -110,31 +126,35 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
       }
       bulk_g2s_p(sB + buf * Cfg::B_BYTES, wsrc + (size_t)it * Cfg::B_BYTES, Cfg::B_BYTES, &full[buf], leader);
     };
-    issue_load(0);
+#pragma unroll 1
+    for (int it = 0; it < Cfg::NBUF - 1 && it < Cfg::NSTAGE; ++it) issue_load(it);
+#pragma unroll 1
     for (int it = 0; it < Cfg::NSTAGE; ++it) {
-      const int buf = it & 1;
-      if (it + 1 < Cfg::NSTAGE) {
-        if (it >= 1) mbar_wait(&mma_done[(it + 1) & 1], ((it - 1) >> 1) & 1);
-        issue_load(it + 1);
+      const int buf = it % Cfg::NBUF;
+      const int nxt = it + Cfg::NBUF - 1;                  // keep NBUF-1 chunks in flight
+      if (nxt < Cfg::NSTAGE) {
+        if (it >= 1) mbar_wait(&mma_done[nxt % Cfg::NBUF], ((it - 1) / Cfg::NBUF) & 1);   // MMAs of stage it-1 freed that buffer
+        issue_load(nxt);
       }
       const int pass = it / (Cfg::NNB * Cfg::NKC);
       const int nbi = (it / Cfg::NKC) % Cfg::NNB;
       const int kc = it % Cfg::NKC;
       if (it == 0 && PRO != PRO_TILED) mbar_wait(a_ready, 0);
-      if (pass > 0 && nbi == 0 && kc == 0) mbar_wait(tmem_free, (pass - 1) & 1);
-      mbar_wait(&full[buf], (it >> 1) & 1);
+      const int tb = pass % Cfg::TBUF;
+      if (pass >= Cfg::TBUF && nbi == 0 && kc == 0) mbar_wait(&tmem_free[tb], ((pass / Cfg::TBUF) - 1) & 1);
+      mbar_wait(&full[buf], (it / Cfg::NBUF) & 1);
       tc_fence_after();
-      const uint64_t ad = umma_desc_adv(a_desc0, PRO == PRO_TILED ? buf * Cfg::A_BYTES : 0);
+      const uint64_t ad = umma_desc_adv(a_desc0, PRO == PRO_TILED ? buf * Cfg::A_BYTES : kc * (Cfg::KCH / 32) * 16384);
       const uint64_t bd = umma_desc_adv(b_desc0, buf * Cfg::B_BYTES);
 #pragma unroll
       for (int at = 0; at < Cfg::KCH / 32; ++at) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          tc_mma_tf32_p(tmem + nbi * Cfg::NB, umma_desc_adv(ad, at * 16384 + ks * 32), umma_desc_adv(bd, at * (Cfg::NB * 128) + ks * 32),
+          tc_mma_tf32_p(tmem + tb * Cfg::PASS_COLS + nbi * Cfg::NB, umma_desc_adv(ad, at * 16384 + ks * 32), umma_desc_adv(bd, at * (Cfg::NB * 128) + ks * 32),
                         idesc, (kc > 0 || at > 0 || ks > 0) ? 1u : 0u, leader);
       }
       tc_commit_p(&mma_done[buf], leader);
-      if (nbi == Cfg::NNB - 1 && kc == Cfg::NKC - 1) tc_commit_p(acc_full, leader);
+      if (nbi == Cfg::NNB - 1 && kc == Cfg::NKC - 1) tc_commit_p(&acc_full[tb], leader);
     }
   } else {
     // ------------------------------- workers: A operand prologue -------------------------------
@@ -221,29 +241,50 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
     const size_t grow = (size_t)pair * a.L + gr;
 #pragma unroll 1
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-      mbar_wait(acc_full, pass & 1);
+      const int tb = pass % Cfg::TBUF;
+      const uint32_t tbase = trow + tb * Cfg::PASS_COLS;
+      mbar_wait(&acc_full[tb], (pass / Cfg::TBUF) & 1);
       tc_fence_after();
-      constexpr int NCHUNK = (EPI == EPI_GEGLU_TILED) ? 8 : Cfg::PASS_COLS / 32;
+      constexpr int NCHUNK = (EPI == EPI_GEGLU_TILED) ? 4 : Cfg::PASS_COLS / 32;
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
         uint32_t v[32];
-        tmem_ld32(trow + c * 32, v);
+        tmem_ld32(tbase + c * 32, v);
         if (EPI == EPI_GEGLU_TILED) {
           uint32_t gt[32];
-          tmem_ld32(trow + 256 + c * 32, gt);
+          tmem_ld32(tbase + 128 + c * 32, gt);
           tmem_ld_wait();
-          const int oc0 = pass * 256 + c * 32;       // output (value) column
-          const float* bv = a.bias + oc0;
-          const float* bg = a.bias + 512 + oc0;
+          const int oc0 = pass * 128 + c * 32;       // output (value) column
+          const float4* bv = reinterpret_cast<const float4*>(a.bias + oc0);
+          const float4* bg = reinterpret_cast<const float4*>(a.bias + 512 + oc0);
           float o[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = (__uint_as_float(v[i]) + __ldg(bv + i)) * gelu_erf(__uint_as_float(gt[i]) + __ldg(bg + i));
-          // tiled image for the next GEMM (K=512 in 8 chunks of 64 = 2 atoms of 32 floats)
-          uint8_t* dst = (uint8_t*)a.out + ((size_t)(pair * a.tiles + tile) * 8 + (oc0 >> 6)) * 32768 + ((oc0 >> 5) & 1) * 16384;
-          if (valid) {
+          for (int i = 0; i < 8; ++i) {
+            const float4 b1 = __ldg(bv + i), b2 = __ldg(bg + i);
+            o[4 * i] = (__uint_as_float(v[4 * i]) + b1.x) * gelu_erf(__uint_as_float(gt[4 * i]) + b2.x);
+            o[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + b1.y) * gelu_erf(__uint_as_float(gt[4 * i + 1]) + b2.y);
+            o[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + b1.z) * gelu_erf(__uint_as_float(gt[4 * i + 2]) + b2.z);
+            o[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + b1.w) * gelu_erf(__uint_as_float(gt[4 * i + 3]) + b2.w);
+          }
+          // tiled image for the next GEMM (K=512 in 8 chunks of 64 floats = 2 swizzle atoms): the 32 KB chunk image is
+          // assembled in shared memory by all 8 warps (round 0: chunks c=0,1 -> k-chunk 2*pass, round 1: c=2,3 -> 2*pass+1)
+          // and leaves as ONE bulk-async store; the wait for the previous store's smem read overlaps the GELU math above.
+          if (tid == 0) bulk_wait_read();                            // the previous chunk image has left shared memory
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          {
+            uint8_t* dst = (uint8_t*)sStg + (c & 1) * 16384;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(dst + swz_off(r, j)) = to_tf32(make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+            for (int j = 0; j < 8; ++j) {
+              float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (valid) ov = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);   // tensor core truncates to tf32
+              *reinterpret_cast<float4*>(dst + swz_off(r, j)) = ov;
+            }
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 256;" ::: "memory");             // image complete
+          if (tid == 0) {
+            bulk_s2g((uint8_t*)a.out + ((size_t)(pair * a.tiles + tile) * 8 + (oc0 >> 6)) * 32768, sStg, 32768);
+            bulk_commit();                                           // drained lazily: overlaps the next chunk's GELU math
           }
         } else {
           tmem_ld_wait();
@@ -300,14 +341,22 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
             if (EPI == EPI_QKV_SC) { which = col0 >> 7; dcol0 = col0 & 127; drows = 128; }
             else if (EPI == EPI_Q_FUS) { which = 0; dcol0 = col0; drows = 64; }
             else { which = 1 + (col0 >> 6); dcol0 = col0 & 63; drows = 64; }
-            const float* bp = a.bias + col0;
             float o[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = valid ? __uint_as_float(v[i]) + (a.bias ? __ldg(bp + i) : 0.f) : 0.f;
-            const size_t tile_elems = (size_t)128 * drows;
+            for (int i = 0; i < 8; ++i) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (a.bias) b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col0) + i);
+              o[4 * i] = valid ? __uint_as_float(v[4 * i]) + b4.x : 0.f;
+              o[4 * i + 1] = valid ? __uint_as_float(v[4 * i + 1]) + b4.y : 0.f;
+              o[4 * i + 2] = valid ? __uint_as_float(v[4 * i + 2]) + b4.z : 0.f;
+              o[4 * i + 3] = valid ? __uint_as_float(v[4 * i + 3]) + b4.w : 0.f;
+            }
+            // the bf16 tile images are assembled in shared memory (the weight ring is dead once acc_full fired) and leave
+            // the SM as one bulk-async store per image instead of scattered 2..16-byte global stores
+            const uint32_t img_bytes = 128u * drows * 2u;
+            uint8_t* img = sB + which * img_bytes;
             if (which < 2) {
-              __nv_bfloat16* base = (which == 0 ? a.t0 : a.t1) + (size_t)(pair * a.tiles + tile) * tile_elems;
-              uint8_t* dst = (uint8_t*)base + (dcol0 >> 6) * 16384;
+              uint8_t* dst = img + (dcol0 >> 6) * 16384;
               const int cc0 = (dcol0 & 63) >> 3;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -317,8 +366,7 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
                 *reinterpret_cast<uint4*>(dst + swz_off(r, cc0 + j)) = pk;
               }
             } else {
-              __nv_bfloat16* base = a.t2 + (size_t)(pair * a.tiles + tile) * tile_elems;
-              uint8_t* dst = (uint8_t*)base + (r >> 6) * (drows * 128) + (r & 7) * 2;
+              uint8_t* dst = img + (r >> 6) * (drows * 128) + (r & 7) * 2;
               const int kchunk = (r & 63) >> 3;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
@@ -329,10 +377,26 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
           }
         }
       }
+      if (EPI == EPI_QKV_SC || EPI == EPI_Q_FUS || EPI == EPI_KV_FUS) {
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");                 // all 8 worker warps finished their image parts
+        if (tid == 0) {
+          const uint32_t drows = (EPI == EPI_QKV_SC) ? 128u : 64u;
+          const uint32_t img_bytes = 128u * drows * 2u;
+          const size_t tix = (size_t)(pair * a.tiles + tile) * (128 * drows);
+          if (EPI == EPI_QKV_SC || EPI == EPI_Q_FUS) bulk_s2g(a.t0 + tix, sB, img_bytes);
+          if (EPI == EPI_QKV_SC || EPI == EPI_KV_FUS) {
+            bulk_s2g(a.t1 + tix, sB + img_bytes, img_bytes);
+            bulk_s2g(a.t2 + tix, sB + 2 * img_bytes, img_bytes);
+          }
+          bulk_commit_wait_read();
+        }
+      }
       tc_fence_before();
-      mbar_arrive(tmem_free);
+      mbar_arrive(&tmem_free[tb]);
     }
   }
+  if (EPI == EPI_GEGLU_TILED && tid == 0) bulk_wait_read();         // last chunk image must leave smem before exit
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, Cfg::TMEM_COLS);
