@@ -11,6 +11,7 @@
 
 #include "attn_tc.cuh"
 #include "linear_tc.cuh"
+#include "sc_attn_tc.cuh"
 #include "tail.cuh"
 
 using namespace gmf;
@@ -193,6 +194,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
+  int sc_impl = 1;          // 1: distances on the tensor pipe (sc_attn_tc.cuh); 0: SIMT distances (attn_tc.cuh)
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
@@ -207,7 +209,7 @@ namespace {
 struct Work {
   float *kpts; float4 *src4, *tgt4;
   float *imgfeat, *featA, *feat1, *x0, *x1, *x2, *of, *g_t, *msg, *m1, *m2;
-  __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts;
+  __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts, *aq, *bd;
   float *normed, *conf, *key, *seed_w, *seed_trans, *pre_refine, *dist, *seedM;
   int *seeds, *knn, *counts, *best;
   unsigned* pair_mask;
@@ -239,6 +241,7 @@ size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k) {
   w.kf = b.take<__nv_bfloat16>(B * tm * 128 * 64); w.vtf = b.take<__nv_bfloat16>(B * tm * 128 * 64);
   w.qs = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128);
   w.ks = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128); w.vts = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128);
+  w.aq = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 64); w.bd = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 64);
   w.normed = b.take<float>((size_t)B * N * 128); w.conf = b.take<float>((size_t)B * N); w.key = b.take<float>((size_t)B * N);
   w.seed_w = b.take<float>((size_t)B * S * k); w.seed_trans = b.take<float>((size_t)B * S * 16);
   w.pre_refine = b.take<float>((size_t)B * 16);
@@ -332,7 +335,10 @@ int run_fusion(const FusionW& f, Work& w, const float* xq, const float* ctxk, in
 
 int run_prep(Work& w, const float* src, const float* tgt, int B, int N, cudaStream_t st) {
   ProfScope ps(CAT_PREP, st);
-  prep_points_kernel<<<B, 256, 0, st>>>(src, tgt, N, cdiv(N, 128) * 128, w.kpts, w.src4, w.tgt4);
+  const int Np = cdiv(N, 128) * 128;
+  prep_points_kernel<<<B, 256, 0, st>>>(src, tgt, N, Np, w.kpts, w.src4, w.tgt4);
+  LAUNCHED();
+  dist_feature_kernel<<<dim3(Np / 128, B), 128, 0, st>>>(w.kpts, Np, w.aq, w.bd);
   LAUNCHED();
   return 0;
 }
@@ -343,6 +349,17 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
     LinArgs a = lin(feat1, N, lw.qkv_w, lw.qkv_b);
     a.t0 = w.qs; a.t1 = w.ks; a.t2 = w.vts;
     TRY((run_linear<128, 384, PRO_NONE, EPI_QKV_SC>(a, B, st, CAT_QKV)));
+  }
+  if (ctx->sc_impl == 1) {
+    ScAttnArgs sa{};
+    sa.q_t = w.qs; sa.k_t = w.ks; sa.vt_t = w.vts; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = msg;
+    sa.N = N; sa.tiles = cdiv(N, 128);
+    sa.neg_inv_sigma2 = -1.0f / (ctx->sigma_spat * ctx->sigma_spat);
+    ProfScope ps(CAT_ATTN_SC, st);
+    cudaError_t e = launch_sc_attn(sa, B, st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail_cuda(e, "sc_attn_tc launch");
+    return 0;
   }
   AttnArgs a{};
   a.q_t = w.qs; a.k_t = w.ks; a.vt_t = w.vts; a.kpts = w.kpts; a.out = msg;
@@ -580,6 +597,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   c->device = device;
   c->cfg = *cfg;
   if (const char* e = getenv("GMF_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, atoi(e));
+  if (const char* e = getenv("GMF_SC_IMPL")) c->sc_impl = atoi(e);
   *out = c;
   return 0;
 }
@@ -938,8 +956,15 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
   cudaError_t e;
   if (sc) {
     TRY(run_prep(w, src, tgt, B, Lk, st));
-    a.kpts = w.kpts; a.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
-    e = launch_attn<128, true>(a, B, st);
+    if (ctx->sc_impl == 1) {
+      ScAttnArgs sa{};
+      sa.q_t = Q; sa.k_t = K; sa.vt_t = V; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = out; sa.N = Lk; sa.tiles = kt;
+      sa.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
+      e = launch_sc_attn(sa, B, st);
+    } else {
+      a.kpts = w.kpts; a.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
+      e = launch_attn<128, true>(a, B, st);
+    }
   } else {
     e = launch_attn<64, false>(a, B, st);
   }

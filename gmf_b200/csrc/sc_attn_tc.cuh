@@ -1,0 +1,336 @@
+// Spatial-consistency guided non-local attention (PointDSC.py:56-64) with the pairwise squared distances ALSO on the tensor
+// pipe:   softmax_j( c_ij * q_i.k_j / sqrt(128) ) v_j,   c_ij = max(0, 1 - (|s_i-s_j| - |t_i-t_j|)^2 / sigma_d^2)   (PointDSC.py:216-221)
+//
+// |s_i - s_j|^2 = |s_i|^2 + |s_j|^2 - 2 s_i.s_j is bilinear in per-point feature vectors, so it is produced by a K=32 bf16 MMA
+// next to S = Q K^T.  fp32 coordinates are split into three bf16 terms (x = x0 + x1 + x2, 24 mantissa bits); the six
+// significant cross products per coordinate plus the split squared norms fill 24 of the 32 K slots, the accumulator is fp32,
+// so D2 carries the same ~1e-7 |s|^2 absolute error as the fp32 FMA expansion it replaces.  The softmax threads then read
+// S, D2S and D2T from TMEM and spend ~10 instructions per (i,j) instead of ~24, and no longer pull key points through the
+// shared-memory broadcast path (which was the co-limiter with the issue slots).  The N x N matrix never exists in HBM.
+//
+// CTA = one 128-query row tile; 64-key pipeline stages {K, V^T, Bd}; TMEM: S[2] | D2S[2] | D2T[2] | O (512 columns).
+//   warps 0-7   softmax: two threads per score row (32 columns each), lazy-rescale online softmax, bf16 P -> smem (2 buffers)
+//   warp 8      producer: bulk-async copies (TMA engine) into a 3-stage mbarrier ring
+//   warp 9      MMA issuer (converged, one elected lane): per key tile 8 (S) + 2 (D2S) + 2 (D2T) + 4 (PV) tcgen05.mma
+#pragma once
+#include "common.cuh"
+
+namespace gmf {
+
+struct ScAttnArgs {
+  const __nv_bfloat16* q_t;   // [pairs][tiles][128*128]   (scale * log2e folded into the projection)
+  const __nv_bfloat16* k_t;   // [pairs][tiles][128*128]
+  const __nv_bfloat16* vt_t;  // [pairs][tiles][128*128]   V^T tiles
+  const __nv_bfloat16* aq_t;  // [pairs][tiles][128*64]    query-side distance features (s-part | t-part)
+  const __nv_bfloat16* bd_t;  // [pairs][tiles][128*64]    key-side distance features
+  float* out;                 // [pairs][N][128] fp32
+  int N, tiles;
+  float neg_inv_sigma2;
+};
+
+struct ScCfg {
+  static constexpr int D = 128, BN = 64, NS = 3, PB = 2;
+  static constexpr int Q_BYTES = 128 * D * 2, AQ_BYTES = 128 * 64 * 2;
+  static constexpr int K_BYTES = BN * D * 2, V_BYTES = D * BN * 2, BD_BYTES = BN * 64 * 2;
+  static constexpr int STAGE_BYTES = K_BYTES + V_BYTES + BD_BYTES;
+  static constexpr int P_TILE = 128 * BN * 2;
+  static constexpr int XCH_BYTES = 3 * 2 * 128 * 4;
+  static constexpr int SMEM = 1024 + Q_BYTES + AQ_BYTES + NS * STAGE_BYTES + PB * P_TILE + XCH_BYTES + 512;
+  static constexpr int COL_S = 0, COL_DS = 128, COL_DT = 256, COL_O = 384;
+};
+
+__global__ void __launch_bounds__(320, 1) sc_attn_tc_kernel(const ScAttnArgs a) {
+  using Cfg = ScCfg;
+  constexpr int D = Cfg::D, BN = Cfg::BN, NS = Cfg::NS, PB = Cfg::PB, HC = BN / 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sAq = sQ + Cfg::Q_BYTES;
+  uint8_t* sStage = sAq + Cfg::AQ_BYTES;                 // [NS] x {K, V^T, Bd}
+  uint8_t* sP = sStage + NS * Cfg::STAGE_BYTES;          // [PB]
+  float* sX = (float*)(sP + PB * Cfg::P_TILE);           // [3][2][128]
+  uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;       // [NS]
+  uint64_t* kv_empty = kv_full + NS;  // [NS]
+  uint64_t* s_full = kv_empty + NS;   // [2]
+  uint64_t* s_free = s_full + 2;      // [2]
+  uint64_t* p_ready = s_free + 2;     // [PB]
+  uint64_t* pv_done = p_ready + PB;   // [PB]
+  uint32_t* tmem_slot = (uint32_t*)(pv_done + PB + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pair = blockIdx.y, qt = blockIdx.x;
+  const int nt = (a.N + BN - 1) / BN;
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 256); }
+    for (int i = 0; i < PB; ++i) { mbar_init(&p_ready[i], 256); mbar_init(&pv_done[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------ producer ------------------------------------
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const size_t tq = (size_t)pair * a.tiles + qt;
+    mbar_expect_tx_p(q_full, Cfg::Q_BYTES + Cfg::AQ_BYTES, leader);
+    bulk_g2s_p(sQ, a.q_t + tq * (128 * D), Cfg::Q_BYTES, q_full, leader);
+    bulk_g2s_p(sAq, a.aq_t + tq * (128 * 64), Cfg::AQ_BYTES, q_full, leader);
+    for (int j = 0; j < nt; ++j) {
+      const int st = j % NS;
+      if (j >= NS) mbar_wait(&kv_empty[st], ((j / NS) - 1) & 1);
+      uint8_t* dst = sStage + st * Cfg::STAGE_BYTES;
+      mbar_expect_tx_p(&kv_full[st], Cfg::STAGE_BYTES, leader);
+      const size_t tix = (size_t)pair * a.tiles + (j >> 1);        // 128-key tile, half h
+      const int h = j & 1;
+      const uint8_t* ksrc = (const uint8_t*)(a.k_t + tix * (128 * D)) + h * 8192;
+      bulk_g2s_p(dst, ksrc, 8192, &kv_full[st], leader);
+      bulk_g2s_p(dst + 8192, ksrc + 16384, 8192, &kv_full[st], leader);
+      bulk_g2s_p(dst + Cfg::K_BYTES, (const uint8_t*)(a.vt_t + tix * (128 * D)) + h * Cfg::V_BYTES, Cfg::V_BYTES, &kv_full[st], leader);
+      bulk_g2s_p(dst + Cfg::K_BYTES + Cfg::V_BYTES, (const uint8_t*)(a.bd_t + tix * (128 * 64)) + h * Cfg::BD_BYTES, Cfg::BD_BYTES,
+                 &kv_full[st], leader);
+    }
+  } else if (warp == 9) {
+    // ------------------------------------ MMA issuer ------------------------------------
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t idesc_s = umma_idesc(128, BN, kFmtBF16);
+    const uint32_t idesc_o = umma_idesc(128, D, kFmtBF16);
+    const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t aq_desc = umma_desc_sw128(smem_u32(sAq));
+    const uint64_t p_desc = umma_desc_sw128(smem_u32(sP));
+    const uint64_t st_desc = umma_desc_sw128(smem_u32(sStage));
+    auto issue_sd = [&](int j) {
+      const int st = j % NS, bb = j & 1;
+      mbar_wait(&kv_full[st], (j / NS) & 1);
+      if (j >= 2) mbar_wait(&s_free[bb], ((j >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint64_t kd = umma_desc_adv(st_desc, st * Cfg::STAGE_BYTES);
+      const uint64_t bd = umma_desc_adv(kd, Cfg::K_BYTES + Cfg::V_BYTES);
+#pragma unroll
+      for (int at = 0; at < 2; ++at)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          tc_mma_bf16_p(tmem + Cfg::COL_S + bb * BN, umma_desc_adv(q_desc, at * 16384 + ks * 32), umma_desc_adv(kd, at * 8192 + ks * 32),
+                        idesc_s, (at | ks) ? 1u : 0u, leader);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)        // source-cloud squared distances: K slots 0..31
+        tc_mma_bf16_p(tmem + Cfg::COL_DS + bb * BN, umma_desc_adv(aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), idesc_s, ks ? 1u : 0u, leader);
+#pragma unroll
+      for (int ks = 2; ks < 4; ++ks)        // target-cloud squared distances: K slots 32..63
+        tc_mma_bf16_p(tmem + Cfg::COL_DT + bb * BN, umma_desc_adv(aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), idesc_s, ks > 2 ? 1u : 0u, leader);
+      tc_commit_p(&s_full[bb], leader);
+    };
+    mbar_wait(q_full, 0);
+    for (int jj = 0; jj < 2 && jj < nt; ++jj) issue_sd(jj);
+    for (int j = 0; j < nt; ++j) {
+      const int st = j % NS, pb = j % PB;
+      mbar_wait(&p_ready[pb], (j / PB) & 1);
+      tc_fence_after();
+      const uint64_t pd = umma_desc_adv(p_desc, pb * Cfg::P_TILE);
+      const uint64_t vd = umma_desc_adv(st_desc, st * Cfg::STAGE_BYTES + Cfg::K_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        tc_mma_bf16_p(tmem + Cfg::COL_O, umma_desc_adv(pd, ks * 32), umma_desc_adv(vd, ks * 32), idesc_o, (j > 0 || ks > 0) ? 1u : 0u, leader);
+      tc_commit_p(&pv_done[pb], leader);
+      tc_commit_p(&kv_empty[st], leader);
+      if (j + 2 < nt) issue_sd(j + 2);
+    }
+  } else {
+    // ------------------------------------ softmax (two threads per query row) ------------------------------------
+    const int q = warp & 3, h = warp >> 2;
+    const int r = q * 32 + lane;
+    const int gq = qt * 128 + r;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + h * HC;
+    const int bar_id = 1 + q;
+    float m_ref = 0.f, l_sum = 0.f;
+    const float nis2 = a.neg_inv_sigma2;
+    for (int j = 0; j < nt; ++j) {
+      const int b = j & 1;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      float sv[HC];
+      {
+        uint32_t us[32], ua[32], ub[32];
+        tmem_ld32(trow + Cfg::COL_S + b * BN, us);
+        tmem_ld32(trow + Cfg::COL_DS + b * BN, ua);
+        tmem_ld32(trow + Cfg::COL_DT + b * BN, ub);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[b]);
+        // (|ds| - |dt|)^2 = ds^2 + dt^2 - 2 sqrt(ds^2 dt^2); |.| guards tiny negative d^2 from cancellation
+#pragma unroll
+        for (int c = 0; c < HC; ++c) {
+          const float d2s = __uint_as_float(ua[c]), d2t = __uint_as_float(ub[c]);
+          const float x = fmaf(-2.f, sqrt_approx(fabsf(d2s * d2t)), d2s + d2t);
+          const float cij = __saturatef(fmaf(x, nis2, 1.f));
+          sv[c] = fmaf(__uint_as_float(us[c]), cij, -m_ref);
+        }
+      }
+      float tmax = -INFINITY;
+      const int nvalid = a.N - j * BN - h * HC;
+      if (nvalid < HC) {
+#pragma unroll
+        for (int c = 0; c < HC; ++c)
+          if (c >= nvalid) sv[c] = -INFINITY;
+      }
+#pragma unroll
+      for (int c = 0; c < HC; ++c) tmax = fmaxf(tmax, sv[c]);
+      sX[(b * 2 + h) * 128 + r] = tmax;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      tmax = fmaxf(tmax, sX[(b * 2 + (h ^ 1)) * 128 + r]);
+      const bool need = (tmax > 8.f) || (j == 0 && tmax < -8.f);
+      float alpha = 1.f;
+      if (need) {
+        alpha = ex2_approx(-tmax);
+        m_ref += tmax;
+        l_sum *= alpha;
+      }
+      float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float sh = need ? tmax : 0.f;
+#pragma unroll
+        for (int c = 0; c < HC; c += 4) {
+          sv[c] = ex2_approx(sv[c] - sh); ps0 += sv[c];
+          sv[c + 1] = ex2_approx(sv[c + 1] - sh); ps1 += sv[c + 1];
+          sv[c + 2] = ex2_approx(sv[c + 2] - sh); ps2 += sv[c + 2];
+          sv[c + 3] = ex2_approx(sv[c + 3] - sh); ps3 += sv[c + 3];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < HC; c += 4) {
+          sv[c] = ex2_approx(sv[c]); ps0 += sv[c];
+          sv[c + 1] = ex2_approx(sv[c + 1]); ps1 += sv[c + 1];
+          sv[c + 2] = ex2_approx(sv[c + 2]); ps2 += sv[c + 2];
+          sv[c + 3] = ex2_approx(sv[c + 3]); ps3 += sv[c + 3];
+        }
+      }
+      l_sum += (ps0 + ps1) + (ps2 + ps3);
+      const int pb = j % PB;
+      uint8_t* myP = sP + pb * Cfg::P_TILE;
+      if (j >= PB) mbar_wait(&pv_done[pb], ((j / PB) - 1) & 1);
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        mbar_wait(&pv_done[(j - 1) % PB], ((j - 1) / PB) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t u[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_O + h * 64 + c * 32, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(__uint_as_float(u[i]) * alpha);
+          tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_O + h * 64 + c * 32, u);
+        }
+        tmem_st_wait();
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < HC / 8; ++c8) {
+        uint4 pk;
+        pk.x = pack_bf16(sv[8 * c8], sv[8 * c8 + 1]); pk.y = pack_bf16(sv[8 * c8 + 2], sv[8 * c8 + 3]);
+        pk.z = pack_bf16(sv[8 * c8 + 4], sv[8 * c8 + 5]); pk.w = pack_bf16(sv[8 * c8 + 6], sv[8 * c8 + 7]);
+        *reinterpret_cast<uint4*>(myP + swz_off(r, h * (HC / 8) + c8)) = pk;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&p_ready[pb]);
+    }
+    sX[(2 * 2 + h) * 128 + r] = l_sum;
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    l_sum += sX[(2 * 2 + (h ^ 1)) * 128 + r];
+    mbar_wait(&pv_done[(nt - 1) % PB], ((nt - 1) / PB) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_sum;
+    float* op = a.out + ((size_t)pair * a.N + gq) * D + h * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t u[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_O + h * 64 + c * 32, u);
+      tmem_ld_wait();
+      if (gq < a.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(op + c * 32 + 4 * i) =
+              make_float4(__uint_as_float(u[4 * i]) * inv, __uint_as_float(u[4 * i + 1]) * inv,
+                          __uint_as_float(u[4 * i + 2]) * inv, __uint_as_float(u[4 * i + 3]) * inv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+inline cudaError_t launch_sc_attn(const ScAttnArgs& a, int pairs, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ScCfg::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  sc_attn_tc_kernel<<<dim3(a.tiles, pairs), 320, ScCfg::SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// distance-feature tiles: per point, 64 bf16 = [s-part (32) | t-part (32)], written in the 128B-swizzled tile image.
+// query side (A):  per coord c: (-2u0,-2u0,-2u1,-2u1,-2u0,-2u2), then |u|^2 split (n0,n1,n2), then (1,1,1), zeros
+// key side   (B):  per coord c: (  w0,  w1,  w0,  w1,  w2,  w0), then (1,1,1), then |w|^2 split (m0,m1,m2), zeros
+// --------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h0, __nv_bfloat16& h1, __nv_bfloat16& h2) {
+  h0 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h0);
+  h1 = __float2bfloat16_rn(r1);
+  h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+}
+
+__global__ void dist_feature_kernel(const float* __restrict__ kpts, int Np, __nv_bfloat16* __restrict__ aq_t, __nv_bfloat16* __restrict__ bd_t) {
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;     // padded point index
+  if (i >= Np) return;
+  const float4 s4 = *reinterpret_cast<const float4*>(kpts + ((size_t)pair * Np + i) * 8);
+  const float4 t4 = *reinterpret_cast<const float4*>(kpts + ((size_t)pair * Np + i) * 8 + 4);
+  __align__(16) __nv_bfloat16 A[64];
+  __align__(16) __nv_bfloat16 B[64];
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
+#pragma unroll
+  for (int k = 0; k < 64; ++k) { A[k] = zero; B[k] = zero; }
+  const float pts[2][4] = {{s4.x, s4.y, s4.z, s4.w}, {t4.x, t4.y, t4.z, t4.w}};
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {
+    const int o = part * 32;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      __nv_bfloat16 h0, h1, h2;
+      split3(pts[part][c], h0, h1, h2);
+      const __nv_bfloat16 m0 = __float2bfloat16_rn(-2.f * __bfloat162float(h0)), m1 = __float2bfloat16_rn(-2.f * __bfloat162float(h1)),
+                          m2 = __float2bfloat16_rn(-2.f * __bfloat162float(h2));
+      A[o + 6 * c + 0] = m0; B[o + 6 * c + 0] = h0;
+      A[o + 6 * c + 1] = m0; B[o + 6 * c + 1] = h1;
+      A[o + 6 * c + 2] = m1; B[o + 6 * c + 2] = h0;
+      A[o + 6 * c + 3] = m1; B[o + 6 * c + 3] = h1;
+      A[o + 6 * c + 4] = m0; B[o + 6 * c + 4] = h2;
+      A[o + 6 * c + 5] = m2; B[o + 6 * c + 5] = h0;
+    }
+    __nv_bfloat16 n0, n1, n2;
+    split3(pts[part][3], n0, n1, n2);
+    A[o + 18] = n0; A[o + 19] = n1; A[o + 20] = n2; B[o + 18] = one; B[o + 19] = one; B[o + 20] = one;
+    A[o + 21] = one; A[o + 22] = one; A[o + 23] = one; B[o + 21] = n0; B[o + 22] = n1; B[o + 23] = n2;
+  }
+  const int tile = i >> 7, r = i & 127;
+  const size_t tbase = ((size_t)pair * (Np >> 7) + tile) * (128 * 64);
+  uint8_t* ad = (uint8_t*)(aq_t + tbase);
+  uint8_t* bd = (uint8_t*)(bd_t + tbase);
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    *reinterpret_cast<uint4*>(ad + swz_off(r, ch)) = *reinterpret_cast<const uint4*>(&A[ch * 8]);
+    *reinterpret_cast<uint4*>(bd + swz_off(r, ch)) = *reinterpret_cast<const uint4*>(&B[ch * 8]);
+  }
+}
+
+}  // namespace gmf
