@@ -185,6 +185,34 @@ __device__ __forceinline__ void mbar_expect_tx_p(uint64_t* bar, uint32_t bytes, 
       : "memory");
 }
 
+// ---- thread-block clusters: multicast TMA + cluster-wide mbarrier arrival ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier (same offset)
+// receives the complete_tx for the bytes it was sent
+__device__ __forceinline__ void bulk_g2s_mc_p(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n\t}" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask), "r"(on)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc_p(uint64_t* bar, uint16_t mask, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"(mask), "r"(on)
+      : "memory");
+}
+
 // TMEM -> registers: this thread's lane (row), 32 consecutive 32-bit columns starting at taddr.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -195,6 +223,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -230,9 +267,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ float ex2_approx(float x) {
+#if defined(GMF_SC_DBG) && GMF_SC_DBG == 2
+  return fmaf(x, 0.001f, 1.0f);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 // round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits)
 __device__ __forceinline__ float to_tf32(float x) {
@@ -241,7 +282,15 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 __device__ __forceinline__ float4 to_tf32(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
+#if defined(GMF_SC_DBG) && GMF_SC_DBG == 2
+  return x * 0.5f;
+#endif
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;

@@ -194,7 +194,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
-  int sc_impl = 1;          // 1: distances on the tensor pipe (sc_attn_tc.cuh); 0: SIMT distances (attn_tc.cuh)
+  int sc_impl = 3;          // tensor-pipe distances: 3 = 4 threads/row, 1 = 2 threads/row, 2 = 2 threads/row + 2-CTA multicast; 0 = SIMT distances
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
@@ -350,13 +350,13 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
     a.t0 = w.qs; a.t1 = w.ks; a.t2 = w.vts;
     TRY((run_linear<128, 384, PRO_NONE, EPI_QKV_SC>(a, B, st, CAT_QKV)));
   }
-  if (ctx->sc_impl == 1) {
+  if (ctx->sc_impl >= 1) {
     ScAttnArgs sa{};
     sa.q_t = w.qs; sa.k_t = w.ks; sa.vt_t = w.vts; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = msg;
     sa.N = N; sa.tiles = cdiv(N, 128);
     sa.neg_inv_sigma2 = -1.0f / (ctx->sigma_spat * ctx->sigma_spat);
     ProfScope ps(CAT_ATTN_SC, st);
-    cudaError_t e = launch_sc_attn(sa, B, st);
+    cudaError_t e = ctx->sc_impl == 3 ? launch_sc_attn<1, 4>(sa, B, st) : ctx->sc_impl == 2 ? launch_sc_attn<2, 2>(sa, B, st) : launch_sc_attn<1, 2>(sa, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "sc_attn_tc launch");
     return 0;
@@ -956,11 +956,11 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
   cudaError_t e;
   if (sc) {
     TRY(run_prep(w, src, tgt, B, Lk, st));
-    if (ctx->sc_impl == 1) {
+    if (ctx->sc_impl >= 1) {
       ScAttnArgs sa{};
       sa.q_t = Q; sa.k_t = K; sa.vt_t = V; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = out; sa.N = Lk; sa.tiles = kt;
       sa.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
-      e = launch_sc_attn(sa, B, st);
+      e = ctx->sc_impl == 3 ? launch_sc_attn<1, 4>(sa, B, st) : ctx->sc_impl == 2 ? launch_sc_attn<2, 2>(sa, B, st) : launch_sc_attn<1, 2>(sa, B, st);
     } else {
       a.kpts = w.kpts; a.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
       e = launch_attn<128, true>(a, B, st);

@@ -14,6 +14,12 @@
 //   warp 9      MMA issuer (converged, one elected lane): per key tile 8 (S) + 2 (D2S) + 2 (D2T) + 4 (PV) tcgen05.mma
 #pragma once
 #include "common.cuh"
+#ifndef GMF_SC_RSQ
+#define GMF_SC_RSQ 0
+#endif
+#ifndef GMF_SC_DBG
+#define GMF_SC_DBG 0   // timing experiments only: 1 = skip D2 TMEM loads, 2 = no MUFU, 3 = no P smem write
+#endif
 
 namespace gmf {
 
@@ -34,21 +40,27 @@ struct ScCfg {
   static constexpr int K_BYTES = BN * D * 2, V_BYTES = D * BN * 2, BD_BYTES = BN * 64 * 2;
   static constexpr int STAGE_BYTES = K_BYTES + V_BYTES + BD_BYTES;
   static constexpr int P_TILE = 128 * BN * 2;
-  static constexpr int XCH_BYTES = 3 * 2 * 128 * 4;
+  static constexpr int XCH_BYTES = 3 * 4 * 128 * 4;
   static constexpr int SMEM = 1024 + Q_BYTES + AQ_BYTES + NS * STAGE_BYTES + PB * P_TILE + XCH_BYTES + 512;
   static constexpr int COL_S = 0, COL_DS = 128, COL_DT = 256, COL_O = 384;
 };
 
-__global__ void __launch_bounds__(320, 1) sc_attn_tc_kernel(const ScAttnArgs a) {
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs own adjacent row tiles of the same pair and SHARE the K / V^T / Bd
+// stream: each producer fetches half of every stage and multicasts it into both CTAs' shared memory, halving L2 -> SM traffic
+// (the limiter once the distances moved to the tensor pipe).  A stage is refilled only after BOTH CTAs retired its MMAs
+// (tcgen05.commit multicast onto a 2-arrival mbarrier).
+template <int CL, int TPR>   // TPR = softmax threads per score row (2 or 4): 4*TPR softmax warps + producer + MMA warp
+__global__ void __launch_bounds__(128 * TPR + 64, 1) sc_attn_tc_kernel(const ScAttnArgs a) {
   using Cfg = ScCfg;
-  constexpr int D = Cfg::D, BN = Cfg::BN, NS = Cfg::NS, PB = Cfg::PB, HC = BN / 2;
+  constexpr int D = Cfg::D, BN = Cfg::BN, NS = Cfg::NS, PB = Cfg::PB, HC = BN / TPR;
+  constexpr int WP = 4 * TPR, WM = 4 * TPR + 1;           // producer / MMA warp index
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sAq = sQ + Cfg::Q_BYTES;
   uint8_t* sStage = sAq + Cfg::AQ_BYTES;                 // [NS] x {K, V^T, Bd}
   uint8_t* sP = sStage + NS * Cfg::STAGE_BYTES;          // [PB]
-  float* sX = (float*)(sP + PB * Cfg::P_TILE);           // [3][2][128]
+  float* sX = (float*)(sP + PB * Cfg::P_TILE);           // [3][TPR][128]
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;       // [NS]
@@ -60,23 +72,26 @@ __global__ void __launch_bounds__(320, 1) sc_attn_tc_kernel(const ScAttnArgs a) 
   uint32_t* tmem_slot = (uint32_t*)(pv_done + PB + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int pair = blockIdx.y, qt = blockIdx.x;
+  const int pair = blockIdx.y;
+  const int qt = min((int)blockIdx.x, a.tiles - 1);          // ghost CTA of an odd tile count recomputes the last tile (no store)
+  const bool store = (int)blockIdx.x < a.tiles;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   const int nt = (a.N + BN - 1) / BN;
 
   if (tid == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 256); }
-    for (int i = 0; i < PB; ++i) { mbar_init(&p_ready[i], 256); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], CL); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128 * TPR); }
+    for (int i = 0; i < PB; ++i) { mbar_init(&p_ready[i], 128 * TPR); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
   }
-  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == WP) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();      // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == WP) {
     // ------------------------------------ producer ------------------------------------
     const uint32_t leader = elect_one() ? 1u : 0u;
     const size_t tq = (size_t)pair * a.tiles + qt;
@@ -91,13 +106,21 @@ __global__ void __launch_bounds__(320, 1) sc_attn_tc_kernel(const ScAttnArgs a) 
       const size_t tix = (size_t)pair * a.tiles + (j >> 1);        // 128-key tile, half h
       const int h = j & 1;
       const uint8_t* ksrc = (const uint8_t*)(a.k_t + tix * (128 * D)) + h * 8192;
-      bulk_g2s_p(dst, ksrc, 8192, &kv_full[st], leader);
-      bulk_g2s_p(dst + 8192, ksrc + 16384, 8192, &kv_full[st], leader);
-      bulk_g2s_p(dst + Cfg::K_BYTES, (const uint8_t*)(a.vt_t + tix * (128 * D)) + h * Cfg::V_BYTES, Cfg::V_BYTES, &kv_full[st], leader);
-      bulk_g2s_p(dst + Cfg::K_BYTES + Cfg::V_BYTES, (const uint8_t*)(a.bd_t + tix * (128 * 64)) + h * Cfg::BD_BYTES, Cfg::BD_BYTES,
-                 &kv_full[st], leader);
+      const uint8_t* vsrc = (const uint8_t*)(a.vt_t + tix * (128 * D)) + h * Cfg::V_BYTES;
+      const uint8_t* bsrc = (const uint8_t*)(a.bd_t + tix * (128 * 64)) + h * Cfg::BD_BYTES;
+      if (CL == 1) {
+        bulk_g2s_p(dst, ksrc, 8192, &kv_full[st], leader);
+        bulk_g2s_p(dst + 8192, ksrc + 16384, 8192, &kv_full[st], leader);
+        bulk_g2s_p(dst + Cfg::K_BYTES, vsrc, Cfg::V_BYTES, &kv_full[st], leader);
+        bulk_g2s_p(dst + Cfg::K_BYTES + Cfg::V_BYTES, bsrc, Cfg::BD_BYTES, &kv_full[st], leader);
+      } else {
+        // this CTA fetches K atom `crank`, V^T rows [64 crank, +64) and Bd rows [32 crank, +32) and multicasts them to both CTAs
+        bulk_g2s_mc_p(dst + crank * 8192, ksrc + crank * 16384, 8192, &kv_full[st], 0x3, leader);
+        bulk_g2s_mc_p(dst + Cfg::K_BYTES + crank * 8192, vsrc + crank * 8192, 8192, &kv_full[st], 0x3, leader);
+        bulk_g2s_mc_p(dst + Cfg::K_BYTES + Cfg::V_BYTES + crank * 4096, bsrc + crank * 4096, 4096, &kv_full[st], 0x3, leader);
+      }
     }
-  } else if (warp == 9) {
+  } else if (warp == WM) {
     // ------------------------------------ MMA issuer ------------------------------------
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t idesc_s = umma_idesc(128, BN, kFmtBF16);
@@ -139,120 +162,123 @@ __global__ void __launch_bounds__(320, 1) sc_attn_tc_kernel(const ScAttnArgs a) 
       for (int ks = 0; ks < 4; ++ks)
         tc_mma_bf16_p(tmem + Cfg::COL_O, umma_desc_adv(pd, ks * 32), umma_desc_adv(vd, ks * 32), idesc_o, (j > 0 || ks > 0) ? 1u : 0u, leader);
       tc_commit_p(&pv_done[pb], leader);
-      tc_commit_p(&kv_empty[st], leader);
+      if (CL == 1) tc_commit_p(&kv_empty[st], leader);
+      else tc_commit_mc_p(&kv_empty[st], 0x3, leader);        // both CTAs must retire a stage before either producer refills it
       if (j + 2 < nt) issue_sd(j + 2);
     }
   } else {
-    // ------------------------------------ softmax (two threads per query row) ------------------------------------
-    const int q = warp & 3, h = warp >> 2;
+    // ------------------------------------ softmax (TPR threads per query row) ------------------------------------
+    const int q = warp & 3, h = warp >> 2;               // TMEM lane quadrant, column slice of the 64-key tile
     const int r = q * 32 + lane;
     const int gq = qt * 128 + r;
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + h * HC;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t trow = tlane + h * HC;
     const int bar_id = 1 + q;
-    float m_ref = 0.f, l_sum = 0.f;
+    // Single-pass online softmax with a DEFERRED reference maximum: tile j is exponentiated against the reference left by
+    // tile j-1 (no pre-exp barrier between the threads sharing a row); the row maximum seen in tile j is exchanged after
+    // P_j has been published and, if it exceeded the reference by more than 2^8, the O accumulator / row sum are rescaled
+    // before P_{j+1} is published.  bf16/fp32 have 8 exponent bits, so one tile of un-normalised weights is harmless.
+    // (Rows always contain zero logits here - c_ij = 0 for incompatible pairs - so the initial reference 0 cannot underflow.)
+    float m_ref = 0.f, l_sum = 0.f, pend_shift = 0.f;     // pend_shift: rescale decided after the previous tile, not yet applied to O
     const float nis2 = a.neg_inv_sigma2;
     for (int j = 0; j < nt; ++j) {
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
-      float sv[HC];
+      uint32_t pk[HC / 2];
+      float tmax = -INFINITY;
       {
-        uint32_t us[32], ua[32], ub[32];
-        tmem_ld32(trow + Cfg::COL_S + b * BN, us);
-        tmem_ld32(trow + Cfg::COL_DS + b * BN, ua);
-        tmem_ld32(trow + Cfg::COL_DT + b * BN, ub);
+        uint32_t us[HC], ua[HC], ub[HC];
+        if (HC == 32) {
+          tmem_ld32(trow + Cfg::COL_S + b * BN, reinterpret_cast<uint32_t(&)[32]>(us));
+          tmem_ld32(trow + Cfg::COL_DS + b * BN, reinterpret_cast<uint32_t(&)[32]>(ua));
+          tmem_ld32(trow + Cfg::COL_DT + b * BN, reinterpret_cast<uint32_t(&)[32]>(ub));
+        } else {
+          tmem_ld16(trow + Cfg::COL_S + b * BN, reinterpret_cast<uint32_t(&)[16]>(us));
+          tmem_ld16(trow + Cfg::COL_DS + b * BN, reinterpret_cast<uint32_t(&)[16]>(ua));
+          tmem_ld16(trow + Cfg::COL_DT + b * BN, reinterpret_cast<uint32_t(&)[16]>(ub));
+        }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&s_free[b]);
+        const int nvalid = a.N - j * BN - h * HC;
+        float ps0 = 0.f, ps1 = 0.f;
         // (|ds| - |dt|)^2 = ds^2 + dt^2 - 2 sqrt(ds^2 dt^2); |.| guards tiny negative d^2 from cancellation
 #pragma unroll
-        for (int c = 0; c < HC; ++c) {
-          const float d2s = __uint_as_float(ua[c]), d2t = __uint_as_float(ub[c]);
-          const float x = fmaf(-2.f, sqrt_approx(fabsf(d2s * d2t)), d2s + d2t);
-          const float cij = __saturatef(fmaf(x, nis2, 1.f));
-          sv[c] = fmaf(__uint_as_float(us[c]), cij, -m_ref);
+        for (int c = 0; c < HC; c += 2) {
+          float t0, t1;
+          {
+            const float d2s = __uint_as_float(ua[c]), d2t = __uint_as_float(ub[c]);
+            const float x = fmaf(-2.f, sqrt_approx(fabsf(d2s * d2t)), d2s + d2t);
+            t0 = fmaf(__uint_as_float(us[c]), __saturatef(fmaf(x, nis2, 1.f)), -m_ref);
+          }
+          {
+            const float d2s = __uint_as_float(ua[c + 1]), d2t = __uint_as_float(ub[c + 1]);
+            const float x = fmaf(-2.f, sqrt_approx(fabsf(d2s * d2t)), d2s + d2t);
+            t1 = fmaf(__uint_as_float(us[c + 1]), __saturatef(fmaf(x, nis2, 1.f)), -m_ref);
+          }
+          if (nvalid < HC) {                               // ragged last tile (warp-uniform)
+            if (c >= nvalid) t0 = -INFINITY;
+            if (c + 1 >= nvalid) t1 = -INFINITY;
+          }
+          tmax = fmaxf(tmax, fmaxf(t0, t1));
+          const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+          ps0 += p0; ps1 += p1;
+          pk[c >> 1] = pack_bf16(p0, p1);
         }
+        l_sum += ps0 + ps1;
       }
-      float tmax = -INFINITY;
-      const int nvalid = a.N - j * BN - h * HC;
-      if (nvalid < HC) {
-#pragma unroll
-        for (int c = 0; c < HC; ++c)
-          if (c >= nvalid) sv[c] = -INFINITY;
-      }
-#pragma unroll
-      for (int c = 0; c < HC; ++c) tmax = fmaxf(tmax, sv[c]);
-      sX[(b * 2 + h) * 128 + r] = tmax;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      tmax = fmaxf(tmax, sX[(b * 2 + (h ^ 1)) * 128 + r]);
-      const bool need = (tmax > 8.f) || (j == 0 && tmax < -8.f);
-      float alpha = 1.f;
-      if (need) {
-        alpha = ex2_approx(-tmax);
-        m_ref += tmax;
-        l_sum *= alpha;
-      }
-      float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-      if (__any_sync(0xffffffffu, need)) {
-        const float sh = need ? tmax : 0.f;
-#pragma unroll
-        for (int c = 0; c < HC; c += 4) {
-          sv[c] = ex2_approx(sv[c] - sh); ps0 += sv[c];
-          sv[c + 1] = ex2_approx(sv[c + 1] - sh); ps1 += sv[c + 1];
-          sv[c + 2] = ex2_approx(sv[c + 2] - sh); ps2 += sv[c + 2];
-          sv[c + 3] = ex2_approx(sv[c + 3] - sh); ps3 += sv[c + 3];
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < HC; c += 4) {
-          sv[c] = ex2_approx(sv[c]); ps0 += sv[c];
-          sv[c + 1] = ex2_approx(sv[c + 1]); ps1 += sv[c + 1];
-          sv[c + 2] = ex2_approx(sv[c + 2]); ps2 += sv[c + 2];
-          sv[c + 3] = ex2_approx(sv[c + 3]); ps3 += sv[c + 3];
-        }
-      }
-      l_sum += (ps0 + ps1) + (ps2 + ps3);
       const int pb = j % PB;
       uint8_t* myP = sP + pb * Cfg::P_TILE;
-      if (j >= PB) mbar_wait(&pv_done[pb], ((j / PB) - 1) & 1);
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
+      if (j >= PB) mbar_wait(&pv_done[pb], ((j / PB) - 1) & 1);        // P buffer free again (PV of tile j-PB retired)
+      if (__any_sync(0xffffffffu, pend_shift != 0.f)) {
+        // rare: the previous tile raised the reference; P_j above already used the new reference, O still holds the old one
         mbar_wait(&pv_done[(j - 1) % PB], ((j - 1) / PB) & 1);
         tc_fence_after();
+        const float alpha = ex2_approx(-pend_shift);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < D / TPR / 32; ++c) {
           uint32_t u[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_O + h * 64 + c * 32, u);
+          tmem_ld32(tlane + Cfg::COL_O + h * (D / TPR) + c * 32, u);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(__uint_as_float(u[i]) * alpha);
-          tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_O + h * 64 + c * 32, u);
+          tmem_st32(tlane + Cfg::COL_O + h * (D / TPR) + c * 32, u);
         }
         tmem_st_wait();
+        pend_shift = 0.f;
       }
 #pragma unroll
-      for (int c8 = 0; c8 < HC / 8; ++c8) {
-        uint4 pk;
-        pk.x = pack_bf16(sv[8 * c8], sv[8 * c8 + 1]); pk.y = pack_bf16(sv[8 * c8 + 2], sv[8 * c8 + 3]);
-        pk.z = pack_bf16(sv[8 * c8 + 4], sv[8 * c8 + 5]); pk.w = pack_bf16(sv[8 * c8 + 6], sv[8 * c8 + 7]);
-        *reinterpret_cast<uint4*>(myP + swz_off(r, h * (HC / 8) + c8)) = pk;
-      }
+      for (int c8 = 0; c8 < HC / 8; ++c8)
+        *reinterpret_cast<uint4*>(myP + swz_off(r, h * (HC / 8) + c8)) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&p_ready[pb]);
+      // deferred row maximum: off the MMA critical path
+      sX[(b * TPR + h) * 128 + r] = tmax;
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * TPR) : "memory");
+#pragma unroll
+      for (int o = 1; o < TPR; ++o) tmax = fmaxf(tmax, sX[(b * TPR + ((h + o) % TPR)) * 128 + r]);
+      if (tmax > 8.f && j + 1 < nt) {                      // identical decision in all TPR threads of the row
+        m_ref += tmax;
+        l_sum *= ex2_approx(-tmax);
+        pend_shift = tmax;
+      }
     }
-    sX[(2 * 2 + h) * 128 + r] = l_sum;
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-    l_sum += sX[(2 * 2 + (h ^ 1)) * 128 + r];
+    sX[(2 * TPR + h) * 128 + r] = l_sum;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * TPR) : "memory");
+#pragma unroll
+    for (int o = 1; o < TPR; ++o) l_sum += sX[(2 * TPR + ((h + o) % TPR)) * 128 + r];
     mbar_wait(&pv_done[(nt - 1) % PB], ((nt - 1) / PB) & 1);
     tc_fence_after();
     const float inv = 1.f / l_sum;
-    float* op = a.out + ((size_t)pair * a.N + gq) * D + h * 64;
+    float* op = a.out + ((size_t)pair * a.N + gq) * D + h * (D / TPR);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < D / TPR / 32; ++c) {
       uint32_t u[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_O + h * 64 + c * 32, u);
+      tmem_ld32(tlane + Cfg::COL_O + h * (D / TPR) + c * 32, u);
       tmem_ld_wait();
-      if (gq < a.N) {
+      if (store && gq < a.N) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<float4*>(op + c * 32 + 4 * i) =
@@ -262,19 +288,29 @@ __global__ void __launch_bounds__(320, 1) sc_attn_tc_kernel(const ScAttnArgs a) 
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (CL > 1) cluster_sync_all(); else __syncthreads();      // the peer may still arrive on / multicast into this CTA's smem
+  if (warp == WP) tmem_dealloc(tmem, 512);
 }
 
+template <int CL, int TPR>
 inline cudaError_t launch_sc_attn(const ScAttnArgs& a, int pairs, cudaStream_t st) {
   static bool configured = false;
+  auto kern = sc_attn_tc_kernel<CL, TPR>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ScCfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ScCfg::SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  sc_attn_tc_kernel<<<dim3(a.tiles, pairs), 320, ScCfg::SMEM, st>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(((a.tiles + CL - 1) / CL) * CL, pairs);
+  cfg.blockDim = dim3(128 * TPR + 64);
+  cfg.dynamicSmemBytes = ScCfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 // --------------------------------------------------------------------------------------------------------------------

@@ -88,6 +88,20 @@ def test_sc_guided_attention_compat_on_the_fly(B, N):
     assert (out - attn_ref(q, k, v, 128 ** -0.5, pr["src_keypts"], pr["tgt_keypts"], 0.1)).abs().max() < 6e-3
 
 
+def test_sc_attention_reference_max_rescale_path():
+    """Logits that grow by >> 2^8 along the key axis force the deferred O-accumulator rescale of the SC kernel."""
+    from gmf_b200.synth import synth_pairs
+    eng = make_engine(dict(O.DEFAULT_CFG, num_layers=1))
+    g = torch.Generator().manual_seed(21)
+    pr = synth_pairs(1, 700, seed=5, inlier_ratio=0.9, noise=0.001)      # many compatible pairs -> c_ij > 0 often
+    q, k, v = (torch.randn(1, 700, 128, generator=g) for _ in range(3))
+    k[:, 200:450] *= 4.0
+    k[:, 450:] *= 9.0
+    out = eng.debug_attention(q.cuda(), k.cuda(), v.cuda(), 128 ** -0.5, pr["src_keypts"].cuda(), pr["tgt_keypts"].cuda(), 0.1).cpu()
+    ref = attn_ref(q, k, v, 128 ** -0.5, pr["src_keypts"], pr["tgt_keypts"], 0.1)
+    assert torch.isfinite(out).all() and (out - ref).abs().max() < 4e-2 and (out - ref).abs().mean() < 3e-3
+
+
 def test_sc_attention_large_coordinates_kitti_scale():
     """|x| ~ 60 m, sigma_d = 1.2: the |s_i|^2+|s_j|^2-2 s_i.s_j expansion must survive the cancellation."""
     from gmf_b200.synth import synth_pairs
