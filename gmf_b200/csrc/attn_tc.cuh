@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(576, 1) attn_tc_kernel(const AttnArgs a) {
     for (int j = 0; j < nt; ++j) {
       const int st = j % NS, pb = j % PB;
       for (int t = 0; t < ntile; ++t) {
+        if (j + 2 < nt) issue_s(t, j + 2);                    // only needs the S buffer drained by softmax(t, j): issue before blocking on P
         mbar_wait(&p_ready[t * PB + pb], (j / PB) & 1);
         tc_fence_after();
         const uint64_t pd = umma_desc_adv(p_desc, (t * PB + pb) * Cfg::P_TILE);
@@ -148,7 +149,6 @@ __global__ void __launch_bounds__(576, 1) attn_tc_kernel(const AttnArgs a) {
                         (j > 0 || ks > 0) ? 1u : 0u, leader);
         tc_commit_p(&pv_done[t * PB + pb], leader);
         if (t == ntile - 1) tc_commit_p(&kv_empty[st], leader);     // both row tiles are done with this K/V stage
-        if (j + 2 < nt) issue_s(t, j + 2);
       }
     }
   } else if ((warp >> 3) < ntile) {

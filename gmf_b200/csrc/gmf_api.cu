@@ -194,7 +194,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
-  int sc_impl = 3;          // tensor-pipe distances: 3 = 4 threads/row, 1 = 2 threads/row, 2 = 2 threads/row + 2-CTA multicast; 0 = SIMT distances
+  int sc_impl = 1;          // tensor-pipe distances: 3 = 4 threads/row, 1 = 2 threads/row, 2 = 2 threads/row + 2-CTA multicast; 0 = SIMT distances
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;

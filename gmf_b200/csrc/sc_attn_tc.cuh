@@ -35,13 +35,13 @@ struct ScAttnArgs {
 };
 
 struct ScCfg {
-  static constexpr int D = 128, BN = 64, NS = 3, PB = 2;
+  static constexpr int D = 128, BN = 64, NS = 3, NV = 3, PB = 2;   // NS: {K, Bd} ring depth, NV: V^T ring depth
   static constexpr int Q_BYTES = 128 * D * 2, AQ_BYTES = 128 * 64 * 2;
   static constexpr int K_BYTES = BN * D * 2, V_BYTES = D * BN * 2, BD_BYTES = BN * 64 * 2;
-  static constexpr int STAGE_BYTES = K_BYTES + V_BYTES + BD_BYTES;
+  static constexpr int KSTAGE_BYTES = K_BYTES + BD_BYTES;   // released as soon as S/D2 of that tile retired (early)
   static constexpr int P_TILE = 128 * BN * 2;
   static constexpr int XCH_BYTES = 3 * 4 * 128 * 4;
-  static constexpr int SMEM = 1024 + Q_BYTES + AQ_BYTES + NS * STAGE_BYTES + PB * P_TILE + XCH_BYTES + 512;
+  static constexpr int SMEM = 1024 + Q_BYTES + AQ_BYTES + NS * KSTAGE_BYTES + NV * V_BYTES + PB * P_TILE + XCH_BYTES + 512;
   static constexpr int COL_S = 0, COL_DS = 128, COL_DT = 256, COL_O = 384;
 };
 
@@ -52,20 +52,23 @@ struct ScCfg {
 template <int CL, int TPR>   // TPR = softmax threads per score row (2 or 4): 4*TPR softmax warps + producer + MMA warp
 __global__ void __launch_bounds__(128 * TPR + 64, 1) sc_attn_tc_kernel(const ScAttnArgs a) {
   using Cfg = ScCfg;
-  constexpr int D = Cfg::D, BN = Cfg::BN, NS = Cfg::NS, PB = Cfg::PB, HC = BN / TPR;
+  constexpr int D = Cfg::D, BN = Cfg::BN, NS = Cfg::NS, NV = Cfg::NV, PB = Cfg::PB, HC = BN / TPR;
   constexpr int WP = 4 * TPR, WM = 4 * TPR + 1;           // producer / MMA warp index
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sAq = sQ + Cfg::Q_BYTES;
-  uint8_t* sStage = sAq + Cfg::AQ_BYTES;                 // [NS] x {K, V^T, Bd}
-  uint8_t* sP = sStage + NS * Cfg::STAGE_BYTES;          // [PB]
+  uint8_t* sK = sAq + Cfg::AQ_BYTES;                     // [NS] x {K, Bd}
+  uint8_t* sV = sK + NS * Cfg::KSTAGE_BYTES;             // [NV] x V^T
+  uint8_t* sP = sV + NV * Cfg::V_BYTES;                  // [PB]
   float* sX = (float*)(sP + PB * Cfg::P_TILE);           // [3][TPR][128]
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;       // [NS]
-  uint64_t* kv_empty = kv_full + NS;  // [NS]
-  uint64_t* s_full = kv_empty + NS;   // [2]
+  uint64_t* k_full = bars + 1;        // [NS]
+  uint64_t* k_empty = k_full + NS;    // [NS]
+  uint64_t* v_full = k_empty + NS;    // [NV]
+  uint64_t* v_empty = v_full + NV;    // [NV]
+  uint64_t* s_full = v_empty + NV;    // [2]
   uint64_t* s_free = s_full + 2;      // [2]
   uint64_t* p_ready = s_free + 2;     // [PB]
   uint64_t* pv_done = p_ready + PB;   // [PB]
@@ -80,7 +83,8 @@ __global__ void __launch_bounds__(128 * TPR + 64, 1) sc_attn_tc_kernel(const ScA
 
   if (tid == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], CL); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], CL); }
+    for (int i = 0; i < NV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128 * TPR); }
     for (int i = 0; i < PB; ++i) { mbar_init(&p_ready[i], 128 * TPR); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
@@ -98,26 +102,38 @@ __global__ void __launch_bounds__(128 * TPR + 64, 1) sc_attn_tc_kernel(const ScA
     mbar_expect_tx_p(q_full, Cfg::Q_BYTES + Cfg::AQ_BYTES, leader);
     bulk_g2s_p(sQ, a.q_t + tq * (128 * D), Cfg::Q_BYTES, q_full, leader);
     bulk_g2s_p(sAq, a.aq_t + tq * (128 * 64), Cfg::AQ_BYTES, q_full, leader);
-    for (int j = 0; j < nt; ++j) {
-      const int st = j % NS;
-      if (j >= NS) mbar_wait(&kv_empty[st], ((j / NS) - 1) & 1);
-      uint8_t* dst = sStage + st * Cfg::STAGE_BYTES;
-      mbar_expect_tx_p(&kv_full[st], Cfg::STAGE_BYTES, leader);
-      const size_t tix = (size_t)pair * a.tiles + (j >> 1);        // 128-key tile, half h
-      const int h = j & 1;
-      const uint8_t* ksrc = (const uint8_t*)(a.k_t + tix * (128 * D)) + h * 8192;
-      const uint8_t* vsrc = (const uint8_t*)(a.vt_t + tix * (128 * D)) + h * Cfg::V_BYTES;
-      const uint8_t* bsrc = (const uint8_t*)(a.bd_t + tix * (128 * 64)) + h * Cfg::BD_BYTES;
-      if (CL == 1) {
-        bulk_g2s_p(dst, ksrc, 8192, &kv_full[st], leader);
-        bulk_g2s_p(dst + 8192, ksrc + 16384, 8192, &kv_full[st], leader);
-        bulk_g2s_p(dst + Cfg::K_BYTES, vsrc, Cfg::V_BYTES, &kv_full[st], leader);
-        bulk_g2s_p(dst + Cfg::K_BYTES + Cfg::V_BYTES, bsrc, Cfg::BD_BYTES, &kv_full[st], leader);
+    // two independent rings: {K, Bd} of tile j is needed when S_j is issued (two tiles ahead of the softmax) and is free again
+    // as soon as those MMAs retire; V^T of tile j is needed only at PV_j.  The producer always serves the older request first.
+    int jk = 0, jv = 0;
+    while (jk < nt || jv < nt) {
+      if (jk < nt && (jv >= nt || jk <= jv + 2)) {
+        const int st = jk % NS;
+        if (jk >= NS) mbar_wait(&k_empty[st], ((jk / NS) - 1) & 1);
+        uint8_t* dst = sK + st * Cfg::KSTAGE_BYTES;
+        mbar_expect_tx_p(&k_full[st], Cfg::KSTAGE_BYTES, leader);
+        const size_t tix = (size_t)pair * a.tiles + (jk >> 1);
+        const int h = jk & 1;
+        const uint8_t* ksrc = (const uint8_t*)(a.k_t + tix * (128 * D)) + h * 8192;
+        const uint8_t* bsrc = (const uint8_t*)(a.bd_t + tix * (128 * 64)) + h * Cfg::BD_BYTES;
+        if (CL == 1) {
+          bulk_g2s_p(dst, ksrc, 8192, &k_full[st], leader);
+          bulk_g2s_p(dst + 8192, ksrc + 16384, 8192, &k_full[st], leader);
+          bulk_g2s_p(dst + Cfg::K_BYTES, bsrc, Cfg::BD_BYTES, &k_full[st], leader);
+        } else {
+          bulk_g2s_mc_p(dst + crank * 8192, ksrc + crank * 16384, 8192, &k_full[st], 0x3, leader);
+          bulk_g2s_mc_p(dst + Cfg::K_BYTES + crank * 4096, bsrc + crank * 4096, 4096, &k_full[st], 0x3, leader);
+        }
+        ++jk;
       } else {
-        // this CTA fetches K atom `crank`, V^T rows [64 crank, +64) and Bd rows [32 crank, +32) and multicasts them to both CTAs
-        bulk_g2s_mc_p(dst + crank * 8192, ksrc + crank * 16384, 8192, &kv_full[st], 0x3, leader);
-        bulk_g2s_mc_p(dst + Cfg::K_BYTES + crank * 8192, vsrc + crank * 8192, 8192, &kv_full[st], 0x3, leader);
-        bulk_g2s_mc_p(dst + Cfg::K_BYTES + Cfg::V_BYTES + crank * 4096, bsrc + crank * 4096, 4096, &kv_full[st], 0x3, leader);
+        const int sv_ = jv % NV;
+        if (jv >= NV) mbar_wait(&v_empty[sv_], ((jv / NV) - 1) & 1);
+        uint8_t* dst = sV + sv_ * Cfg::V_BYTES;
+        mbar_expect_tx_p(&v_full[sv_], Cfg::V_BYTES, leader);
+        const size_t tix = (size_t)pair * a.tiles + (jv >> 1);
+        const uint8_t* vsrc = (const uint8_t*)(a.vt_t + tix * (128 * D)) + (jv & 1) * Cfg::V_BYTES;
+        if (CL == 1) bulk_g2s_p(dst, vsrc, Cfg::V_BYTES, &v_full[sv_], leader);
+        else bulk_g2s_mc_p(dst + crank * 8192, vsrc + crank * 8192, 8192, &v_full[sv_], 0x3, leader);
+        ++jv;
       }
     }
   } else if (warp == WM) {
@@ -128,14 +144,15 @@ __global__ void __launch_bounds__(128 * TPR + 64, 1) sc_attn_tc_kernel(const ScA
     const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
     const uint64_t aq_desc = umma_desc_sw128(smem_u32(sAq));
     const uint64_t p_desc = umma_desc_sw128(smem_u32(sP));
-    const uint64_t st_desc = umma_desc_sw128(smem_u32(sStage));
+    const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK));
+    const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV));
     auto issue_sd = [&](int j) {
       const int st = j % NS, bb = j & 1;
-      mbar_wait(&kv_full[st], (j / NS) & 1);
+      mbar_wait(&k_full[st], (j / NS) & 1);
       if (j >= 2) mbar_wait(&s_free[bb], ((j >> 1) - 1) & 1);
       tc_fence_after();
-      const uint64_t kd = umma_desc_adv(st_desc, st * Cfg::STAGE_BYTES);
-      const uint64_t bd = umma_desc_adv(kd, Cfg::K_BYTES + Cfg::V_BYTES);
+      const uint64_t kd = umma_desc_adv(k_desc0, st * Cfg::KSTAGE_BYTES);
+      const uint64_t bd = umma_desc_adv(kd, Cfg::K_BYTES);
 #pragma unroll
       for (int at = 0; at < 2; ++at)
 #pragma unroll
@@ -149,22 +166,27 @@ __global__ void __launch_bounds__(128 * TPR + 64, 1) sc_attn_tc_kernel(const ScA
       for (int ks = 2; ks < 4; ++ks)        // target-cloud squared distances: K slots 32..63
         tc_mma_bf16_p(tmem + Cfg::COL_DT + bb * BN, umma_desc_adv(aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), idesc_s, ks > 2 ? 1u : 0u, leader);
       tc_commit_p(&s_full[bb], leader);
+      if (CL == 1) tc_commit_p(&k_empty[st], leader);          // the {K, Bd} stage is free once these MMAs retire
+      else tc_commit_mc_p(&k_empty[st], 0x3, leader);
     };
     mbar_wait(q_full, 0);
     for (int jj = 0; jj < 2 && jj < nt; ++jj) issue_sd(jj);
     for (int j = 0; j < nt; ++j) {
-      const int st = j % NS, pb = j % PB;
+      const int sv_ = j % NV, pb = j % PB;
+      // scores run two key tiles ahead: S/D2 of tile j+2 only need the S buffer drained by softmax(j) (early in its tile) and
+      // a {K, Bd} stage that was prefetched long ago, so they are issued BEFORE blocking on P_j
+      if (j + 2 < nt) issue_sd(j + 2);
       mbar_wait(&p_ready[pb], (j / PB) & 1);
+      mbar_wait(&v_full[sv_], (j / NV) & 1);
       tc_fence_after();
       const uint64_t pd = umma_desc_adv(p_desc, pb * Cfg::P_TILE);
-      const uint64_t vd = umma_desc_adv(st_desc, st * Cfg::STAGE_BYTES + Cfg::K_BYTES);
+      const uint64_t vd = umma_desc_adv(v_desc0, sv_ * Cfg::V_BYTES);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
         tc_mma_bf16_p(tmem + Cfg::COL_O, umma_desc_adv(pd, ks * 32), umma_desc_adv(vd, ks * 32), idesc_o, (j > 0 || ks > 0) ? 1u : 0u, leader);
       tc_commit_p(&pv_done[pb], leader);
-      if (CL == 1) tc_commit_p(&kv_empty[st], leader);
-      else tc_commit_mc_p(&kv_empty[st], 0x3, leader);        // both CTAs must retire a stage before either producer refills it
-      if (j + 2 < nt) issue_sd(j + 2);
+      if (CL == 1) tc_commit_p(&v_empty[sv_], leader);
+      else tc_commit_mc_p(&v_empty[sv_], 0x3, leader);        // both CTAs must retire a stage before either producer refills it
     }
   } else {
     // ------------------------------------ softmax (TPR threads per query row) ------------------------------------
@@ -248,17 +270,23 @@ __global__ void __launch_bounds__(128 * TPR + 64, 1) sc_attn_tc_kernel(const ScA
         tmem_st_wait();
         pend_shift = 0.f;
       }
+#if GMF_SC_DBG != 3
 #pragma unroll
       for (int c8 = 0; c8 < HC / 8; ++c8)
         *reinterpret_cast<uint4*>(myP + swz_off(r, h * (HC / 8) + c8)) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
       fence_proxy_async();
+#else
+      if (pk[0] == 0x12345678u) *reinterpret_cast<uint4*>(myP + swz_off(r, h * (HC / 8))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#endif
       tc_fence_before();
       mbar_arrive(&p_ready[pb]);
       // deferred row maximum: off the MMA critical path
+#if GMF_SC_DBG != 4
       sX[(b * TPR + h) * 128 + r] = tmax;
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * TPR) : "memory");
 #pragma unroll
       for (int o = 1; o < TPR; ++o) tmax = fmaxf(tmax, sX[(b * TPR + ((h + o) % TPR)) * 128 + r]);
+#endif
       if (tmax > 8.f && j + 1 < nt) {                      // identical decision in all TPR threads of the row
         m_ref += tmax;
         l_sum *= ex2_approx(-tmax);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # timing experiments: rebuild with GMF_SC_DBG variants ON THE BOX and bench only
 mkdir -p gpurun_out
-for v in 1 2 0; do
+for v in ${DBG_LIST:-1 2 0}; do
   GMF_SC_DBG=$v python gmf_b200/build.py > /dev/null 2>&1
   timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_dbg$v.json 2> gpurun_out/bench_dbg$v.err
   python - <<PY
