@@ -58,6 +58,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait on two barriers with the two phase checks in flight together (a completed-phase TRYWAIT still costs ~70-90 cycles).
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  uint32_t oka, okb;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "selp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(oka), "=r"(okb)
+      : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b)
+      : "memory");
+  if (!oka) mbar_wait(bar_a, parity_a);
+  if (!okb) mbar_wait(bar_b, parity_b);
+}
+
 // ------------------------------------------------------------------------------------------------
 // bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
 // ------------------------------------------------------------------------------------------------
@@ -165,6 +181,21 @@ __device__ __forceinline__ void tc_mma_tf32_p(uint32_t d_tmem, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(on)
       : "memory");
 }
+// A operand in TMEM (lane = row, each 32-bit column packs two bf16 K elements), B from shared memory.
+__device__ __forceinline__ void tc_mma_bf16_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_p(uint64_t* bar, uint32_t on) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
@@ -245,6 +276,19 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
       "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]),
       "r"(v[29]), "r"(v[30]), "r"(v[31]), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};" ::"r"(v[0]),
+      "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -12,6 +12,8 @@
 #include "attn_tc.cuh"
 #include "linear_tc.cuh"
 #include "sc_attn_tc.cuh"
+#include "sc_attn_v8.cuh"
+#include "sc_attn_v9.cuh"
 #include "tail.cuh"
 
 using namespace gmf;
@@ -194,7 +196,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
-  int sc_impl = 1;          // tensor-pipe distances: 3 = 4 threads/row, 1 = 2 threads/row, 2 = 2 threads/row + 2-CTA multicast; 0 = SIMT distances
+  int sc_impl = 11;         // 11/12/13 = gen-9 kernel (0/1/2 of 4 exponentials on the FMA pipe); 8/9/10 = gen-8; 1/2/3 = gen-7 variants; 0 = SIMT distances
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
@@ -333,14 +335,47 @@ int run_fusion(const FusionW& f, Work& w, const float* xq, const float* ctxk, in
   return 0;
 }
 
-int run_prep(Work& w, const float* src, const float* tgt, int B, int N, cudaStream_t st) {
+int run_prep(const gmf_ctx* ctx, Work& w, const float* src, const float* tgt, int B, int N, cudaStream_t st, float sigma_d = 0.f) {
   ProfScope ps(CAT_PREP, st);
   const int Np = cdiv(N, 128) * 128;
   prep_points_kernel<<<B, 256, 0, st>>>(src, tgt, N, Np, w.kpts, w.src4, w.tgt4);
   LAUNCHED();
-  dist_feature_kernel<<<dim3(Np / 128, B), 128, 0, st>>>(w.kpts, Np, w.aq, w.bd);
+  if (ctx->sc_impl >= 8) dist_feature_scaled_kernel<<<dim3(Np / 128, B), 128, 0, st>>>(w.kpts, Np, 1.0f / (sigma_d > 0.f ? sigma_d : ctx->sigma_spat), w.aq, w.bd);
+  else dist_feature_kernel<<<dim3(Np / 128, B), 128, 0, st>>>(w.kpts, Np, w.aq, w.bd);
   LAUNCHED();
   return 0;
+}
+
+cudaError_t launch_sc_dispatch(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, cudaStream_t st);
+cudaError_t launch_sc_any(const gmf_ctx* ctx, const ScAttnArgs& sa_in, int B, cudaStream_t st) {
+  // GMF_SC_TRACE=<file>: the second launch of the process records the role timeline of CTA (0,0) (tools/sc_trace.py reads it)
+  static int n_launch = 0;
+  const char* tf = getenv("GMF_SC_TRACE");
+  if (!tf || ++n_launch != 2) return launch_sc_dispatch(ctx, sa_in, B, st);
+  ScAttnArgs sa = sa_in;
+  const size_t bytes = 4 * 256 * 4 * sizeof(long long);
+  cudaMalloc(&sa.trace, bytes);
+  cudaMemsetAsync(sa.trace, 0, bytes, st);
+  cudaError_t e = launch_sc_dispatch(ctx, sa, B, st);
+  cudaStreamSynchronize(st);
+  std::vector<long long> h(4 * 256 * 4);
+  cudaMemcpy(h.data(), sa.trace, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(sa.trace);
+  if (FILE* f = fopen(tf, "wb")) { fwrite(h.data(), 1, bytes, f); fclose(f); }
+  return e;
+}
+cudaError_t launch_sc_dispatch(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, cudaStream_t st) {
+  switch (ctx->sc_impl) {
+    case 11: return launch_sc_attn_v9<0>(sa, B, st);
+    case 12: return launch_sc_attn_v9<1>(sa, B, st);
+    case 13: return launch_sc_attn_v9<2>(sa, B, st);
+    case 8: return launch_sc_attn_v8<0>(sa, B, st);
+    case 9: return launch_sc_attn_v8<1>(sa, B, st);
+    case 10: return launch_sc_attn_v8<2>(sa, B, st);
+    case 3: return launch_sc_attn<1, 4>(sa, B, st);
+    case 2: return launch_sc_attn<2, 2>(sa, B, st);
+    default: return launch_sc_attn<1, 2>(sa, B, st);
+  }
 }
 
 // Q/K/V projections + SC-guided attention (PointDSC.py:56-64); feat1 = PointCN output
@@ -356,7 +391,7 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
     sa.N = N; sa.tiles = cdiv(N, 128);
     sa.neg_inv_sigma2 = -1.0f / (ctx->sigma_spat * ctx->sigma_spat);
     ProfScope ps(CAT_ATTN_SC, st);
-    cudaError_t e = ctx->sc_impl == 3 ? launch_sc_attn<1, 4>(sa, B, st) : ctx->sc_impl == 2 ? launch_sc_attn<2, 2>(sa, B, st) : launch_sc_attn<1, 2>(sa, B, st);
+    cudaError_t e = launch_sc_any(ctx, sa, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "sc_attn_tc launch");
     return 0;
@@ -485,7 +520,7 @@ int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, co
                   int B, int N, int T, int testing, float* final_trans, float* labels, float* conf_out, int* seeds_out, float* feat_out,
                   cudaStream_t st) {
   const int S = num_seeds(ctx, N), k = eff_k(ctx, N);
-  TRY(run_prep(w, src, tgt, B, N, st));
+  TRY(run_prep(ctx, w, src, tgt, B, N, st));
   {
     ProfScope ps(CAT_PREP, st);
     const long long rows = (long long)B * N;
@@ -840,7 +875,7 @@ int gmf_sc_attention(gmf_ctx* ctx, int layer, const float* feat, const float* sr
   CU(cudaSetDevice(ctx->device));
   Work w;
   TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, 1));
-  TRY(run_prep(w, src, tgt, B, N, (cudaStream_t)stream));
+  TRY(run_prep(ctx, w, src, tgt, B, N, (cudaStream_t)stream));
   return run_sc_attention(ctx, ctx->layers[layer], w, feat, B, N, msg, (cudaStream_t)stream);
 }
 
@@ -852,7 +887,7 @@ int gmf_encoder_layer(gmf_ctx* ctx, int layer, const float* feat_in, const float
   CU(cudaSetDevice(ctx->device));
   Work w;
   TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, T));
-  TRY(run_prep(w, src, tgt, B, N, (cudaStream_t)stream));
+  TRY(run_prep(ctx, w, src, tgt, B, N, (cudaStream_t)stream));
   return run_encoder_layer(ctx, layer, w, feat_in, image_feat, B, N, T, feat_out, (cudaStream_t)stream);
 }
 
@@ -869,7 +904,7 @@ int gmf_pick_seeds(gmf_ctx* ctx, const float* src, const float* confidence, int 
   CU(cudaSetDevice(ctx->device));
   Work w;
   TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, 1));
-  TRY(run_prep(w, src, src, B, N, (cudaStream_t)stream));
+  TRY(run_prep(ctx, w, src, src, B, N, (cudaStream_t)stream));
   return run_pick_seeds(ctx, w, confidence, B, N, num_seeds(ctx, N), use_nms, seeds, (cudaStream_t)stream);
 }
 
@@ -894,7 +929,7 @@ int gmf_score_hypotheses(gmf_ctx* ctx, const float* seed_trans, const float* src
   CU(cudaSetDevice(ctx->device));
   Work w;
   TRY(check_ws(ctx, w, workspace, workspace_bytes, B, N, 1));
-  TRY(run_prep(w, src, tgt, B, N, (cudaStream_t)stream));
+  TRY(run_prep(ctx, w, src, tgt, B, N, (cudaStream_t)stream));
   return run_score(ctx, w, seed_trans, B, N, S, refine, final_trans, final_labels, fitness_counts ? fitness_counts : w.counts, best,
                    pre_refine, (cudaStream_t)stream);
 }
@@ -955,12 +990,12 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
   a.q_t = Q; a.k_t = K; a.vt_t = V; a.out = out; a.Lq = Lq; a.Lk = Lk; a.q_tiles = qt; a.k_tiles = kt;
   cudaError_t e;
   if (sc) {
-    TRY(run_prep(w, src, tgt, B, Lk, st));
+    TRY(run_prep(ctx, w, src, tgt, B, Lk, st, sigma_d));
     if (ctx->sc_impl >= 1) {
       ScAttnArgs sa{};
       sa.q_t = Q; sa.k_t = K; sa.vt_t = V; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = out; sa.N = Lk; sa.tiles = kt;
       sa.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
-      e = ctx->sc_impl == 3 ? launch_sc_attn<1, 4>(sa, B, st) : ctx->sc_impl == 2 ? launch_sc_attn<2, 2>(sa, B, st) : launch_sc_attn<1, 2>(sa, B, st);
+      e = launch_sc_any(ctx, sa, B, st);
     } else {
       a.kpts = w.kpts; a.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
       e = launch_attn<128, true>(a, B, st);

@@ -32,6 +32,7 @@ struct ScAttnArgs {
   float* out;                 // [pairs][N][128] fp32
   int N, tiles;
   float neg_inv_sigma2;
+  long long* trace;           // optional timeline of CTA (0,0): [role 0..3][tile][4] clock64 stamps (GMF_SC_TRACE)
 };
 
 struct ScCfg {

@@ -1,0 +1,335 @@
+// Spatial-consistency guided non-local attention, generation 9 (PointDSC.py:56-64, 216-221).  Same math as gen 8
+// (sc_attn_v8.cuh: S, DA = |ds|^2/sigma^2, DB = 1 - |dt|^2/sigma^2 from the tensor pipe; c = sat(2 sqrt(DA (1 - DB)) + DB - DA);
+// fixed softmax reference with a block-wide "repeat once with the exact row maxima" vote), re-pipelined around the two facts the
+// gen-8 profile exposed (profiles/r01_sc_attention.md):
+//   * with ONE score buffer per softmax group the chain  softmax(v) -> PV_v -> S_{v+2} -> softmax(v+2)  is serial, the two groups
+//     drift into lock step and wait 43 % of the time for the tensor pipe;
+//   * SS-mode MMAs re-read the 128 x 128 Q tile from shared memory for every key tile and are shared-memory bound (48 clk for an
+//     M128 N64 K16 step that needs 32).
+// Gen 9 therefore keeps Q and the query-side distance features in TENSOR MEMORY (A operand from TMEM for every MMA of the kernel;
+// shared memory only streams K / Bd / V^T) and cuts the key tile to 32 columns so that THREE {S | DA | DB} buffers fit:
+//   TMEM columns: buffer b at 96 b: S[0,32) DA[32,64) DB[64,96), P_b aliases S_b[0,16); Q 288..351; Aq 352..383; O 384..511.
+// Scores are issued three tiles ahead (S_{v+3} right after PV_v), so a softmax group always finds its next tile ready.
+// Warps 0-3 / 4-7: softmax groups (even / odd tiles, one thread per score row); 8: producer; 9: P V issuer; 10: score issuer
+// (two issuing warps: a single one spends ~800 cycles per 32-key tile on its serial chain of barrier waits, MMA issue and commits).
+#pragma once
+#include "sc_attn_v8.cuh"
+
+namespace gmf {
+
+struct Sc9Cfg {
+  static constexpr int D = 128, BT = 32, NS = 3, NV = 3;   // ring depth 3 x 64 keys: the MMA issue loop has period 6 tiles
+  static constexpr int K_BYTES = 64 * D * 2, BD_BYTES = 64 * 64 * 2, V_BYTES = D * 64 * 2;   // stages hold 64 keys = two 32-key tiles
+  static constexpr int KSTAGE_BYTES = K_BYTES + BD_BYTES;
+  static constexpr int XCH_BYTES = 2 * 2 * 128 * 4;
+  static constexpr int SMEM = 1024 + NS * KSTAGE_BYTES + NV * V_BYTES + XCH_BYTES + 256;
+  static constexpr int COL_Q = 288, COL_AQ = 352, COL_O = 384;
+  static constexpr float WINDOW = 80.f;
+};
+
+
+// Loop-invariant operands of the MMA issuer.  The issue loop is unrolled over its period (6 tiles = 3 ring stages x 2 sub-tiles =
+// 2 x 3 score buffers) so that every descriptor is "uniform base + compile-time constant": with run-time ring indices the
+// compiler built each descriptor in vector registers and moved it to the uniform file (R2UR) — ~80 issue cycles per MMA, which
+// made the single issuing warp the bottleneck of the whole kernel (gen-9a profile: softmax warps 51 % idle on s_full).
+struct Sc9Mma {
+  uint32_t tmem, idesc_s, idesc_o, leader;
+  uint64_t k_desc0, v_desc0;
+  uint64_t *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_ready, *pv_issued, *o_full;
+  int nt;
+};
+
+// scores + distance accumulators of the tile at period position T (tile index j): stage T/2, sub-tile T&1, buffer T%3
+template <int T>
+__device__ __forceinline__ void sc9_issue_sd(const Sc9Mma& m, int j, uint32_t ring_parity) {
+  using Cfg = Sc9Cfg;
+  constexpr int ST = T >> 1, SUB = T & 1, B = T % 3;
+  if (SUB == 0) { mbar_wait(&m.k_full[ST], ring_parity); tc_fence_after(); }     // the stage's second sub-tile was acquired with the first
+  if (m.leader) {                                                                                    // one lane; every operand is warp-uniform
+    const uint32_t col = m.tmem + B * 96;
+    const uint64_t kd = umma_desc_adv(m.k_desc0, ST * Cfg::KSTAGE_BYTES + SUB * 4096);                // rows 32 SUB .. +31 of each atom
+    const uint64_t bd = umma_desc_adv(m.k_desc0, ST * Cfg::KSTAGE_BYTES + Cfg::K_BYTES + SUB * 4096);
+#pragma unroll
+    for (int at = 0; at < 2; ++at)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        tc_mma_bf16_ts(col, m.tmem + Cfg::COL_Q + at * 32 + ks * 8, umma_desc_adv(kd, at * 8192 + ks * 32), m.idesc_s, (at | ks) ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      tc_mma_bf16_ts(col + 32, m.tmem + Cfg::COL_AQ + ks * 8, umma_desc_adv(bd, ks * 32), m.idesc_s, ks ? 1u : 0u);
+#pragma unroll
+    for (int ks = 2; ks < 4; ++ks)
+      tc_mma_bf16_ts(col + 64, m.tmem + Cfg::COL_AQ + ks * 8, umma_desc_adv(bd, ks * 32), m.idesc_s, ks > 2 ? 1u : 0u);
+    tc_commit(&m.s_full[B]);
+    if (SUB || j == m.nt - 1) tc_commit(&m.k_empty[ST]);
+  }
+  __syncwarp();
+}
+
+// PV issuer (warp 9), tile j = j0 + T: O += P_j V_j, then tell the score issuer that buffer T%3 may be overwritten
+template <int T>
+__device__ __forceinline__ void sc9_pv_step(const Sc9Mma& m, int j0, uint32_t ph) {
+  using Cfg = Sc9Cfg;
+  constexpr int ST = T >> 1, SUB = T & 1, B = T % 3;
+  const int j = j0 + T;
+  if (j >= m.nt) return;
+  if (SUB == 0) mbar_wait2(&m.p_ready[B], T >= 3 ? 1u : 0u, &m.v_full[ST], ph);
+  else mbar_wait(&m.p_ready[B], T >= 3 ? 1u : 0u);
+  tc_fence_after();
+  if (m.leader) {
+    const uint64_t vd = umma_desc_adv(m.v_desc0, ST * Cfg::V_BYTES + SUB * 64);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      tc_mma_bf16_ts(m.tmem + Cfg::COL_O, m.tmem + B * 96 + ks * 8, umma_desc_adv(vd, ks * 32), m.idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+    mbar_arrive(&m.pv_issued[B]);                             // PV_j is in the (in-order) tensor queue
+    if (SUB || j == m.nt - 1) tc_commit(&m.v_empty[ST]);
+    if (j == m.nt - 1) tc_commit(m.o_full);
+  }
+  __syncwarp();
+}
+
+// score issuer (warp 10): S/DA/DB of tile j + 3 go into the buffer P_j vacates, queued behind PV_j
+template <int T>
+__device__ __forceinline__ void sc9_sd_step(const Sc9Mma& m, int j0, uint32_t ph) {
+  constexpr int B = T % 3;
+  const int j = j0 + T;
+  if (j + 3 >= m.nt) return;
+  mbar_wait(&m.pv_issued[B], T >= 3 ? 1u : 0u);
+  sc9_issue_sd<(T + 3) % 6>(m, j + 3, T + 3 < 6 ? ph : ph ^ 1u);
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) {
+  using Cfg = Sc9Cfg;
+  constexpr int D = Cfg::D, BT = Cfg::BT, NS = Cfg::NS, NV = Cfg::NV;
+  constexpr int WP = 8, WM = 9, WS = 10;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sK = smem;                                    // [NS] x {K, Bd} (64 keys)
+  uint8_t* sV = sK + NS * Cfg::KSTAGE_BYTES;             // [NV] x V^T (64 keys)
+  float* sX = (float*)(sV + NV * Cfg::V_BYTES);          // [2][2][128]
+  uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;        // [NS]
+  uint64_t* k_empty = k_full + NS;    // [NS]
+  uint64_t* v_full = k_empty + NS;    // [NV]
+  uint64_t* v_empty = v_full + NV;    // [NV]
+  uint64_t* s_full = v_empty + NV;    // [3]
+  uint64_t* p_ready = s_full + 3;     // [3]
+  uint64_t* pv_issued = p_ready + 3;  // [3]
+  uint64_t* o_full = pv_issued + 3;   // 1
+  uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pair = blockIdx.y, qt = blockIdx.x;
+  const int nt = (a.N + BT - 1) / BT;                     // 32-key tiles
+  const int nw = (a.N + 63) / 64;                         // 64-key stages
+
+  if (tid == 0) {
+    mbar_init(q_full, 256);
+    for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < NV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_issued[i], 1); }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == WP) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int g = warp >> 2;                                  // softmax group
+  const int r = (warp & 3) * 32 + lane;                     // score row == TMEM lane
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  float ref = 0.f, l_sum = 0.f, rmax = -INFINITY;
+  int pass = 0;
+
+  if (warp < 8) {
+    // Q row r (this group's 64-element half) and its distance features -> tensor memory, two bf16 per 32-bit column
+    const size_t tq = (size_t)pair * a.tiles + qt;
+    const uint8_t* qsrc = (const uint8_t*)(a.q_t + tq * (128 * D)) + g * 16384;
+    const uint8_t* asrc = (const uint8_t*)(a.aq_t + tq * (128 * 64));
+    uint32_t w[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(qsrc + swz_off(r, c)));
+      w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+    }
+    tmem_st32(tlane + Cfg::COL_Q + g * 32, w);
+    uint32_t w2[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(asrc + swz_off(r, g * 4 + c)));
+      w2[4 * c] = x.x; w2[4 * c + 1] = x.y; w2[4 * c + 2] = x.z; w2[4 * c + 3] = x.w;
+    }
+    tmem_st16(tlane + Cfg::COL_AQ + g * 16, w2);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(q_full);
+  }
+
+  for (;; ++pass) {
+    int bad = 0;
+    if (warp == WP) {
+      // ------------------------------------ producer (64-key stages) ------------------------------------
+      const uint32_t leader = elect_one() ? 1u : 0u;
+      int wk = 0, wv = 0;
+      const int wend = nw;
+      while (wk < wend || wv < wend) {
+        if (wk < wend && (wv >= wend || wk <= wv + 2)) {
+          const int st = wk % NS, j = wk;
+          if (wk >= NS) mbar_wait(&k_empty[st], ((wk / NS) - 1) & 1);
+          uint8_t* dst = sK + st * Cfg::KSTAGE_BYTES;
+          mbar_expect_tx_p(&k_full[st], Cfg::KSTAGE_BYTES, leader);
+          const size_t tix = (size_t)pair * a.tiles + (j >> 1);
+          const int h = j & 1;
+          const uint8_t* ksrc = (const uint8_t*)(a.k_t + tix * (128 * D)) + h * 8192;
+          bulk_g2s_p(dst, ksrc, 8192, &k_full[st], leader);
+          bulk_g2s_p(dst + 8192, ksrc + 16384, 8192, &k_full[st], leader);
+          bulk_g2s_p(dst + Cfg::K_BYTES, (const uint8_t*)(a.bd_t + tix * (128 * 64)) + h * Cfg::BD_BYTES, Cfg::BD_BYTES, &k_full[st], leader);
+          ++wk;
+        } else {
+          const int sv_ = wv % NV, j = wv;
+          if (wv >= NV) mbar_wait(&v_empty[sv_], ((wv / NV) - 1) & 1);
+          mbar_expect_tx_p(&v_full[sv_], Cfg::V_BYTES, leader);
+          const size_t tix = (size_t)pair * a.tiles + (j >> 1);
+          bulk_g2s_p(sV + sv_ * Cfg::V_BYTES, (const uint8_t*)(a.vt_t + tix * (128 * D)) + (j & 1) * Cfg::V_BYTES, Cfg::V_BYTES, &v_full[sv_], leader);
+          ++wv;
+        }
+      }
+    } else if (warp == WM || warp == WS) {
+      // ------------------------------------ MMA issuers: warp 9 = P V products, warp 10 = scores ------------------------------------
+      Sc9Mma m;
+      m.tmem = __shfl_sync(0xffffffffu, tmem, 0); m.idesc_s = umma_idesc(128, BT, kFmtBF16); m.idesc_o = umma_idesc(128, D, kFmtBF16);
+      m.leader = elect_one() ? 1u : 0u;
+      m.k_desc0 = umma_desc_sw128(smem_u32(sK)); m.v_desc0 = umma_desc_sw128(smem_u32(sV));
+      m.k_full = k_full; m.k_empty = k_empty; m.v_full = v_full; m.v_empty = v_empty; m.s_full = s_full; m.p_ready = p_ready;
+      m.pv_issued = pv_issued; m.o_full = o_full;
+      m.nt = nt;
+      if (warp == WS) {
+        if (pass == 0) { mbar_wait(q_full, 0); tc_fence_after(); }
+        sc9_issue_sd<0>(m, 0, 0u);
+        if (nt > 1) sc9_issue_sd<1>(m, 1, 0u);
+        if (nt > 2) sc9_issue_sd<2>(m, 2, 0u);
+#pragma unroll 1
+        for (int j0 = 0; j0 + 3 < nt; j0 += 6) {
+          const uint32_t ph = (uint32_t)(j0 / 6) & 1u;
+          sc9_sd_step<0>(m, j0, ph); sc9_sd_step<1>(m, j0, ph); sc9_sd_step<2>(m, j0, ph);
+          sc9_sd_step<3>(m, j0, ph); sc9_sd_step<4>(m, j0, ph); sc9_sd_step<5>(m, j0, ph);
+        }
+      } else {
+#pragma unroll 1
+        for (int j0 = 0; j0 < nt; j0 += 6) {
+          const uint32_t ph = (uint32_t)(j0 / 6) & 1u;
+          sc9_pv_step<0>(m, j0, ph); sc9_pv_step<1>(m, j0, ph); sc9_pv_step<2>(m, j0, ph);
+          sc9_pv_step<3>(m, j0, ph); sc9_pv_step<4>(m, j0, ph); sc9_pv_step<5>(m, j0, ph);
+        }
+        mbar_wait(o_full, 0);                                 // every MMA and commit of this pass has retired before the vote
+      }
+    } else {
+      // ------------------------------------ softmax group g: virtual tiles v with (v & 1) == g ------------------------------------
+      float ps0 = 0.f, ps1 = 0.f;
+      for (int j = g; j < nt; j += 2) {
+        const int b = j % 3;
+        const uint32_t tbuf = tlane + (uint32_t)b * 96u;
+        mbar_wait(&s_full[b], (j / 3) & 1);
+        tc_fence_after();
+        const int nvalid = a.N - j * BT;
+        uint32_t us[32], ua[32], ub[32], pk[16];
+        tmem_ld32(tbuf, us); tmem_ld32(tbuf + 32, ua); tmem_ld32(tbuf + 64, ub);
+        tmem_ld_wait();
+        auto tile_body = [&](auto ragged_tag) {
+          constexpr bool RAGGED = decltype(ragged_tag)::value;
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float t0, t1;
+            {
+              const float da = __uint_as_float(ua[c]), db = __uint_as_float(ub[c]);
+              const float rt = sqrt_approx(fabsf(fmaf(-da, db, da)));
+              t0 = fmaf(__uint_as_float(us[c]), __saturatef(fmaf(rt, 2.f, db - da)), -ref);
+            }
+            {
+              const float da = __uint_as_float(ua[c + 1]), db = __uint_as_float(ub[c + 1]);
+              const float rt = sqrt_approx(fabsf(fmaf(-da, db, da)));
+              t1 = fmaf(__uint_as_float(us[c + 1]), __saturatef(fmaf(rt, 2.f, db - da)), -ref);
+            }
+            if (RAGGED) {
+              if (c >= nvalid) t0 = -INFINITY;
+              if (c + 1 >= nvalid) t1 = -INFINITY;
+            }
+            rmax = fmaxf(rmax, fmaxf(t0, t1));
+            const float p0 = (!RAGGED && (c & 3) < POLY) ? ex2_poly(t0) : ex2_approx(t0);
+            const float p1 = (!RAGGED && ((c + 1) & 3) < POLY) ? ex2_poly(t1) : ex2_approx(t1);
+            ps0 += p0; ps1 += p1;
+            pk[c >> 1] = pack_bf16(p0, p1);
+          }
+        };
+        if (nvalid >= BT) tile_body(std::false_type{});
+        else tile_body(std::true_type{});                    // ragged last tile (CTA-uniform)
+        tmem_st16(tbuf, pk);                                 // P over S columns 0..15 (already in registers)
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[b]);
+      }
+      l_sum += ps0 + ps1;
+      sX[g * 128 + r] = rmax;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float comb = fmaxf(rmax, sX[(g ^ 1) * 128 + r]);
+      if (pass == 0 && !(comb >= -Cfg::WINDOW && comb <= Cfg::WINDOW)) { bad = 1; ref = comb; }
+    }
+    const int redo = __syncthreads_or(bad);
+    if (!redo || pass == 1) break;
+    if (bad == 0 && warp < 8) ref = fmaxf(rmax, sX[((warp >> 2) ^ 1) * 128 + r]);   // rows that were fine also move to their exact maximum
+    l_sum = 0.f; rmax = -INFINITY;
+    if (tid == 0) {                                          // every async arrival of the pass has landed (MMA warp waited on o_full): restart the protocol
+      for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+      for (int i = 0; i < NV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+      for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_issued[i], 1); }
+      mbar_init(o_full, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();                                         // also: sX is rewritten by the next pass
+  }
+
+  if (warp < 8) {
+    sX[256 + g * 128 + r] = l_sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv = 1.f / (l_sum + sX[256 + (g ^ 1) * 128 + r]);
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int gq = qt * 128 + r;
+    float* op = a.out + ((size_t)pair * a.N + gq) * D + g * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t u[32];
+      tmem_ld32(tlane + Cfg::COL_O + g * 64 + c * 32, u);
+      tmem_ld_wait();
+      if (gq < a.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(op + c * 32 + 4 * i) =
+              make_float4(__uint_as_float(u[4 * i]) * inv, __uint_as_float(u[4 * i + 1]) * inv,
+                          __uint_as_float(u[4 * i + 2]) * inv, __uint_as_float(u[4 * i + 3]) * inv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WP) tmem_dealloc(tmem, 512);
+}
+
+template <int POLY>
+inline cudaError_t launch_sc_attn_v9(const ScAttnArgs& a, int pairs, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = sc_attn_v9_kernel<POLY>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Sc9Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<dim3(a.tiles, pairs), 352, Sc9Cfg::SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gmf
