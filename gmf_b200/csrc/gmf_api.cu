@@ -196,7 +196,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
-  int sc_impl = 11;         // 11/12/13 = gen-9 kernel (0/1/2 of 4 exponentials on the FMA pipe); 8/9/10 = gen-8; 1/2/3 = gen-7 variants; 0 = SIMT distances
+  int sc_impl = 14;         // gen 9: 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12/13 = 1 thread per row; 8/9/10 = gen 8; 1/2/3 = gen 7; 0 = SIMT distances
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
@@ -366,9 +366,12 @@ cudaError_t launch_sc_any(const gmf_ctx* ctx, const ScAttnArgs& sa_in, int B, cu
 }
 cudaError_t launch_sc_dispatch(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, cudaStream_t st) {
   switch (ctx->sc_impl) {
-    case 11: return launch_sc_attn_v9<0>(sa, B, st);
-    case 12: return launch_sc_attn_v9<1>(sa, B, st);
-    case 13: return launch_sc_attn_v9<2>(sa, B, st);
+    case 11: return launch_sc_attn_v9<0, 1>(sa, B, st);
+    case 12: return launch_sc_attn_v9<1, 1>(sa, B, st);
+    case 13: return launch_sc_attn_v9<2, 1>(sa, B, st);
+    case 14: return launch_sc_attn_v9<0, 2>(sa, B, st);
+    case 15: return launch_sc_attn_v9<1, 2>(sa, B, st);
+    case 16: return launch_sc_attn_v9<2, 2>(sa, B, st);
     case 8: return launch_sc_attn_v8<0>(sa, B, st);
     case 9: return launch_sc_attn_v8<1>(sa, B, st);
     case 10: return launch_sc_attn_v8<2>(sa, B, st);

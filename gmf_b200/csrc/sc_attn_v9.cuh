@@ -8,8 +8,11 @@
 //     M128 N64 K16 step that needs 32).
 // Gen 9 therefore keeps Q and the query-side distance features in TENSOR MEMORY (A operand from TMEM for every MMA of the kernel;
 // shared memory only streams K / Bd / V^T) and cuts the key tile to 32 columns so that THREE {S | DA | DB} buffers fit:
-//   TMEM columns: buffer b at 96 b: S[0,32) DA[32,64) DB[64,96), P_b aliases S_b[0,16); Q 288..351; Aq 352..383; O 384..511.
-// Scores are issued three tiles ahead (S_{v+3} right after PV_v), so a softmax group always finds its next tile ready.
+//   TMEM columns: buffer b at 96 b: S[0,32) DA[32,64) DB[64,96); Q 288..351; P of softmax group g 352+16g; O 384..511.
+// A buffer is handed back to the score issuer as soon as its tile sits in the softmax threads' registers, i.e. S/DA/DB of tile
+// j+3 are computed while tile j is still being exponentiated (P has its own columns; with P aliasing the score buffer the chain
+// softmax -> PV issue -> score issue -> score done was ~700 cycles and set the tile cadence).  The query-side distance features
+// stay in shared memory (4 small SS-mode MMAs per tile) to make room for P.
 // Warps 0-3 / 4-7: softmax groups (even / odd tiles, one thread per score row); 8: producer; 9: P V issuer; 10: score issuer
 // (two issuing warps: a single one spends ~800 cycles per 32-key tile on its serial chain of barrier waits, MMA issue and commits).
 #pragma once
@@ -21,9 +24,10 @@ struct Sc9Cfg {
   static constexpr int D = 128, BT = 32, NS = 3, NV = 3;   // ring depth 3 x 64 keys: the MMA issue loop has period 6 tiles
   static constexpr int K_BYTES = 64 * D * 2, BD_BYTES = 64 * 64 * 2, V_BYTES = D * 64 * 2;   // stages hold 64 keys = two 32-key tiles
   static constexpr int KSTAGE_BYTES = K_BYTES + BD_BYTES;
-  static constexpr int XCH_BYTES = 2 * 2 * 128 * 4;
-  static constexpr int SMEM = 1024 + NS * KSTAGE_BYTES + NV * V_BYTES + XCH_BYTES + 256;
-  static constexpr int COL_Q = 288, COL_AQ = 352, COL_O = 384;
+  static constexpr int XCH_BYTES = 2 * 4 * 128 * 4;       // [max | sum][group x row part][row]
+  static constexpr int AQ_BYTES = 128 * 64 * 2;
+  static constexpr int SMEM = 1024 + AQ_BYTES + NS * KSTAGE_BYTES + NV * V_BYTES + XCH_BYTES + 256;
+  static constexpr int COL_Q = 288, COL_P = 352, COL_O = 384;   // P: 16 columns per softmax group
   static constexpr float WINDOW = 80.f;
 };
 
@@ -34,8 +38,8 @@ struct Sc9Cfg {
 // made the single issuing warp the bottleneck of the whole kernel (gen-9a profile: softmax warps 51 % idle on s_full).
 struct Sc9Mma {
   uint32_t tmem, idesc_s, idesc_o, leader;
-  uint64_t k_desc0, v_desc0;
-  uint64_t *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_ready, *pv_issued, *o_full;
+  uint64_t k_desc0, v_desc0, aq_desc;
+  uint64_t *k_full, *k_empty, *v_full, *v_empty, *s_full, *s_free, *p_ready, *pv_done, *o_full;
   int nt;
 };
 
@@ -56,56 +60,58 @@ __device__ __forceinline__ void sc9_issue_sd(const Sc9Mma& m, int j, uint32_t ri
         tc_mma_bf16_ts(col, m.tmem + Cfg::COL_Q + at * 32 + ks * 8, umma_desc_adv(kd, at * 8192 + ks * 32), m.idesc_s, (at | ks) ? 1u : 0u);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
-      tc_mma_bf16_ts(col + 32, m.tmem + Cfg::COL_AQ + ks * 8, umma_desc_adv(bd, ks * 32), m.idesc_s, ks ? 1u : 0u);
+      tc_mma_bf16(col + 32, umma_desc_adv(m.aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), m.idesc_s, ks ? 1u : 0u);
 #pragma unroll
     for (int ks = 2; ks < 4; ++ks)
-      tc_mma_bf16_ts(col + 64, m.tmem + Cfg::COL_AQ + ks * 8, umma_desc_adv(bd, ks * 32), m.idesc_s, ks > 2 ? 1u : 0u);
+      tc_mma_bf16(col + 64, umma_desc_adv(m.aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), m.idesc_s, ks > 2 ? 1u : 0u);
     tc_commit(&m.s_full[B]);
     if (SUB || j == m.nt - 1) tc_commit(&m.k_empty[ST]);
   }
   __syncwarp();
 }
 
-// PV issuer (warp 9), tile j = j0 + T: O += P_j V_j, then tell the score issuer that buffer T%3 may be overwritten
+// PV issuer (warp 9), tile j = j0 + T: O += P_j V_j with P in its group's own TMEM columns
 template <int T>
 __device__ __forceinline__ void sc9_pv_step(const Sc9Mma& m, int j0, uint32_t ph) {
   using Cfg = Sc9Cfg;
-  constexpr int ST = T >> 1, SUB = T & 1, B = T % 3;
+  constexpr int ST = T >> 1, SUB = T & 1, G = T & 1;
   const int j = j0 + T;
   if (j >= m.nt) return;
-  if (SUB == 0) mbar_wait2(&m.p_ready[B], T >= 3 ? 1u : 0u, &m.v_full[ST], ph);
-  else mbar_wait(&m.p_ready[B], T >= 3 ? 1u : 0u);
+  const uint32_t pp = (uint32_t)(j >> 1) & 1u;                  // p_ready[G] completes once per tile of group G
+  if (SUB == 0) mbar_wait2(&m.p_ready[G], pp, &m.v_full[ST], ph);
+  else mbar_wait(&m.p_ready[G], pp);
   tc_fence_after();
   if (m.leader) {
     const uint64_t vd = umma_desc_adv(m.v_desc0, ST * Cfg::V_BYTES + SUB * 64);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
-      tc_mma_bf16_ts(m.tmem + Cfg::COL_O, m.tmem + B * 96 + ks * 8, umma_desc_adv(vd, ks * 32), m.idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-    mbar_arrive(&m.pv_issued[B]);                             // PV_j is in the (in-order) tensor queue
+      tc_mma_bf16_ts(m.tmem + Cfg::COL_O, m.tmem + Cfg::COL_P + G * 16 + ks * 8, umma_desc_adv(vd, ks * 32), m.idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+    tc_commit(&m.pv_done[G]);                                  // P columns of group G are free again
     if (SUB || j == m.nt - 1) tc_commit(&m.v_empty[ST]);
     if (j == m.nt - 1) tc_commit(m.o_full);
   }
   __syncwarp();
 }
 
-// score issuer (warp 10): S/DA/DB of tile j + 3 go into the buffer P_j vacates, queued behind PV_j
+// score issuer (warp 10): S/DA/DB of tile j + 3 as soon as the softmax group has pulled tile j out of buffer T%3
 template <int T>
 __device__ __forceinline__ void sc9_sd_step(const Sc9Mma& m, int j0, uint32_t ph) {
   constexpr int B = T % 3;
   const int j = j0 + T;
   if (j + 3 >= m.nt) return;
-  mbar_wait(&m.pv_issued[B], T >= 3 ? 1u : 0u);
+  mbar_wait(&m.s_free[B], T >= 3 ? 1u : 0u);
   sc9_issue_sd<(T + 3) % 6>(m, j + 3, T + 3 < 6 ? ph : ph ^ 1u);
 }
 
-template <int POLY>
-__global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) {
+template <int POLY, int TPR>   // TPR softmax threads share a score row (each takes 32 / TPR columns of a tile): 8 TPR softmax warps
+__global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScAttnArgs a) {
   using Cfg = Sc9Cfg;
   constexpr int D = Cfg::D, BT = Cfg::BT, NS = Cfg::NS, NV = Cfg::NV;
-  constexpr int WP = 8, WM = 9, WS = 10;
+  constexpr int NW = 8 * TPR, WP = NW, WM = NW + 1, WS = NW + 2, HC = 32 / TPR, NPART = 2 * TPR;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sK = smem;                                    // [NS] x {K, Bd} (64 keys)
+  uint8_t* sAq = smem;                                   // query-side distance features (SS-mode A operand)
+  uint8_t* sK = sAq + Cfg::AQ_BYTES;                     // [NS] x {K, Bd} (64 keys)
   uint8_t* sV = sK + NS * Cfg::KSTAGE_BYTES;             // [NV] x V^T (64 keys)
   float* sX = (float*)(sV + NV * Cfg::V_BYTES);          // [2][2][128]
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
@@ -115,9 +121,11 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
   uint64_t* v_full = k_empty + NS;    // [NV]
   uint64_t* v_empty = v_full + NV;    // [NV]
   uint64_t* s_full = v_empty + NV;    // [3]
-  uint64_t* p_ready = s_full + 3;     // [3]
-  uint64_t* pv_issued = p_ready + 3;  // [3]
-  uint64_t* o_full = pv_issued + 3;   // 1
+  uint64_t* s_free = s_full + 3;      // [3]
+  uint64_t* p_ready = s_free + 3;     // [2]
+  uint64_t* pv_done = p_ready + 2;    // [2]
+  uint64_t* aq_full = pv_done + 2;    // 1
+  uint64_t* o_full = aq_full + 1;     // 1
   uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -126,11 +134,12 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
   const int nw = (a.N + 63) / 64;                         // 64-key stages
 
   if (tid == 0) {
-    mbar_init(q_full, 256);
+    mbar_init(q_full, NW * 32);
     for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < NV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_issued[i], 1); }
-    mbar_init(o_full, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128 * TPR); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 128 * TPR); mbar_init(&pv_done[i], 1); }
+    mbar_init(o_full, 1); mbar_init(aq_full, 1);
     fence_mbar_init();
   }
   if (warp == WP) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -139,31 +148,26 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const int g = warp >> 2;                                  // softmax group
+  const int g = warp / (4 * TPR);                           // softmax group
+  const int h = (warp >> 2) % TPR;                          // column part inside a tile
+  const int part = g * TPR + h;
   const int r = (warp & 3) * 32 + lane;                     // score row == TMEM lane
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   float ref = 0.f, l_sum = 0.f, rmax = -INFINITY;
   int pass = 0;
 
-  if (warp < 8) {
-    // Q row r (this group's 64-element half) and its distance features -> tensor memory, two bf16 per 32-bit column
+  if (warp < NW) {
+    // this thread's share of Q row r -> tensor memory, two bf16 per 32-bit column (atom g of the swizzled tile image)
     const size_t tq = (size_t)pair * a.tiles + qt;
     const uint8_t* qsrc = (const uint8_t*)(a.q_t + tq * (128 * D)) + g * 16384;
-    const uint8_t* asrc = (const uint8_t*)(a.aq_t + tq * (128 * 64));
-    uint32_t w[32];
+    uint32_t w[HC];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 x = __ldg(reinterpret_cast<const uint4*>(qsrc + swz_off(r, c)));
+    for (int c = 0; c < HC / 4; ++c) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(qsrc + swz_off(r, h * (HC / 4) + c)));
       w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
     }
-    tmem_st32(tlane + Cfg::COL_Q + g * 32, w);
-    uint32_t w2[16];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint4 x = __ldg(reinterpret_cast<const uint4*>(asrc + swz_off(r, g * 4 + c)));
-      w2[4 * c] = x.x; w2[4 * c + 1] = x.y; w2[4 * c + 2] = x.z; w2[4 * c + 3] = x.w;
-    }
-    tmem_st16(tlane + Cfg::COL_AQ + g * 16, w2);
+    if constexpr (TPR == 1) tmem_st32(tlane + Cfg::COL_Q + g * 32, w);
+    else tmem_st16(tlane + Cfg::COL_Q + g * 32 + h * 16, w);
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(q_full);
@@ -174,6 +178,10 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
     if (warp == WP) {
       // ------------------------------------ producer (64-key stages) ------------------------------------
       const uint32_t leader = elect_one() ? 1u : 0u;
+      if (pass == 0) {
+        mbar_expect_tx_p(aq_full, Cfg::AQ_BYTES, leader);
+        bulk_g2s_p(sAq, a.aq_t + ((size_t)pair * a.tiles + qt) * (128 * 64), Cfg::AQ_BYTES, aq_full, leader);
+      }
       int wk = 0, wv = 0;
       const int wend = nw;
       while (wk < wend || wv < wend) {
@@ -203,12 +211,12 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
       Sc9Mma m;
       m.tmem = __shfl_sync(0xffffffffu, tmem, 0); m.idesc_s = umma_idesc(128, BT, kFmtBF16); m.idesc_o = umma_idesc(128, D, kFmtBF16);
       m.leader = elect_one() ? 1u : 0u;
-      m.k_desc0 = umma_desc_sw128(smem_u32(sK)); m.v_desc0 = umma_desc_sw128(smem_u32(sV));
-      m.k_full = k_full; m.k_empty = k_empty; m.v_full = v_full; m.v_empty = v_empty; m.s_full = s_full; m.p_ready = p_ready;
-      m.pv_issued = pv_issued; m.o_full = o_full;
+      m.k_desc0 = umma_desc_sw128(smem_u32(sK)); m.v_desc0 = umma_desc_sw128(smem_u32(sV)); m.aq_desc = umma_desc_sw128(smem_u32(sAq));
+      m.k_full = k_full; m.k_empty = k_empty; m.v_full = v_full; m.v_empty = v_empty; m.s_full = s_full; m.s_free = s_free; m.p_ready = p_ready;
+      m.pv_done = pv_done; m.o_full = o_full;
       m.nt = nt;
       if (warp == WS) {
-        if (pass == 0) { mbar_wait(q_full, 0); tc_fence_after(); }
+        if (pass == 0) { mbar_wait(q_full, 0); mbar_wait(aq_full, 0); tc_fence_after(); }
         sc9_issue_sd<0>(m, 0, 0u);
         if (nt > 1) sc9_issue_sd<1>(m, 1, 0u);
         if (nt > 2) sc9_issue_sd<2>(m, 2, 0u);
@@ -236,13 +244,16 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
         mbar_wait(&s_full[b], (j / 3) & 1);
         tc_fence_after();
         const int nvalid = a.N - j * BT;
-        uint32_t us[32], ua[32], ub[32], pk[16];
-        tmem_ld32(tbuf, us); tmem_ld32(tbuf + 32, ua); tmem_ld32(tbuf + 64, ub);
+        uint32_t us[HC], ua[HC], ub[HC], pk[HC / 2];
+        if constexpr (TPR == 1) { tmem_ld32(tbuf, us); tmem_ld32(tbuf + 32, ua); tmem_ld32(tbuf + 64, ub); }
+        else { tmem_ld16(tbuf + h * 16, us); tmem_ld16(tbuf + 32 + h * 16, ua); tmem_ld16(tbuf + 64 + h * 16, ub); }
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[b]);                             // the score issuer may refill this buffer with tile j + 3
         auto tile_body = [&](auto ragged_tag) {
           constexpr bool RAGGED = decltype(ragged_tag)::value;
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
+          for (int c = 0; c < HC; c += 2) {
             float t0, t1;
             {
               const float da = __uint_as_float(ua[c]), db = __uint_as_float(ub[c]);
@@ -255,8 +266,8 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
               t1 = fmaf(__uint_as_float(us[c + 1]), __saturatef(fmaf(rt, 2.f, db - da)), -ref);
             }
             if (RAGGED) {
-              if (c >= nvalid) t0 = -INFINITY;
-              if (c + 1 >= nvalid) t1 = -INFINITY;
+              if (h * HC + c >= nvalid) t0 = -INFINITY;
+              if (h * HC + c + 1 >= nvalid) t1 = -INFINITY;
             }
             rmax = fmaxf(rmax, fmaxf(t0, t1));
             const float p0 = (!RAGGED && (c & 3) < POLY) ? ex2_poly(t0) : ex2_approx(t0);
@@ -267,43 +278,55 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
         };
         if (nvalid >= BT) tile_body(std::false_type{});
         else tile_body(std::true_type{});                    // ragged last tile (CTA-uniform)
-        tmem_st16(tbuf, pk);                                 // P over S columns 0..15 (already in registers)
+        if (j >= 2) { mbar_wait(&pv_done[g], ((j >> 1) - 1) & 1); tc_fence_after(); }   // P V of this group's previous tile has read the P columns
+        if constexpr (TPR == 1) tmem_st16(tlane + Cfg::COL_P + g * 16, pk);
+        else tmem_st8(tlane + Cfg::COL_P + g * 16 + h * 8, pk);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_ready[b]);
+        mbar_arrive(&p_ready[g]);
       }
       l_sum += ps0 + ps1;
-      sX[g * 128 + r] = rmax;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float comb = fmaxf(rmax, sX[(g ^ 1) * 128 + r]);
+      sX[part * 128 + r] = rmax;
+      asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+      float comb = rmax;
+#pragma unroll
+      for (int o = 1; o < NPART; ++o) comb = fmaxf(comb, sX[((part + o) % NPART) * 128 + r]);
       if (pass == 0 && !(comb >= -Cfg::WINDOW && comb <= Cfg::WINDOW)) { bad = 1; ref = comb; }
     }
     const int redo = __syncthreads_or(bad);
     if (!redo || pass == 1) break;
-    if (bad == 0 && warp < 8) ref = fmaxf(rmax, sX[((warp >> 2) ^ 1) * 128 + r]);   // rows that were fine also move to their exact maximum
+    if (bad == 0 && warp < NW) {                             // rows that were fine also move to their exact maximum
+      ref = rmax;
+#pragma unroll
+      for (int o = 1; o < NPART; ++o) ref = fmaxf(ref, sX[((part + o) % NPART) * 128 + r]);
+    }
     l_sum = 0.f; rmax = -INFINITY;
     if (tid == 0) {                                          // every async arrival of the pass has landed (MMA warp waited on o_full): restart the protocol
       for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
       for (int i = 0; i < NV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-      for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_issued[i], 1); }
+      for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128 * TPR); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 128 * TPR); mbar_init(&pv_done[i], 1); }
       mbar_init(o_full, 1);
       fence_mbar_init();
     }
     __syncthreads();                                         // also: sX is rewritten by the next pass
   }
 
-  if (warp < 8) {
-    sX[256 + g * 128 + r] = l_sum;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float inv = 1.f / (l_sum + sX[256 + (g ^ 1) * 128 + r]);
+  if (warp < NW) {
+    sX[512 + part * 128 + r] = l_sum;
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+#pragma unroll
+    for (int o = 1; o < NPART; ++o) l_sum += sX[512 + ((part + o) % NPART) * 128 + r];
+    const float inv = 1.f / l_sum;
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int gq = qt * 128 + r;
-    float* op = a.out + ((size_t)pair * a.N + gq) * D + g * 64;
+    constexpr int OC = D / NPART;                             // output columns per thread
+    float* op = a.out + ((size_t)pair * a.N + gq) * D + part * OC;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < OC / 32; ++c) {
       uint32_t u[32];
-      tmem_ld32(tlane + Cfg::COL_O + g * 64 + c * 32, u);
+      tmem_ld32(tlane + Cfg::COL_O + part * OC + c * 32, u);
       tmem_ld_wait();
       if (gq < a.N) {
 #pragma unroll
@@ -319,16 +342,16 @@ __global__ void __launch_bounds__(352, 1) sc_attn_v9_kernel(const ScAttnArgs a) 
   if (warp == WP) tmem_dealloc(tmem, 512);
 }
 
-template <int POLY>
+template <int POLY, int TPR>
 inline cudaError_t launch_sc_attn_v9(const ScAttnArgs& a, int pairs, cudaStream_t st) {
   static bool configured = false;
-  auto kern = sc_attn_v9_kernel<POLY>;
+  auto kern = sc_attn_v9_kernel<POLY, TPR>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Sc9Cfg::SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<dim3(a.tiles, pairs), 352, Sc9Cfg::SMEM, st>>>(a);
+  kern<<<dim3(a.tiles, pairs), 256 * TPR + 96, Sc9Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
