@@ -1,0 +1,295 @@
+// Fusion cross-attention (Fusion-1 / Fusion-2, fusion_layer.py:82-94), head dim 64:  out = softmax(q k^T / 8) v, generation 2.
+// Same recipe as the gen-9 SC kernel (sc_attn_v9.cuh; measurements in profiles/r01_sc_attention.md):
+//   * every MMA takes its A operand from TENSOR MEMORY: Q (written once per CTA) for the scores, bf16 P for P.V — shared memory
+//     only streams K and V^T, so an M128 N64 K16 step costs 32 clk instead of the shared-memory-bound 48;
+//   * fixed softmax reference per pass (0 first) + block-wide "repeat once with the exact row maxima" vote instead of a per-tile
+//     maximum exchange / accumulator rescale;
+//   * a score buffer is handed back to the issuer as soon as its tile is in registers (scores run two key tiles ahead);
+//   * MMA issue loops unrolled over the ring period with warp-uniform operands, issued from an elected lane.
+// CTA = TWO 128-query row tiles of one pair sharing the K / V^T stream (halves the L2 -> SM traffic).  The row tiles are
+// independent pipelines: 8 softmax warps (two threads per score row, 32 columns each), one P.V issuer warp and one score issuer
+// warp per row tile; one producer warp.  21 warps.
+// TMEM (512 columns): S[t][b] at 64 (2t + b) | O[t] at 256 + 64 t | P[t] at 384 + 32 t | Q[t] at 448 + 32 t.
+#pragma once
+#include "attn_tc.cuh"
+#include "sc_attn_v8.cuh"
+
+namespace gmf {
+
+struct Fa2Cfg {
+  static constexpr int D = 64, BN = 64, NR = 4;                 // NR: K ring depth = V^T ring depth = unroll period
+  static constexpr int K_BYTES = BN * D * 2, V_BYTES = D * BN * 2;
+  static constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;         // [max | sum][row tile][half][row]
+  static constexpr int SMEM = 1024 + NR * K_BYTES + NR * V_BYTES + XCH_BYTES + 512;
+  static constexpr int COL_O = 256, COL_P = 384, COL_Q = 448;
+  static constexpr float WINDOW = 80.f;
+};
+
+struct Fa2Mma {
+  uint32_t tmem, idesc, leader;
+  uint64_t k_desc0, v_desc0;
+  uint64_t *k_full, *k_empty, *v_full, *v_empty, *s_full, *s_free, *p_ready, *pv_done, *o_full;
+  int nt, t;                                                   // key tiles, this issuer's row tile
+};
+
+// S[t][T&1] = Q_t K_j^T for the key tile at ring position T
+template <int T>
+__device__ __forceinline__ void fa2_issue_s(const Fa2Mma& m, uint32_t ring_parity) {
+  using Cfg = Fa2Cfg;
+  mbar_wait(&m.k_full[T], ring_parity);
+  tc_fence_after();
+  if (m.leader) {
+    const uint32_t col = m.tmem + (uint32_t)(2 * m.t + (T & 1)) * 64u;
+    const uint32_t qcol = m.tmem + Cfg::COL_Q + (uint32_t)m.t * 32u;
+    const uint64_t kd = umma_desc_adv(m.k_desc0, T * Cfg::K_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) tc_mma_bf16_ts(col, qcol + ks * 8, umma_desc_adv(kd, ks * 32), m.idesc, ks ? 1u : 0u);
+    tc_commit(&m.s_full[2 * m.t + (T & 1)]);
+    tc_commit(&m.k_empty[T]);
+  }
+  __syncwarp();
+}
+
+template <int T>
+__device__ __forceinline__ void fa2_s_step(const Fa2Mma& m, int j0, uint32_t ph) {
+  const int j = j0 + T;
+  if (j + 2 >= m.nt) return;
+  mbar_wait(&m.s_free[2 * m.t + (T & 1)], (T >> 1) & 1);       // softmax pulled tile j out of buffer T&1
+  fa2_issue_s<(T + 2) % 4>(m, T + 2 < 4 ? ph : ph ^ 1u);
+}
+
+template <int T>
+__device__ __forceinline__ void fa2_pv_step(const Fa2Mma& m, int j0, uint32_t ph) {
+  using Cfg = Fa2Cfg;
+  const int j = j0 + T;
+  if (j >= m.nt) return;
+  mbar_wait2(&m.p_ready[m.t], T & 1, &m.v_full[T], ph);
+  tc_fence_after();
+  if (m.leader) {
+    const uint32_t pcol = m.tmem + Cfg::COL_P + (uint32_t)m.t * 32u;
+    const uint64_t vd = umma_desc_adv(m.v_desc0, T * Cfg::V_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      tc_mma_bf16_ts(m.tmem + Cfg::COL_O + (uint32_t)m.t * 64u, pcol + ks * 8, umma_desc_adv(vd, ks * 32), m.idesc, (j > 0 || ks > 0) ? 1u : 0u);
+    tc_commit(&m.pv_done[m.t]);
+    tc_commit(&m.v_empty[T]);
+    if (j == m.nt - 1) tc_commit(&m.o_full[m.t]);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
+  using Cfg = Fa2Cfg;
+  constexpr int D = Cfg::D, BN = Cfg::BN, NR = Cfg::NR;
+  constexpr int WP = 16;                                        // producer; 17,18: P.V issuers; 19,20: score issuers
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sK = smem;                                    // [NR] x K (64 keys x 64)
+  uint8_t* sV = sK + NR * Cfg::K_BYTES;                  // [NR] x V^T (64 x 64 keys)
+  float* sX = (float*)(sV + NR * Cfg::V_BYTES);          // [2][2][2][128]
+  uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* k_full = bars + 2;        // [NR]
+  uint64_t* k_empty = k_full + NR;    // [NR]
+  uint64_t* v_full = k_empty + NR;    // [NR]
+  uint64_t* v_empty = v_full + NR;    // [NR]
+  uint64_t* s_full = v_empty + NR;    // [2][2]
+  uint64_t* s_free = s_full + 4;      // [2][2]
+  uint64_t* p_ready = s_free + 4;     // [2]
+  uint64_t* pv_done = p_ready + 2;    // [2]
+  uint64_t* o_full = pv_done + 2;     // [2]
+  uint32_t* tmem_slot = (uint32_t*)(o_full + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pair = blockIdx.y;
+  const int qt0 = blockIdx.x * 2;
+  const int ntile = (qt0 + 1 < a.q_tiles) ? 2 : 1;                  // active row tiles
+  const int nt = (a.Lk + BN - 1) / BN;
+
+  auto init_bars = [&]() {
+    for (int i = 0; i < NR; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], ntile); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], ntile); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 256); mbar_init(&pv_done[i], 1); mbar_init(&o_full[i], 1); }
+  };
+  if (tid == 0) {
+    mbar_init(&q_full[0], 256); mbar_init(&q_full[1], 256);
+    init_bars();
+    fence_mbar_init();
+  }
+  if (warp == WP) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int t = (warp >> 3) & 1;                            // softmax warps: row tile
+  const int h = (warp >> 2) & 1;                            // column half of a key tile
+  const int r = (warp & 3) * 32 + lane;                     // row in tile == TMEM lane
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const bool softmax_role = warp < 16 && t < ntile;
+  float ref = 0.f, l_sum = 0.f, rmax = -INFINITY;
+  int pass = 0;
+
+  if (softmax_role) {
+    // this thread's half of Q row r -> tensor memory (two bf16 per 32-bit column)
+    const uint8_t* qsrc = (const uint8_t*)(a.q_t + (size_t)(pair * a.q_tiles + qt0 + t) * (128 * D));
+    uint32_t w[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(qsrc + swz_off(r, h * 4 + c)));
+      w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+    }
+    tmem_st16(tlane + Cfg::COL_Q + t * 32 + h * 16, w);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&q_full[t]);
+  }
+
+  for (;; ++pass) {
+    int bad = 0;
+    if (warp == WP) {
+      // ------------------------------------ producer ------------------------------------
+      const uint32_t leader = elect_one() ? 1u : 0u;
+      for (int j = 0; j < nt; ++j) {
+        const int st = j % NR;
+        const size_t tix = (size_t)pair * a.k_tiles + (j >> 1);
+        const int hh = j & 1;
+        if (j >= NR) mbar_wait(&k_empty[st], ((j / NR) - 1) & 1);
+        mbar_expect_tx_p(&k_full[st], Cfg::K_BYTES, leader);
+        bulk_g2s_p(sK + st * Cfg::K_BYTES, (const uint8_t*)(a.k_t + tix * (128 * D)) + hh * Cfg::K_BYTES, Cfg::K_BYTES, &k_full[st], leader);
+        // V^T of tile j - 1 (needed one softmax period after its K): the producer never blocks on V before the K that is due first
+        if (j >= 1) {
+          const int jv = j - 1, sv = jv % NR;
+          const size_t tv = (size_t)pair * a.k_tiles + (jv >> 1);
+          if (jv >= NR) mbar_wait(&v_empty[sv], ((jv / NR) - 1) & 1);
+          mbar_expect_tx_p(&v_full[sv], Cfg::V_BYTES, leader);
+          bulk_g2s_p(sV + sv * Cfg::V_BYTES, (const uint8_t*)(a.vt_t + tv * (128 * D)) + (jv & 1) * Cfg::V_BYTES, Cfg::V_BYTES, &v_full[sv], leader);
+        }
+      }
+      {
+        const int jv = nt - 1, sv = jv % NR;
+        const size_t tv = (size_t)pair * a.k_tiles + (jv >> 1);
+        if (jv >= NR) mbar_wait(&v_empty[sv], ((jv / NR) - 1) & 1);
+        mbar_expect_tx_p(&v_full[sv], Cfg::V_BYTES, leader);
+        bulk_g2s_p(sV + sv * Cfg::V_BYTES, (const uint8_t*)(a.vt_t + tv * (128 * D)) + (jv & 1) * Cfg::V_BYTES, Cfg::V_BYTES, &v_full[sv], leader);
+      }
+    } else if (warp > WP) {
+      // ------------------------------------ MMA issuers ------------------------------------
+      Fa2Mma m;
+      m.t = (warp - 17) & 1;
+      const bool is_pv = warp < 19;
+      m.tmem = __shfl_sync(0xffffffffu, tmem, 0); m.idesc = umma_idesc(128, BN, kFmtBF16);
+      m.leader = elect_one() ? 1u : 0u;
+      m.k_desc0 = umma_desc_sw128(smem_u32(sK)); m.v_desc0 = umma_desc_sw128(smem_u32(sV));
+      m.k_full = k_full; m.k_empty = k_empty; m.v_full = v_full; m.v_empty = v_empty; m.s_full = s_full; m.s_free = s_free;
+      m.p_ready = p_ready; m.pv_done = pv_done; m.o_full = o_full; m.nt = nt;
+      if (m.t < ntile) {
+        if (!is_pv) {
+          if (pass == 0) { mbar_wait(&q_full[m.t], 0); tc_fence_after(); }
+          fa2_issue_s<0>(m, 0u);
+          if (nt > 1) fa2_issue_s<1>(m, 0u);
+#pragma unroll 1
+          for (int j0 = 0; j0 + 2 < nt; j0 += 4) {
+            const uint32_t ph = (uint32_t)(j0 / 4) & 1u;
+            fa2_s_step<0>(m, j0, ph); fa2_s_step<1>(m, j0, ph); fa2_s_step<2>(m, j0, ph); fa2_s_step<3>(m, j0, ph);
+          }
+        } else {
+#pragma unroll 1
+          for (int j0 = 0; j0 < nt; j0 += 4) {
+            const uint32_t ph = (uint32_t)(j0 / 4) & 1u;
+            fa2_pv_step<0>(m, j0, ph); fa2_pv_step<1>(m, j0, ph); fa2_pv_step<2>(m, j0, ph); fa2_pv_step<3>(m, j0, ph);
+          }
+          mbar_wait(&o_full[m.t], 0);                           // every MMA and commit of this row tile has retired before the vote
+        }
+      }
+    } else if (softmax_role) {
+      // ------------------------------------ softmax: row tile t, column half h ------------------------------------
+      float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+      for (int j = 0; j < nt; ++j) {
+        const int b = j & 1;
+        mbar_wait(&s_full[2 * t + b], (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t us[32], pk[16];
+        tmem_ld32(tlane + (uint32_t)(2 * t + b) * 64u + h * 32, us);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[2 * t + b]);                     // the score issuer may refill this buffer with tile j + 2
+        const int nvalid = a.Lk - j * BN - h * 32;
+        if (nvalid >= 32) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float t0 = __uint_as_float(us[c]) - ref, t1 = __uint_as_float(us[c + 1]) - ref;
+            const float t2 = __uint_as_float(us[c + 2]) - ref, t3 = __uint_as_float(us[c + 3]) - ref;
+            rmax = fmaxf(rmax, fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)));
+            const float p0 = ex2_approx(t0), p1 = ex2_approx(t1), p2 = ex2_approx(t2), p3 = ex2_approx(t3);
+            ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+            pk[c >> 1] = pack_bf16(p0, p1); pk[(c >> 1) + 1] = pack_bf16(p2, p3);
+          }
+        } else {                                             // ragged last key tile (warp-uniform)
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float t0 = c < nvalid ? __uint_as_float(us[c]) - ref : -INFINITY;
+            const float t1 = c + 1 < nvalid ? __uint_as_float(us[c + 1]) - ref : -INFINITY;
+            rmax = fmaxf(rmax, fmaxf(t0, t1));
+            const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+            ps0 += p0; ps1 += p1;
+            pk[c >> 1] = pack_bf16(p0, p1);
+          }
+        }
+        if (j >= 1) { mbar_wait(&pv_done[t], (j - 1) & 1); tc_fence_after(); }     // P.V of the previous tile has read the P columns
+        tmem_st16(tlane + Cfg::COL_P + t * 32 + h * 16, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[t]);
+      }
+      l_sum += (ps0 + ps1) + (ps2 + ps3);
+      sX[(t * 2 + h) * 128 + r] = rmax;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      const float comb = fmaxf(rmax, sX[(t * 2 + (h ^ 1)) * 128 + r]);
+      if (pass == 0 && !(comb >= -Cfg::WINDOW && comb <= Cfg::WINDOW)) bad = 1;
+      rmax = comb;
+    }
+    const int redo = __syncthreads_or(bad);
+    if (!redo || pass == 1) break;
+    ref = rmax;                                              // exact row maximum (softmax threads; unused elsewhere)
+    l_sum = 0.f; rmax = -INFINITY;
+    if (tid == 0) { init_bars(); fence_mbar_init(); }        // every async arrival of the pass has landed (issuers waited on o_full)
+    __syncthreads();
+  }
+
+  if (softmax_role) {
+    sX[512 + (t * 2 + h) * 128 + r] = l_sum;
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+    const float inv = 1.f / (l_sum + sX[512 + (t * 2 + (h ^ 1)) * 128 + r]);
+    mbar_wait(&o_full[t], 0);
+    tc_fence_after();
+    const int gq = (qt0 + t) * 128 + r;
+    float* op = a.out + ((size_t)pair * a.Lq + gq) * D + h * 32;
+    uint32_t u[32];
+    tmem_ld32(tlane + Cfg::COL_O + t * 64 + h * 32, u);
+    tmem_ld_wait();
+    if (gq < a.Lq) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(op + 4 * i) =
+            make_float4(__uint_as_float(u[4 * i]) * inv, __uint_as_float(u[4 * i + 1]) * inv,
+                        __uint_as_float(u[4 * i + 2]) * inv, __uint_as_float(u[4 * i + 3]) * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WP) tmem_dealloc(tmem, 512);
+}
+
+inline cudaError_t launch_fus_attn_v2(const AttnArgs& a, int pairs, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fus_attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa2Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  fus_attn_v2_kernel<<<dim3((a.q_tiles + 1) / 2, pairs), 672, Fa2Cfg::SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gmf

@@ -14,6 +14,7 @@
 #include "sc_attn_tc.cuh"
 #include "sc_attn_v8.cuh"
 #include "sc_attn_v9.cuh"
+#include "fus_attn_v2.cuh"
 #include "tail.cuh"
 
 using namespace gmf;
@@ -196,6 +197,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
+  int fus_impl = 2;         // 2 = gen-2 fusion attention (Q/P in TMEM, fixed reference), 1 = gen 1
   int sc_impl = 14;         // gen 9: 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12/13 = 1 thread per row; 8/9/10 = gen 8; 1/2/3 = gen 7; 0 = SIMT distances
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
@@ -286,7 +288,7 @@ LinArgs lin(const float* x, int L, const float* w, const float* bias) {
 }
 
 // FusionLayer.forward (fusion_layer.py:172-201)
-int run_fusion(const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st) {
+int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st) {
   const float* resid0 = xq;
   {  // queries: (CPE) -> LN -> to_q  => bf16 Q tiles (scale folded)
     LinArgs a = lin(xq, Lq, f.wq, nullptr);
@@ -313,9 +315,9 @@ int run_fusion(const FusionW& f, Work& w, const float* xq, const float* ctxk, in
     a.q_t = w.qf; a.k_t = w.kf; a.vt_t = w.vtf; a.out = w.of;
     a.Lq = Lq; a.Lk = Lk; a.q_tiles = cdiv(Lq, 128); a.k_tiles = cdiv(Lk, 128);
     ProfScope ps(CAT_ATTN_FUS, st);
-    cudaError_t e = launch_attn<64, false>(a, B, st);
+    cudaError_t e = ctx->fus_impl >= 2 ? launch_fus_attn_v2(a, B, st) : launch_attn<64, false>(a, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (e != cudaSuccess) return fail_cuda(e, "attn_tc<64> launch");
+    if (e != cudaSuccess) return fail_cuda(e, "fusion attention launch");
   }
   {  // to_out + bias + residual
     LinArgs a = lin(w.of, Lq, f.wo, f.bo);
@@ -430,7 +432,7 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     a.out = w.m2;
     TRY((run_linear<64, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
   }
-  TRY(run_fusion(lw.f2, w, w.feat1, image_feat, B, N, T, w.x2, st));
+  TRY(run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, w.x2, st));
   {
     LinArgs a = lin(w.m2, N, lw.fc3_w, lw.fc3_b);
     a.residual = w.x2; a.out = feat_out;
@@ -531,7 +533,7 @@ int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, co
     LAUNCHED();
   }
   // Fusion-1: queries = q-image tokens, context = p-image tokens (PointDSC.py:137)
-  TRY(run_fusion(ctx->f1, w, q_tok, p_tok, B, T, T, w.imgfeat, st));
+  TRY(run_fusion(ctx, ctx->f1, w, q_tok, p_tok, B, T, T, w.imgfeat, st));
   for (int li = 0; li < ctx->cfg.num_layers; ++li) TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st));
   if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
   TRY(run_classify(ctx, w.featA, (long long)B * N, w.normed, conf_out, st));
@@ -636,6 +638,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   c->cfg = *cfg;
   if (const char* e = getenv("GMF_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, atoi(e));
   if (const char* e = getenv("GMF_SC_IMPL")) c->sc_impl = atoi(e);
+  if (const char* e = getenv("GMF_FUS_IMPL")) c->fus_impl = atoi(e);
   *out = c;
   return 0;
 }
@@ -867,7 +870,7 @@ int gmf_fusion_layer(gmf_ctx* ctx, int layer, const float* queries, const float*
   CU(cudaSetDevice(ctx->device));
   Work w;
   TRY(check_ws(ctx, w, workspace, workspace_bytes, B, std::max(Lq, 2), Lk));
-  return run_fusion(layer < 0 ? ctx->f1 : ctx->layers[layer].f2, w, queries, context, B, Lq, Lk, out, (cudaStream_t)stream);
+  return run_fusion(ctx, layer < 0 ? ctx->f1 : ctx->layers[layer].f2, w, queries, context, B, Lq, Lk, out, (cudaStream_t)stream);
 }
 
 int gmf_sc_attention(gmf_ctx* ctx, int layer, const float* feat, const float* src, const float* tgt, int B, int N, float* msg,
@@ -1004,7 +1007,7 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
       e = launch_attn<128, true>(a, B, st);
     }
   } else {
-    e = launch_attn<64, false>(a, B, st);
+    e = ctx->fus_impl >= 2 ? launch_fus_attn_v2(a, B, st) : launch_attn<64, false>(a, B, st);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail_cuda(e, "attn launch");
