@@ -164,6 +164,14 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       : "memory");
 }
 
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 // Predicated single-lane variants for warp-converged role code: every lane executes the call, only the lane with
 // `on != 0` (from elect_one()) issues.  Keeping the call site convergent lets the compiler keep the descriptors in uniform
 // registers instead of emitting a per-lane serialisation loop around every UTCHMMA.

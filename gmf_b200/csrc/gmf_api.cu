@@ -15,6 +15,7 @@
 #include "sc_attn_v8.cuh"
 #include "sc_attn_v9.cuh"
 #include "fus_attn_v2.cuh"
+#include "ffn_fused.cuh"
 #include "tail.cuh"
 
 using namespace gmf;
@@ -178,6 +179,7 @@ struct FusionW {
   const float *cpe_q_w = nullptr, *cpe_q_b = nullptr, *cpe_c_w = nullptr, *cpe_c_b = nullptr;
   const float *lnq_g, *lnq_b, *lnc_g, *lnc_b, *lnf_g, *lnf_b;
   const float *wq, *wkv, *wo, *bo, *w1, *b1, *w2, *b2;
+  const float *w1f, *w2f;   // fused-FFN packing (8 passes of 64 hidden columns)
 };
 struct LayerW {
   const float *pcn_w, *pcn_b, *qkv_w, *qkv_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
@@ -197,6 +199,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
+  int ffn_impl = 2;         // 2 = fused GEGLU FFN kernel (hidden activation stays on chip), 1 = two linear kernels
   int fus_impl = 2;         // 2 = gen-2 fusion attention (Q/P in TMEM, fixed reference), 1 = gen 1
   int sc_impl = 14;         // gen 9: 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12/13 = 1 thread per row; 8/9/10 = gen 8; 1/2/3 = gen 7; 0 = SIMT distances
   // staging for the host-buffer entry point
@@ -323,6 +326,16 @@ int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, c
     LinArgs a = lin(w.of, Lq, f.wo, f.bo);
     a.residual = resid0; a.out = w.x1;
     TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st, CAT_OUT64)));
+  }
+  if (ctx->ffn_impl >= 2) {   // LN -> Linear(128,1024) -> GEGLU -> Linear(512,128) + bias + residual, hidden activation on chip
+    FfnArgs a{};
+    a.x = w.x1; a.L = Lq; a.tiles = cdiv(Lq, 128); a.ln_g = f.lnf_g; a.ln_b = f.lnf_b;
+    a.w1_packed = f.w1f; a.b1 = f.b1; a.w2_packed = f.w2f; a.b2 = f.b2; a.out = out;
+    ProfScope ps(CAT_FFN1, st);
+    cudaError_t e = launch_ffn_fused(a, B, st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail_cuda(e, "ffn_fused launch");
+    return 0;
   }
   {  // LN -> Linear(128,1024) -> GEGLU => tiled activation image
     LinArgs a = lin(w.x1, Lq, f.w1, f.b1);
@@ -639,6 +652,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   if (const char* e = getenv("GMF_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, atoi(e));
   if (const char* e = getenv("GMF_SC_IMPL")) c->sc_impl = atoi(e);
   if (const char* e = getenv("GMF_FUS_IMPL")) c->fus_impl = atoi(e);
+  if (const char* e = getenv("GMF_FFN_IMPL")) c->ffn_impl = atoi(e);
   *out = c;
   return 0;
 }
@@ -673,7 +687,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
   auto vec = [](const float* p, size_t n) { return std::vector<float>(p, p + n); };
 
   Blob blob;
-  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wkv, wo, bo, w1, b1, w2, b2; };
+  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wkv, wo, bo, w1, b1, w2, b2, w1f, w2f; };
   auto pack_fusion = [&](bool pe) {
     FusionOff o{};
     o.pe = pe;
@@ -686,8 +700,8 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     std::vector<float> wq = vec(next("to_q.weight"), 64 * 128);
     const float qs = kLog2e / 8.0f;   // dim_head ** -0.5 (fusion_layer.py:76) in log2 units
     for (auto& v : wq) v *= qs;
-    o.wq = blob.push(pack_linear(wq, 64, 128, 128, 64));
-    o.wkv = blob.push(pack_linear(vec(next("to_kv.weight"), 128 * 128), 128, 128, 128, 128));
+    o.wq = blob.push(pack_linear(wq, 64, 128, 32, 64));
+    o.wkv = blob.push(pack_linear(vec(next("to_kv.weight"), 128 * 128), 128, 128, 32, 128));
     o.wo = blob.push(pack_linear(vec(next("to_out.weight"), 128 * 64), 128, 64, 64, 128));
     o.bo = blob.push(next("to_out.bias"), 128);
     o.lfg = blob.push(next("1.norm.weight"), 128); o.lfb = blob.push(next("1.norm.bias"), 128);
@@ -695,9 +709,16 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     for (int p = 0; p < 4; ++p)
       for (int nbi = 0; nbi < 2; ++nbi)
         for (int n = 0; n < 128; ++n) rowmap[(p * 2 + nbi) * 128 + n] = (nbi ? 512 : 0) + p * 128 + n;
-    o.w1 = blob.push(pack_linear(vec(next("net.0.weight"), 1024 * 128), 1024, 128, 64, 128, &rowmap));
+    const std::vector<float> W1 = vec(next("net.0.weight"), 1024 * 128);
+    o.w1 = blob.push(pack_linear(W1, 1024, 128, 64, 128, &rowmap));
+    std::vector<int> rowmap8(1024);     // fused FFN: pass p = [value rows 64p.., gate rows 512+64p..]
+    for (int p = 0; p < 8; ++p)
+      for (int n = 0; n < 128; ++n) rowmap8[p * 128 + n] = n < 64 ? p * 64 + n : 512 + p * 64 + (n - 64);
+    o.w1f = blob.push(pack_linear(W1, 1024, 128, 64, 128, &rowmap8));
     o.b1 = blob.push(next("net.0.bias"), 1024);
-    o.w2 = blob.push(pack_linear(vec(next("net.2.weight"), 128 * 512), 128, 512, 64, 128));
+    const std::vector<float> W2 = vec(next("net.2.weight"), 128 * 512);
+    o.w2 = blob.push(pack_linear(W2, 128, 512, 32, 128));
+    o.w2f = blob.push(pack_linear(W2, 128, 512, 64, 128));
     o.b2 = blob.push(next("net.2.bias"), 128);
     return o;
   };
@@ -723,14 +744,14 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
       std::vector<float> W = vec(next("0.weight"), 128 * 128), b = vec(next("0.bias"), 128);
       const float *g = next("1.weight"), *be = next("1.bias"), *mu = next("1.running_mean"), *va = next("1.running_var");
       fold_bn(W, b, 128, 128, g, be, mu, va);
-      o.pw = blob.push(pack_linear(W, 128, 128, 128, 128)); o.pb = blob.push(b);
+      o.pw = blob.push(pack_linear(W, 128, 128, 32, 128)); o.pb = blob.push(b);
     }
     {
       std::vector<float> W = vec(next("fc_message.0.weight"), 64 * 128), b = vec(next("fc_message.0.bias"), 64);
       const float *g = next("fc_message.1.weight"), *be = next("fc_message.1.bias"), *mu = next("fc_message.1.running_mean"),
                   *va = next("fc_message.1.running_var");
       fold_bn(W, b, 64, 128, g, be, mu, va);
-      o.f1w = blob.push(pack_linear(W, 64, 128, 128, 64)); o.f1b = blob.push(b);
+      o.f1w = blob.push(pack_linear(W, 64, 128, 32, 64)); o.f1b = blob.push(b);
     }
     {
       std::vector<float> W = vec(next("fc_message.3.weight"), 64 * 64), b = vec(next("fc_message.3.bias"), 64);
@@ -771,6 +792,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     if (o.pe) { f.cpe_q_w = d + o.cqw; f.cpe_q_b = d + o.cqb; f.cpe_c_w = d + o.ccw; f.cpe_c_b = d + o.ccb; }
     f.lnq_g = d + o.lqg; f.lnq_b = d + o.lqb; f.lnc_g = d + o.lcg; f.lnc_b = d + o.lcb; f.lnf_g = d + o.lfg; f.lnf_b = d + o.lfb;
     f.wq = d + o.wq; f.wkv = d + o.wkv; f.wo = d + o.wo; f.bo = d + o.bo; f.w1 = d + o.w1; f.b1 = d + o.b1; f.w2 = d + o.w2; f.b2 = d + o.b2;
+    f.w1f = d + o.w1f; f.w2f = d + o.w2f;
     return f;
   };
   ctx->sigma = sigma; ctx->sigma_spat = sigma_spat;
@@ -956,7 +978,7 @@ int gmf_debug_linear(gmf_ctx* ctx, const float* x, const float* w_host, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = nout >= 128 ? 128 : nout;
   std::vector<float> W(w_host, w_host + (size_t)nout * k);
-  std::vector<float> packed = pack_linear(W, nout, k, k, nb);
+  std::vector<float> packed = pack_linear(W, nout, k, k >= 128 ? 32 : k, nb);
   float *dw = nullptr, *db = nullptr;
   CU(cudaMalloc(&dw, packed.size() * 4));
   CU(cudaMalloc(&db, (size_t)nout * 4));

@@ -40,8 +40,12 @@ struct LinArgs {
 
 template <int K, int NOUT, int PRO>
 struct LinCfg {
-  static constexpr bool STREAM = (PRO == PRO_TILED) || (NOUT > 128);   // weights arrive as a stream of chunks
-  static constexpr int KCH = STREAM ? 64 : K;                           // K extent of one weight chunk
+  // "LIGHT" kernels (one accumulator block of <= 128 columns) are HBM/latency bound: they are sized for TWO CTAs per SM
+  // (<= 113 KB shared memory, <= 256 TMEM columns, <= 113 registers) so that one tile's global loads / epilogue stores overlap
+  // the other's MMAs; weights stream through a small ring in 32-float K chunks.
+  static constexpr bool LIGHT = NOUT <= 128;
+  static constexpr bool STREAM = true;                                   // weights arrive as a stream of chunks
+  static constexpr int KCH = LIGHT ? (K >= 128 ? 32 : K) : 64;          // K extent of one weight chunk
   static constexpr int NKC = K / KCH;
   static constexpr int NB = NOUT >= 128 ? 128 : NOUT;                   // MMA N = rows of one weight chunk
   static constexpr int PASSES = NOUT > 512 ? NOUT / 256 : 1;       // GEGLU: 4 passes of (128 value | 128 gate) columns
@@ -50,34 +54,37 @@ struct LinCfg {
   static constexpr int TBUF = (PASSES > 1 && 2 * PASS_COLS <= 512) ? 2 : 1;   // double-buffered accumulators: MMAs of pass p+1
   static constexpr int TCOLS_RAW = TBUF * PASS_COLS;                          // overlap the epilogue of pass p
   static constexpr int TMEM_COLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
-  static constexpr int NBUF = STREAM ? (PRO == PRO_TILED ? 3 : 4) : 2;  // weight ring depth (TMA latency > one chunk of MMAs)
+  static constexpr int NBUF = LIGHT ? (PRO == PRO_TILED ? 3 : (NKC > 1 ? 2 : 1)) : 4;   // weight ring depth
   static constexpr int A_BYTES = 128 * KCH * 4;            // per k-chunk
   static constexpr int A_TOTAL = (PRO == PRO_TILED) ? NBUF * A_BYTES : 128 * K * 4;
   static constexpr int B_BYTES = NB * KCH * 4;
   static constexpr int NSTAGE = PASSES * NNB * NKC;
   // per-warp 32x32 fp32 transpose staging for coalesced row-major epilogue I/O: aliases the idle second weight buffer
   // when the kernel streams a single weight chunk, else lives behind the barriers
-  static constexpr bool STG_ALIAS = (NSTAGE == 1) && (B_BYTES >= 32768);
+  // LIGHT kernels: the A operand is dead once the accumulator is complete -> epilogue staging / tile images alias it
+  static constexpr bool STG_ALIAS = LIGHT;
   static constexpr int STG_BYTES = 8 * 32 * 32 * 4;
+  static_assert(!LIGHT || A_TOTAL >= STG_BYTES, "staging must fit in the A region");
   static constexpr int SMEM = 1024 + A_TOTAL + NBUF * B_BYTES + 256 + (STG_ALIAS ? 0 : STG_BYTES);
+  static constexpr int MIN_CTAS = (LIGHT && SMEM <= 113 * 1024) ? 2 : 1;
 };
 
-// exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one RCP + one EX2 + 7 FMA instead of erff's
-// ~30-instruction branchy polynomial.  F.gelu default in the reference (fusion_layer.py:57).
+// exact (erf) GELU, F.gelu default in the reference (fusion_layer.py:57), with erf from Abramowitz-Stegun 7.1.25
+// (|err| <= 2.5e-5, i.e. <= 1.3e-5 |x| on gelu, two decades below the TF32 rounding of the product): one RCP + one EX2 + 8 FMA-pipe
+// instructions instead of erff's ~30-instruction branchy polynomial.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
+  const float ax = fabsf(x);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // MUFU.RCP (1 ulp) instead of IEEE refinement
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * ex2_approx(-z * z * 1.4426950408889634f);   // erf(|x|/sqrt2)
-  return 0.5f * x + 0.5f * fabsf(x) * e;                                     // x/2 (1 + sign(x) erf)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.33267263f, ax, 1.0f)));    // 1 / (1 + 0.47047 |x| / sqrt2)
+  float p = fmaf(0.7478556f, t, -0.0958798f);
+  p = fmaf(p, t, 0.3480242f);
+  const float e = p * t * ex2_approx(-0.72134752f * x * x);                          // (1 - erf(|x| / sqrt2))
+  const float hx = 0.5f * x;
+  return fmaf(-fabsf(hx), e, hx + fabsf(hx));                                         // x/2 (1 + sign(x) erf) = hx + |hx| (1 - e)
 }
 
 template <int K, int NOUT, int PRO, int EPI>
-__global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
+__global__ void __launch_bounds__(288, LinCfg<K, NOUT, PRO>::MIN_CTAS) linear_tc_kernel(const LinArgs a) {
   using Cfg = LinCfg<K, NOUT, PRO>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
@@ -90,7 +97,8 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
   uint64_t* acc_full = bars + 9;  // [2] accumulators of a pass complete (per TMEM buffer)
   uint64_t* tmem_free = bars + 11; // [2] workers drained the TMEM buffer of a pass
   uint32_t* tmem_slot = (uint32_t*)(bars + 14);
-  float* sStg = Cfg::STG_ALIAS ? (float*)(sB + Cfg::B_BYTES) : (float*)(sB + Cfg::NBUF * Cfg::B_BYTES + 256);
+  float* sStg = Cfg::STG_ALIAS ? (float*)sA : (float*)(sB + Cfg::NBUF * Cfg::B_BYTES + 256);
+  uint8_t* sImg = Cfg::LIGHT ? sA : sB;                  // bf16 tile images are assembled here once the MMAs have retired
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, pair = blockIdx.y;
@@ -109,8 +117,11 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 8) {
-    // ------------------------------- control warp (converged; one elected lane issues TMA + MMA) ---------------
+    // ------------------------------- control warp: one elected lane issues TMA + MMA ---------------
+    // The stage loop is fully unrolled for short schedules so that every descriptor is "uniform base + constant" (run-time ring
+    // indices cost ~8 extra SASS instructions per MMA in vector->uniform register moves).
     const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc = umma_idesc(128, Cfg::NB, kFmtTF32);
     const uint8_t* wsrc = (const uint8_t*)a.w_packed;
     const uint8_t* asrc = (const uint8_t*)a.x + (size_t)(pair * a.tiles + tile) * (size_t)(Cfg::NKC * Cfg::A_BYTES);
@@ -126,14 +137,14 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
       }
       bulk_g2s_p(sB + buf * Cfg::B_BYTES, wsrc + (size_t)it * Cfg::B_BYTES, Cfg::B_BYTES, &full[buf], leader);
     };
-#pragma unroll 1
-    for (int it = 0; it < Cfg::NBUF - 1 && it < Cfg::NSTAGE; ++it) issue_load(it);
-#pragma unroll 1
-    for (int it = 0; it < Cfg::NSTAGE; ++it) {
+    constexpr int PRE = Cfg::NBUF > 1 ? Cfg::NBUF - 1 : 1;      // chunks in flight ahead of the MMAs
+#pragma unroll
+    for (int it = 0; it < PRE && it < Cfg::NSTAGE; ++it) issue_load(it);
+    auto stage = [&](int it) {
       const int buf = it % Cfg::NBUF;
-      const int nxt = it + Cfg::NBUF - 1;                  // keep NBUF-1 chunks in flight
+      const int nxt = it + PRE;
       if (nxt < Cfg::NSTAGE) {
-        if (it >= 1) mbar_wait(&mma_done[nxt % Cfg::NBUF], ((it - 1) / Cfg::NBUF) & 1);   // MMAs of stage it-1 freed that buffer
+        if (nxt >= Cfg::NBUF) mbar_wait(&mma_done[nxt % Cfg::NBUF], ((nxt / Cfg::NBUF) - 1) & 1);   // MMAs of the previous occupant retired
         issue_load(nxt);
       }
       const int pass = it / (Cfg::NNB * Cfg::NKC);
@@ -144,17 +155,27 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
       if (pass >= Cfg::TBUF && nbi == 0 && kc == 0) mbar_wait(&tmem_free[tb], ((pass / Cfg::TBUF) - 1) & 1);
       mbar_wait(&full[buf], (it / Cfg::NBUF) & 1);
       tc_fence_after();
-      const uint64_t ad = umma_desc_adv(a_desc0, PRO == PRO_TILED ? buf * Cfg::A_BYTES : kc * (Cfg::KCH / 32) * 16384);
-      const uint64_t bd = umma_desc_adv(b_desc0, buf * Cfg::B_BYTES);
+      if (leader) {
+        const uint64_t ad = umma_desc_adv(a_desc0, PRO == PRO_TILED ? buf * Cfg::A_BYTES : kc * (Cfg::KCH / 32) * 16384);
+        const uint64_t bd = umma_desc_adv(b_desc0, buf * Cfg::B_BYTES);
 #pragma unroll
-      for (int at = 0; at < Cfg::KCH / 32; ++at) {
+        for (int at = 0; at < Cfg::KCH / 32; ++at) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          tc_mma_tf32_p(tmem + tb * Cfg::PASS_COLS + nbi * Cfg::NB, umma_desc_adv(ad, at * 16384 + ks * 32), umma_desc_adv(bd, at * (Cfg::NB * 128) + ks * 32),
-                        idesc, (kc > 0 || at > 0 || ks > 0) ? 1u : 0u, leader);
+          for (int ks = 0; ks < 4; ++ks)
+            tc_mma_tf32(tm + tb * Cfg::PASS_COLS + nbi * Cfg::NB, umma_desc_adv(ad, at * 16384 + ks * 32), umma_desc_adv(bd, at * (Cfg::NB * 128) + ks * 32),
+                        idesc, (kc > 0 || at > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(&mma_done[buf]);
+        if (nbi == Cfg::NNB - 1 && kc == Cfg::NKC - 1) tc_commit(&acc_full[tb]);
       }
-      tc_commit_p(&mma_done[buf], leader);
-      if (nbi == Cfg::NNB - 1 && kc == Cfg::NKC - 1) tc_commit_p(&acc_full[tb], leader);
+      __syncwarp();
+    };
+    if constexpr (Cfg::NSTAGE <= 16) {
+#pragma unroll
+      for (int it = 0; it < Cfg::NSTAGE; ++it) stage(it);
+    } else {
+#pragma unroll 1
+      for (int it = 0; it < Cfg::NSTAGE; ++it) stage(it);
     }
   } else {
     // ------------------------------- workers: A operand prologue -------------------------------
@@ -354,7 +375,7 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
             // the bf16 tile images are assembled in shared memory (the weight ring is dead once acc_full fired) and leave
             // the SM as one bulk-async store per image instead of scattered 2..16-byte global stores
             const uint32_t img_bytes = 128u * drows * 2u;
-            uint8_t* img = sB + which * img_bytes;
+            uint8_t* img = sImg + which * img_bytes;
             if (which < 2) {
               uint8_t* dst = img + (dcol0 >> 6) * 16384;
               const int cc0 = (dcol0 & 63) >> 3;
@@ -384,10 +405,10 @@ __global__ void __launch_bounds__(288, 1) linear_tc_kernel(const LinArgs a) {
           const uint32_t drows = (EPI == EPI_QKV_SC) ? 128u : 64u;
           const uint32_t img_bytes = 128u * drows * 2u;
           const size_t tix = (size_t)(pair * a.tiles + tile) * (128 * drows);
-          if (EPI == EPI_QKV_SC || EPI == EPI_Q_FUS) bulk_s2g(a.t0 + tix, sB, img_bytes);
+          if (EPI == EPI_QKV_SC || EPI == EPI_Q_FUS) bulk_s2g(a.t0 + tix, sImg, img_bytes);
           if (EPI == EPI_QKV_SC || EPI == EPI_KV_FUS) {
-            bulk_s2g(a.t1 + tix, sB + img_bytes, img_bytes);
-            bulk_s2g(a.t2 + tix, sB + 2 * img_bytes, img_bytes);
+            bulk_s2g(a.t1 + tix, sImg + img_bytes, img_bytes);
+            bulk_s2g(a.t2 + tix, sImg + 2 * img_bytes, img_bytes);
           }
           bulk_commit_wait_read();
         }
