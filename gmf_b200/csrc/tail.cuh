@@ -291,62 +291,80 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(const float* __restrict
 // seed kNN in feature space (common.py:53-75 restricted to the seed rows; PointDSC.py:325-329):
 // d_j = 2 - 2 <f_seed, f_j>, (k+1) smallest, rank 0 dropped.  Ties -> lower index first.
 // ------------------------------------------------------------------------------------------------
-// Kernel 1: D[seed][j] = 2 - 2 <f_seed, f_j> as a register-blocked fp32 SGEMM (64 seeds x 64 points per CTA, 4x4 per thread).
+// Kernel 1: D[seed][j] = 2 - 2 <f_seed, f_j> as a register-blocked fp32 SGEMM: 128 seeds x 128 points per CTA, 8x8 accumulators per
+// thread (16 FFMA per shared-memory float4), k consumed strictly in order so every distance is one sequential fmaf chain.
 __global__ void __launch_bounds__(256) seed_dist_kernel(const float* __restrict__ normed, const int* __restrict__ seeds, int N, int S,
                                                         float* __restrict__ dist) {
-  __shared__ __align__(16) float As[16][68];
-  __shared__ __align__(16) float Bs[16][68];
-  __shared__ int sidx[64];
-  const int pair = blockIdx.z, m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, tid = threadIdx.x;
+  __shared__ __align__(16) float As[16][132];
+  __shared__ __align__(16) float Bs[16][132];
+  __shared__ int sidx[128];
+  const int pair = blockIdx.z, m0 = blockIdx.y * 128, n0 = blockIdx.x * 128, tid = threadIdx.x;
   const float* F = normed + (size_t)pair * N * 128;
-  if (tid < 64) sidx[tid] = (m0 + tid < S) ? seeds[(size_t)pair * S + m0 + tid] : -1;
+  if (tid < 128) sidx[tid] = (m0 + tid < S) ? seeds[(size_t)pair * S + m0 + tid] : -1;
   __syncthreads();
-  const int lr = tid >> 2, lk = (tid & 3) * 4;            // loader: row within tile, k offset
+  // loader: thread -> (row = tid / 2 (+0), k offset = (tid & 1) * 8): two float4 per operand per 16-wide k slab
+  const int lr = tid >> 1, lk = (tid & 1) * 8;
   const int arow = sidx[lr];
   const int brow = (n0 + lr < N) ? n0 + lr : -1;
-  const int ty = tid >> 4, tx = tid & 15;
-  float acc[4][4];
+  const int ty = tid >> 4, tx = tid & 15;                  // 16 x 16 threads, each 8 (seeds) x 8 (points): rows ty*4+{0..3}, 64+ty*4+{0..3}
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
-  if (arow >= 0) av = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + lk);
-  if (brow >= 0) bv = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + lk);
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a0 = z4, a1 = z4, b0 = z4, b1 = z4;
+  if (arow >= 0) { a0 = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + lk); a1 = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + lk + 4); }
+  if (brow >= 0) { b0 = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + lk); b1 = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + lk + 4); }
   for (int k0 = 0; k0 < 128; k0 += 16) {
-    As[lk][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
-    Bs[lk][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
+    As[lk][lr] = a0.x; As[lk + 1][lr] = a0.y; As[lk + 2][lr] = a0.z; As[lk + 3][lr] = a0.w;
+    As[lk + 4][lr] = a1.x; As[lk + 5][lr] = a1.y; As[lk + 6][lr] = a1.z; As[lk + 7][lr] = a1.w;
+    Bs[lk][lr] = b0.x; Bs[lk + 1][lr] = b0.y; Bs[lk + 2][lr] = b0.z; Bs[lk + 3][lr] = b0.w;
+    Bs[lk + 4][lr] = b1.x; Bs[lk + 5][lr] = b1.y; Bs[lk + 6][lr] = b1.z; Bs[lk + 7][lr] = b1.w;
     __syncthreads();
     if (k0 + 16 < 128) {                                   // prefetch the next k-slab while computing this one
-      av = make_float4(0.f, 0.f, 0.f, 0.f); bv = av;
-      if (arow >= 0) av = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + k0 + 16 + lk);
-      if (brow >= 0) bv = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + k0 + 16 + lk);
+      a0 = a1 = b0 = b1 = z4;
+      if (arow >= 0) { a0 = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + k0 + 16 + lk); a1 = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + k0 + 20 + lk); }
+      if (brow >= 0) { b0 = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + k0 + 16 + lk); b1 = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + k0 + 20 + lk); }
     }
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float4 p0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]), p1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+      const float4 q0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]), q1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      const float aa[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w}, bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
     if (m >= S) continue;
-    float* d = dist + ((size_t)pair * S + m) * N + n0 + tx * 4;
+    float* d = dist + ((size_t)pair * S + m) * N;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (n0 + tx * 4 + j < N) d[j] = 2.0f - 2.0f * acc[i][j];
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 64 + tx * 4;
+      if (n + 3 < N && (N & 3) == 0) {
+        *reinterpret_cast<float4*>(d + n) = make_float4(2.0f - 2.0f * acc[i][jh * 4], 2.0f - 2.0f * acc[i][jh * 4 + 1], 2.0f - 2.0f * acc[i][jh * 4 + 2],
+                                                        2.0f - 2.0f * acc[i][jh * 4 + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < N) d[n + j] = 2.0f - 2.0f * acc[i][jh * 4 + j];
+      }
+    }
   }
 }
 
-// Kernel 2: per seed, the (k+1) smallest distances in ascending order (ties -> lower index), rank 0 dropped.
-// One warp per seed; the seed's distance row lives in shared memory and is consumed by repeated (value, index) arg-min.
+// Kernel 2: per seed, the (k+1) smallest distances in ascending order (ties -> lower index), rank 0 dropped.  One warp per seed,
+// the seed's distance row in shared memory.  Two scans instead of k+1: (1) every lane finds its two smallest values; the (k+1)-th
+// smallest of those 64 is an upper bound T of the row's (k+1)-th smallest; (2) all entries <= T (usually 41..100) are compacted
+// into a candidate list, from which the k+1 smallest are extracted by repeated (value, index) arg-min.  Rows with too many
+// candidates (massive ties) or fewer than 64 entries take the plain k+1 full scans.
+constexpr int kSelCap = 256;
 template <int SPC>   // seeds (warps) per CTA
 __global__ void __launch_bounds__(SPC * 32) seed_select_kernel(const float* __restrict__ dist, int N, int S, int k, int* __restrict__ knn_idx) {
   extern __shared__ float sm[];
@@ -354,9 +372,62 @@ __global__ void __launch_bounds__(SPC * 32) seed_select_kernel(const float* __re
   const int s = blockIdx.x * SPC + warp;
   if (s >= S) return;
   float* d = sm + (size_t)warp * N;
+  float* cv = sm + (size_t)SPC * N + (size_t)warp * 2 * kSelCap;
+  int* ci = reinterpret_cast<int*>(cv + kSelCap);
   const float* src = dist + ((size_t)pair * S + s) * N;
-  for (int j = lane; j < N; j += 32) d[j] = src[j];
+  float m1 = INFINITY, m2 = INFINITY;
+  for (int j = lane; j < N; j += 32) {
+    const float v = src[j];
+    d[j] = v;
+    if (v < m1) { m2 = m1; m1 = v; } else if (v < m2) m2 = v;
+  }
   __syncwarp();
+  int ncand = -1;
+  if (N >= 64 && k + 1 <= 64) {
+    // rank of m1 / m2 among the 64 lane minima (ties broken by slot number): the value of rank k is the threshold
+    int r1 = 0, r2 = 0;
+    for (int l = 0; l < 32; ++l) {
+      const float o1 = __shfl_sync(0xffffffffu, m1, l), o2 = __shfl_sync(0xffffffffu, m2, l);
+      r1 += (o1 < m1 || (o1 == m1 && 2 * l < 2 * lane)) + (o2 < m1 || (o2 == m1 && 2 * l + 1 < 2 * lane));
+      r2 += (o1 < m2 || (o1 == m2 && 2 * l < 2 * lane + 1)) + (o2 < m2 || (o2 == m2 && 2 * l + 1 < 2 * lane + 1));
+    }
+    const unsigned h1 = __ballot_sync(0xffffffffu, r1 == k), h2 = __ballot_sync(0xffffffffu, r2 == k);
+    const float T = h1 ? __shfl_sync(0xffffffffu, m1, __ffs(h1) - 1) : __shfl_sync(0xffffffffu, m2, __ffs(h2) - 1);
+    ncand = 0;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      const float v = j < N ? d[j] : INFINITY;
+      const unsigned mk = __ballot_sync(0xffffffffu, v <= T);
+      const int pos = ncand + __popc(mk & ((1u << lane) - 1u));
+      if (v <= T && pos < kSelCap) { cv[pos] = v; ci[pos] = j; }
+      ncand += __popc(mk);
+    }
+    __syncwarp();
+    if (ncand > kSelCap) ncand = -1;
+  }
+  if (ncand >= 0) {
+    for (int rnk = 0; rnk <= k; ++rnk) {
+      float bv = INFINITY;
+      int bi = 0x7fffffff, bp = -1;
+      for (int c = lane; c < ncand; c += 32) {
+        const float v = cv[c];
+        const int i = ci[c];
+        if (v < bv || (v == bv && i < bi)) { bv = v; bi = i; bp = c; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bp = op; }
+      }
+      if (lane == 0) {
+        if (bp >= 0) { cv[bp] = INFINITY; ci[bp] = 0x7fffffff; }
+        if (rnk > 0) knn_idx[((size_t)pair * S + s) * k + rnk - 1] = bi < N ? bi : 0;
+      }
+      __syncwarp();
+    }
+    return;
+  }
   for (int rnk = 0; rnk <= k; ++rnk) {
     float bv = INFINITY;
     int bi = 0x7fffffff;
