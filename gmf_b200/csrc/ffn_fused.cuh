@@ -163,18 +163,30 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
         rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gr < a.L) rv[i] = *reinterpret_cast<const float4*>(xp + (size_t)gr * 128 + c4);
       }
+      // branch-free sweeps so that the shuffle-reduction chains of the 8 rows interleave (rows past L are zeros, never stored)
+      float mean[RPW], rs[RPW];
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) mean[i] = rv[i].x + rv[i].y + rv[i].z + rv[i].w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) mean[i] += __shfl_xor_sync(0xffffffffu, mean[i], o);
 #pragma unroll
       for (int i = 0; i < RPW; ++i) {
-        const int r = rbase + i;
-        float4 v = rv[i];
-        if (row0 + r < a.L) {
-          const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / 128.0f);
-          const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-          const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / 128.0f);
-          const float rs = rsqrtf(var + 1e-5f);
-          v = make_float4(fmaf(dx * rs, g4.x, b4.x), fmaf(dy * rs, g4.y, b4.y), fmaf(dz * rs, g4.z, b4.z), fmaf(dw * rs, g4.w, b4.w));
-        }
-        *reinterpret_cast<float4*>(sA + (lane >> 3) * 16384 + swz_off(r, lane & 7)) = to_tf32(v);
+        mean[i] *= (1.0f / 128.0f);
+        const float dx = rv[i].x - mean[i], dy = rv[i].y - mean[i], dz = rv[i].z - mean[i], dw = rv[i].w - mean[i];
+        rv[i] = make_float4(dx, dy, dz, dw);
+        rs[i] = dx * dx + dy * dy + dz * dz + dw * dw;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const float r_ = rsqrtf(rs[i] * (1.0f / 128.0f) + 1e-5f);
+        const float4 v = make_float4(fmaf(rv[i].x * r_, g4.x, b4.x), fmaf(rv[i].y * r_, g4.y, b4.y), fmaf(rv[i].z * r_, g4.z, b4.z), fmaf(rv[i].w * r_, g4.w, b4.w));
+        *reinterpret_cast<float4*>(sA + (lane >> 3) * 16384 + swz_off(rbase + i, lane & 7)) = to_tf32(v);
       }
       fence_proxy_async();
       mbar_arrive(a_ready);

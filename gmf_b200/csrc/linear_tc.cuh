@@ -208,31 +208,51 @@ __global__ void __launch_bounds__(288, LinCfg<K, NOUT, PRO>::MIN_CTAS) linear_tc
           rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (want && gr >= 0 && gr < a.L) rv[i] = *reinterpret_cast<const float4*>(xp + (size_t)gr * K + c4);
         }
+        // Rows are processed without per-row branches (rows past L are zeros and are never stored), in three sweeps, so that the
+        // 16 shuffle-reduction chains of a warp interleave instead of running back to back (~150 cycles each).
+        float4 xv[RPW];
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
-          const int r = rbase + i;
-          const int gr = row0 + r;
           float4 v = rv[i + 1];
-          if (gr < a.L) {
-            if (PRO == PRO_CPE_LN) {
-              const float4 pv = rv[i], nv = rv[i + 2];
-              v.x += fmaf(w0.x, pv.x, fmaf(w1.x, v.x, fmaf(w2.x, nv.x, cb.x)));
-              v.y += fmaf(w0.y, pv.y, fmaf(w1.y, v.y, fmaf(w2.y, nv.y, cb.y)));
-              v.z += fmaf(w0.z, pv.z, fmaf(w1.z, v.z, fmaf(w2.z, nv.z, cb.z)));
-              v.w += fmaf(w0.w, pv.w, fmaf(w1.w, v.w, fmaf(w2.w, nv.w, cb.w)));
-              if (a.x0_out) *reinterpret_cast<float4*>(a.x0_out + ((size_t)pair * a.L + gr) * K + c4) = v;
-            }
-            if (PRO == PRO_LN || PRO == PRO_CPE_LN) {
-              const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / 128.0f);
-              const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-              const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / 128.0f);
-              const float rs = rsqrtf(var + 1e-5f);
-              v = make_float4(fmaf(dx * rs, g4.x, b4.x), fmaf(dy * rs, g4.y, b4.y), fmaf(dz * rs, g4.z, b4.z),
-                              fmaf(dw * rs, g4.w, b4.w));
-            }
+          if (PRO == PRO_CPE_LN) {
+            const float4 pv = rv[i], nv = rv[i + 2];
+            v.x += fmaf(w0.x, pv.x, fmaf(w1.x, v.x, fmaf(w2.x, nv.x, cb.x)));
+            v.y += fmaf(w0.y, pv.y, fmaf(w1.y, v.y, fmaf(w2.y, nv.y, cb.y)));
+            v.z += fmaf(w0.z, pv.z, fmaf(w1.z, v.z, fmaf(w2.z, nv.z, cb.z)));
+            v.w += fmaf(w0.w, pv.w, fmaf(w1.w, v.w, fmaf(w2.w, nv.w, cb.w)));
+            const int gr = row0 + rbase + i;
+            if (a.x0_out && gr < a.L) *reinterpret_cast<float4*>(a.x0_out + ((size_t)pair * a.L + gr) * K + c4) = v;
           }
-          *reinterpret_cast<float4*>(sA + (lane >> 3) * 16384 + swz_off(r, lane & 7)) = to_tf32(v);
+          xv[i] = v;
         }
+        if (PRO == PRO_LN || PRO == PRO_CPE_LN) {
+          float mean[RPW], rs[RPW];
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) mean[i] = xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) mean[i] += __shfl_xor_sync(0xffffffffu, mean[i], o);
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) {
+            mean[i] *= (1.0f / 128.0f);
+            const float dx = xv[i].x - mean[i], dy = xv[i].y - mean[i], dz = xv[i].z - mean[i], dw = xv[i].w - mean[i];
+            xv[i] = make_float4(dx, dy, dz, dw);
+            rs[i] = dx * dx + dy * dy + dz * dz + dw * dw;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) {
+            const float r_ = rsqrtf(rs[i] * (1.0f / 128.0f) + 1e-5f);
+            xv[i] = make_float4(fmaf(xv[i].x * r_, g4.x, b4.x), fmaf(xv[i].y * r_, g4.y, b4.y), fmaf(xv[i].z * r_, g4.z, b4.z), fmaf(xv[i].w * r_, g4.w, b4.w));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i)
+          *reinterpret_cast<float4*>(sA + (lane >> 3) * 16384 + swz_off(rbase + i, lane & 7)) = to_tf32(xv[i]);
       } else {  // K == 64: half a warp per row
         const float* xp = a.x + (size_t)pair * a.L * K;
         const int ch = lane & 15;

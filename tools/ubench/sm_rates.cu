@@ -132,6 +132,26 @@ __global__ void __launch_bounds__(512, 1) k_tmem_deep(int reader_warps, int iter
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// T7: packed half-precision exponential: one MUFU op per TWO values?
+__global__ void k_ex2_h2(int iters, long long* out, float* sink) {
+  unsigned x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = 0x38003400u + threadIdx.x + i;   // two small halves
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(x[i]));
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  unsigned s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s ^= x[i];
+  if (s == 0x12345678u) sink[threadIdx.x] = (float)s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+}
+
 template <int OP>   // 0 ex2, 1 sqrt, 2 ffma
 __global__ void k_mufu(int iters, long long* out, float* sink) {
   float x[16];
@@ -266,6 +286,11 @@ int main() {
     k_mufu<2><<<148, 32 * w>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
     printf("  warps=%2d  ex2 %.1f /clk/SM   sqrt %.1f /clk/SM   ffma %.1f /clk/SM\n", w, ex2, sq, (double)w * 32 * 16 * iters / h);
+  }
+  for (int w : {4, 8, 16}) {
+    k_ex2_h2<<<148, 32 * w>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
+    printf("  warps=%2d  ex2.approx.f16x2: %.1f instr-lanes/clk/SM = %.1f exponentials/clk/SM\n", w, (double)w * 32 * 16 * iters / h, 2.0 * w * 32 * 16 * iters / h);
   }
   printf("== T3 MMA sequence, cycles per key tile (tensor floor: all 640, S 256, PV 256, S128 512 @ 8192 flop/clk)\n");
   {
