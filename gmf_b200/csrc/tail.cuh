@@ -225,6 +225,16 @@ constexpr int kClsSmem = (64 * 132 + 128 * 32 + 32 * 32 + 2 * 64 * 33 + 64) * 4;
 // seed picking: NMS (PointDSC.py:268-286) on the fly (no N x N distance matrix), then a stable descending sort
 // ------------------------------------------------------------------------------------------------
 // key_i = score_i * is_local_max_i, is_local_max_i = AND_j (score_i >= score_j  OR  |s_i - s_j| >= R)
+// The reference compares sqrt(d2) >= R in fp32.  sqrtf is monotone and correctly rounded, so that test equals d2 >= T2 with T2 the
+// smallest float whose square root reaches R (found by stepping a few ulps around R*R): no square root in the N^2 loop, same bits.
+__device__ __forceinline__ float sqrt_threshold(float radius) {
+  float t = radius * radius;
+  if (!(t > 0.f) || !isfinite(t)) return t;
+  for (int n = 0; n < 8 && sqrtf(t) >= radius; ++n) t = __uint_as_float(__float_as_uint(t) - 1u);   // now sqrtf(t) < radius (or 8 ulps below)
+  for (int n = 0; n < 16 && sqrtf(t) < radius; ++n) t = __uint_as_float(__float_as_uint(t) + 1u);   // first float with sqrtf(t) >= radius
+  return t;
+}
+
 __global__ void __launch_bounds__(256) nms_key_kernel(const float4* __restrict__ src4, const float* __restrict__ score, int N,
                                                       float radius, int use_nms, float* __restrict__ key) {
   __shared__ float4 tp[256];
@@ -237,19 +247,20 @@ __global__ void __launch_bounds__(256) nms_key_kernel(const float4* __restrict__
   if (i < N) { me = P[i]; ms = S[i]; }
   bool ismax = true;
   if (use_nms) {
+    const float t2 = sqrt_threshold(radius);
     for (int j0 = 0; j0 < N; j0 += 256) {
       const int j = j0 + threadIdx.x;
-      float4 v = make_float4(0.f, 0.f, 0.f, -INFINITY);
+      float4 v = make_float4(0.f, 0.f, 0.f, -INFINITY);     // padding never suppresses: its score is -inf
       if (j < N) { v = P[j]; v.w = S[j]; }
       __syncthreads();
       tp[threadIdx.x] = v;
       __syncthreads();
-      const int lim = min(256, N - j0);
-      for (int jj = 0; jj < lim; ++jj) {
+#pragma unroll 8
+      for (int jj = 0; jj < 256; ++jj) {
         const float4 o = tp[jj];
         const float dx = me.x - o.x, dy = me.y - o.y, dz = me.z - o.z;
-        const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-        ismax = ismax && ((ms >= o.w) || (d >= radius));
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        ismax = ismax && ((ms >= o.w) || (d2 >= t2));
       }
     }
   }
@@ -486,29 +497,48 @@ __global__ void __launch_bounds__(128) seed_spectral_kernel(const float* __restr
     }
     __syncthreads();
     const float inv_s2 = 1.0f / (sigma * sigma), inv_d2 = 1.0f / (sigma_spat * sigma_spat);
-    const int kq = (k + 3) >> 2;                        // 1 x 4 register blocking: one kf[i] load feeds four dot products
-    for (int e = tid; e < k * kq; e += 128) {
-      const int i = e / kq, j0 = (e % kq) * 4;
-      float dot[4] = {0.f, 0.f, 0.f, 0.f};
-      const int j1 = min(j0 + 1, k - 1), j2 = min(j0 + 2, k - 1), j3 = min(j0 + 3, k - 1);
-#pragma unroll 8
+    // M is symmetric: only the 4 x 4 blocks on and above the diagonal are computed (55 of 100 for k = 40), one block per
+    // thread: 8 shared-memory loads feed 16 FMAs per channel (the 1 x 4 version was shared-memory bound: 5 loads per 4 FMAs).
+    const int nb = (k + 3) >> 2;
+    int t = tid, bi = 0;
+    while (bi < nb && t >= nb - bi) { t -= nb - bi; ++bi; }
+    if (bi < nb) {
+      const int bj = bi + t, i0 = bi * 4, j0 = bj * 4;
+      int ri[4], rj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { ri[u] = min(i0 + u, k - 1); rj[u] = min(j0 + u, k - 1); }
+      float dot[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) dot[u][w] = 0.f;
+#pragma unroll 4
       for (int c = 0; c < 128; ++c) {
-        const float a = kf[i][c];
-        dot[0] = fmaf(a, kf[j0][c], dot[0]); dot[1] = fmaf(a, kf[j1][c], dot[1]);
-        dot[2] = fmaf(a, kf[j2][c], dot[2]); dot[3] = fmaf(a, kf[j3][c], dot[3]);
+        float av[4], bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { av[u] = kf[ri[u]][c]; bv[u] = kf[rj[u]][c]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) dot[u][w] = fmaf(av[u], bv[w], dot[u][w]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u;
-        if (j >= k) break;
-        const float mf = fmaxf(1.0f - (1.0f - dot[u]) * inv_s2, 0.f);                   // PointDSC.py:338
-        const float ax = ks[i][0] - ks[j][0], ay = ks[i][1] - ks[j][1], az = ks[i][2] - ks[j][2];
-        const float bx = kt[i][0] - kt[j][0], by = kt[i][1] - kt[j][1], bz = kt[i][2] - kt[j][2];
-        const float dd = sqrtf(ax * ax + ay * ay + az * az) - sqrtf(bx * bx + by * by + bz * bz);
-        const float ms = fmaxf(1.0f - dd * dd * inv_d2, 0.f);                          // :351
-        const float m = (i == j) ? 0.f : mf * ms;                                      // :360-361
-        M[i][j] = m;
-        Mg[i * KM + j] = m;
+        const int i = i0 + u;
+        if (i >= k) break;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int j = j0 + w;
+          if (j >= k || (bi == bj && j < i)) continue;
+          const float mf = fmaxf(1.0f - (1.0f - dot[u][w]) * inv_s2, 0.f);                 // PointDSC.py:338
+          const float ax = ks[i][0] - ks[j][0], ay = ks[i][1] - ks[j][1], az = ks[i][2] - ks[j][2];
+          const float bx = kt[i][0] - kt[j][0], by = kt[i][1] - kt[j][1], bz = kt[i][2] - kt[j][2];
+          const float dd = sqrtf(ax * ax + ay * ay + az * az) - sqrtf(bx * bx + by * by + bz * bz);
+          const float ms = fmaxf(1.0f - dd * dd * inv_d2, 0.f);                          // :351
+          const float m = (i == j) ? 0.f : mf * ms;                                      // :360-361
+          M[i][j] = m; M[j][i] = m;
+          Mg[i * KM + j] = m; Mg[j * KM + i] = m;
+        }
       }
     }
   } else {
