@@ -30,6 +30,12 @@ struct AttnArgs {
   float* out;                 // [pairs][Lq][D] fp32
   int Lq, Lk, q_tiles, k_tiles;   // tiles of 128 rows
   float neg_inv_sigma2;       // SC only: -1/sigma_d^2
+  // fusion attention gen 2 only: fused to_out (fusion_layer.py:94) + residual.  wo_packed != NULL switches it on:
+  //   xout[B, Lq, 128] = softmax(..) v . Wo^T + bo + resid        (`out` is then unused)
+  const float* wo_packed;     // [128 x 64] tf32, swizzled K-major image (pack_linear(wo, 128, 64, 64, 128))
+  const float* bo;            // [128]
+  const float* resid;         // [B, Lq, 128]
+  float* xout;                // [B, Lq, 128]
 };
 
 template <int D, bool SC>

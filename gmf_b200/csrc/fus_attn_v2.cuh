@@ -20,7 +20,9 @@ struct Fa2Cfg {
   static constexpr int D = 64, BN = 64, NR = 4;                 // NR: K ring depth = V^T ring depth = unroll period
   static constexpr int K_BYTES = BN * D * 2, V_BYTES = D * BN * 2;
   static constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;         // [max | sum][row tile][half][row]
-  static constexpr int SMEM = 1024 + NR * K_BYTES + NR * V_BYTES + XCH_BYTES + 512;
+  static constexpr int WO_BYTES = 128 * 64 * 4;                 // to_out weight (tf32) for the fused output projection
+  static constexpr int STG_BYTES = 16 * 32 * 32 * 4;            // per-warp 32 x 32 transpose tiles for coalesced epilogue I/O
+  static constexpr int SMEM = 1024 + NR * K_BYTES + NR * V_BYTES + WO_BYTES + STG_BYTES + XCH_BYTES + 512;
   static constexpr int COL_O = 256, COL_P = 384, COL_Q = 448;
   static constexpr float WINDOW = 80.f;
 };
@@ -86,7 +88,9 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sK = smem;                                    // [NR] x K (64 keys x 64)
   uint8_t* sV = sK + NR * Cfg::K_BYTES;                  // [NR] x V^T (64 x 64 keys)
-  float* sX = (float*)(sV + NR * Cfg::V_BYTES);          // [2][2][2][128]
+  uint8_t* sWo = sV + NR * Cfg::V_BYTES;                 // to_out weight image (fused output projection)
+  float* sStg = (float*)(sWo + Cfg::WO_BYTES);           // [16 warps][32][32]
+  float* sX = (float*)((uint8_t*)sStg + Cfg::STG_BYTES); // [2][2][2][128]
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
   uint64_t* q_full = bars;            // [2]
   uint64_t* k_full = bars + 2;        // [NR]
@@ -98,7 +102,10 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   uint64_t* p_ready = s_free + 4;     // [2]
   uint64_t* pv_done = p_ready + 2;    // [2]
   uint64_t* o_full = pv_done + 2;     // [2]
-  uint32_t* tmem_slot = (uint32_t*)(o_full + 2);
+  uint64_t* on_ready = o_full + 2;    // [2] normalised, tf32-rounded O written back to TMEM
+  uint64_t* x_full = on_ready + 2;    // [2] O . Wo^T complete
+  uint64_t* wo_full = x_full + 2;     // 1
+  uint32_t* tmem_slot = (uint32_t*)(wo_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pair = blockIdx.y;
@@ -113,6 +120,7 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   };
   if (tid == 0) {
     mbar_init(&q_full[0], 256); mbar_init(&q_full[1], 256);
+    mbar_init(&on_ready[0], 256); mbar_init(&on_ready[1], 256); mbar_init(&x_full[0], 1); mbar_init(&x_full[1], 1); mbar_init(wo_full, 1);
     init_bars();
     fence_mbar_init();
   }
@@ -150,6 +158,10 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
     if (warp == WP) {
       // ------------------------------------ producer ------------------------------------
       const uint32_t leader = elect_one() ? 1u : 0u;
+      if (pass == 0 && a.wo_packed) {
+        mbar_expect_tx_p(wo_full, Cfg::WO_BYTES, leader);
+        bulk_g2s_p(sWo, a.wo_packed, Cfg::WO_BYTES, wo_full, leader);
+      }
       for (int j = 0; j < nt; ++j) {
         const int st = j % NR;
         const size_t tix = (size_t)pair * a.k_tiles + (j >> 1);
@@ -257,6 +269,25 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
     __syncthreads();
   }
 
+  const bool fused_out = a.wo_packed != nullptr;
+  if (fused_out && (warp == 17 || warp == 18) && (warp - 17) < ntile) {
+    // ------------------------------------ P.V issuer of row tile tt: X = (O / l) . Wo^T  (tf32, A operand = O in tensor memory) -----------
+    const int tt = warp - 17;
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc_x = umma_idesc(128, 128, kFmtTF32);
+    const uint64_t wo_desc = umma_desc_sw128(smem_u32(sWo));
+    mbar_wait2(&on_ready[tt], 0, wo_full, 0);
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        tc_mma_tf32_ts(tm + (uint32_t)tt * 128u, tm + Cfg::COL_O + (uint32_t)tt * 64u + i * 8, umma_desc_adv(wo_desc, (i >> 2) * 16384 + (i & 3) * 32), idesc_x,
+                       i ? 1u : 0u);
+      tc_commit(&x_full[tt]);
+    }
+    __syncwarp();
+  }
   if (softmax_role) {
     sX[512 + (t * 2 + h) * 128 + r] = l_sum;
     asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
@@ -264,16 +295,68 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
     mbar_wait(&o_full[t], 0);
     tc_fence_after();
     const int gq = (qt0 + t) * 128 + r;
-    float* op = a.out + ((size_t)pair * a.Lq + gq) * D + h * 32;
     uint32_t u[32];
     tmem_ld32(tlane + Cfg::COL_O + t * 64 + h * 32, u);
     tmem_ld_wait();
-    if (gq < a.Lq) {
+    if (!fused_out) {
+      float* op = a.out + ((size_t)pair * a.Lq + gq) * D + h * 32;
+      if (gq < a.Lq) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(op + 4 * i) =
-            make_float4(__uint_as_float(u[4 * i]) * inv, __uint_as_float(u[4 * i + 1]) * inv,
-                        __uint_as_float(u[4 * i + 2]) * inv, __uint_as_float(u[4 * i + 3]) * inv);
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(op + 4 * i) =
+              make_float4(__uint_as_float(u[4 * i]) * inv, __uint_as_float(u[4 * i + 1]) * inv,
+                          __uint_as_float(u[4 * i + 2]) * inv, __uint_as_float(u[4 * i + 3]) * inv);
+      }
+    } else {
+      // normalised attention output, rounded to tf32, back into its TMEM columns: it is the A operand of the output projection
+#pragma unroll
+      for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(to_tf32(__uint_as_float(u[i]) * inv));
+      tmem_st32(tlane + Cfg::COL_O + t * 64 + h * 32, u);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&on_ready[t]);
+      mbar_wait(&x_full[t], 0);
+      tc_fence_after();
+      // coalesced I/O through a per-warp XOR-swizzled 32 x 32 staging tile (global accesses touch 4 rows x 128 B per instruction)
+      float* stg = sStg + warp * 1024;
+      const int srow = lane >> 3, sj = lane & 7;
+      const int grow0 = (qt0 + t) * 128 + (warp & 3) * 32;             // first row of this warp's lane quadrant
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld32(tlane + (uint32_t)t * 128u + h * 64 + c * 32, u);      // X lives in the (now idle) score buffers of row tile t
+        tmem_ld_wait();
+        const int col0 = h * 64 + c * 32;
+        const size_t gbase = ((size_t)pair * a.Lq + grow0) * 128 + col0;
+        float4 rr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rw = i * 4 + srow;
+          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow0 + rw < a.Lq) rr[i] = *reinterpret_cast<const float4*>(a.resid + gbase + (size_t)rw * 128 + sj * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rw = i * 4 + srow;
+          *reinterpret_cast<float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2)) = rr[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bo + col0) + j);
+          float4* slot = reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2));
+          const float4 res = *slot;
+          *slot = make_float4(__uint_as_float(u[4 * j]) + bb.x + res.x, __uint_as_float(u[4 * j + 1]) + bb.y + res.y,
+                              __uint_as_float(u[4 * j + 2]) + bb.z + res.z, __uint_as_float(u[4 * j + 3]) + bb.w + res.w);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rw = i * 4 + srow;
+          if (grow0 + rw < a.Lq)
+            *reinterpret_cast<float4*>(a.xout + gbase + (size_t)rw * 128 + sj * 4) = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
+        }
+        __syncwarp();
+      }
     }
   }
   tc_fence_before();

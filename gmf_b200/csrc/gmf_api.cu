@@ -200,7 +200,7 @@ struct gmf_ctx {
   ClsWeights cls{};
   int chunk_pairs = 64;
   int ffn_impl = 2;         // 2 = fused GEGLU FFN kernel (hidden activation stays on chip), 1 = two linear kernels
-  int fus_impl = 2;         // 2 = gen-2 fusion attention (Q/P in TMEM, fixed reference), 1 = gen 1
+  int fus_impl = 3;         // 3 = gen-2 fusion attention with fused to_out + residual, 2 = gen 2, 1 = gen 1
   int sc_impl = 14;         // gen 9: 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12/13 = 1 thread per row; 8/9/10 = gen 8; 1/2/3 = gen 7; 0 = SIMT distances
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
@@ -317,12 +317,13 @@ int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, c
     AttnArgs a{};
     a.q_t = w.qf; a.k_t = w.kf; a.vt_t = w.vtf; a.out = w.of;
     a.Lq = Lq; a.Lk = Lk; a.q_tiles = cdiv(Lq, 128); a.k_tiles = cdiv(Lk, 128);
+    if (ctx->fus_impl >= 3) { a.wo_packed = f.wo; a.bo = f.bo; a.resid = resid0; a.xout = w.x1; }   // to_out + bias + residual fused
     ProfScope ps(CAT_ATTN_FUS, st);
     cudaError_t e = ctx->fus_impl >= 2 ? launch_fus_attn_v2(a, B, st) : launch_attn<64, false>(a, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "fusion attention launch");
   }
-  {  // to_out + bias + residual
+  if (ctx->fus_impl < 3) {  // to_out + bias + residual
     LinArgs a = lin(w.of, Lq, f.wo, f.bo);
     a.residual = resid0; a.out = w.x1;
     TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st, CAT_OUT64)));
