@@ -244,10 +244,17 @@ def main():
         sc_ms, sc_n = prof["attn_sc"]
         sc_flops = 4.0 * a.corr * a.corr * 128 * a.pairs * a.layers * a.steps           # 4 N^2 C per pair-layer
         ach = sc_flops / (sc_ms / 1000.0) / 1e12
-        roof = {"kernel": "attn_tc_kernel<128,SC> (SC-guided non-local flash attention, compat on the fly)", "bound": "tensor",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+        # DRAM bytes of one launch from the committed `ncu --set full` capture of this configuration
+        # (profiles/r01_top3_cfg2_ncu_raw.csv: dram__bytes_read.sum 332.97 MB + dram__bytes_write.sum 134.56 MB at 64 pairs, N=5000)
+        traffic = 467.53e6 if (a.pairs == 64 and a.corr == 5000) else None
+        # co-limit: every score element costs one MUFU.SQRT and one MUFU.EX2 at the measured 16 MUFU/clk/SM (tools/ubench/sm_rates.cu)
+        mufu_floor_ms = 2.0 * a.corr * a.corr * a.pairs / (16.0 * 148 * 1.965e9) * 1e3
+        roof = {"kernel": "sc_attn_v9_kernel<0,2> (SC-guided non-local flash attention, compat on the fly, gen 9)", "bound": "tensor",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r01_top3_cfg2_ncu_raw.csv)",
                 "peak_source": how, "avg_launch_ms": sc_ms / max(sc_n, 1), "launches": sc_n,
                 "algorithmic_flops_per_launch": sc_flops / max(sc_n, 1),
+                "mufu_colimit": {"floor_ms_per_launch": mufu_floor_ms, "frac": mufu_floor_ms / (sc_ms / max(sc_n, 1))},
                 "whole_path": {"flops_per_pair": flops_per_pair(a.corr, a.tokens, a.layers),
                                "achieved_tflops": flops_per_pair(a.corr, a.tokens, a.layers) * value / world / 1e12,
                                "frac_of_tensor_peak": flops_per_pair(a.corr, a.tokens, a.layers) * value / world / 1e12 / peak_tf}}

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the oracle / reference-generated golden fixtures.  Run on the B200
 box: python -m pytest tests -m gpu.  Tolerances (BASELINE.json north_star): logits 1e-2 abs, pose 0.01 deg / 1 mm,
 seeds identical except exact ties (teacher-forced)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -308,6 +310,55 @@ def test_full_size_properties_n5000():
     h_tr, h_lab, h_conf = torch.empty(2, 4, 4), torch.empty(2, 5000), torch.empty(2, 5000)
     eng.forward_host(*args, h_tr, h_lab, h_conf, testing=True)
     assert torch.equal(h_tr, tr) and torch.equal(h_lab, lab) and torch.equal(h_conf, out["confidence"].cpu())
+
+
+def test_kitti_shape_chunked_batch_cfg3():
+    """cfg#3 shape (KITTI: 60 m extent, sigma_d = inlier threshold = 1.2, N=5000) with a batch larger than the engine's chunk size:
+    pose recovery on every pair and chunked == per-pair results (the batch loop must not couple pairs)."""
+    from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
+    from gmf_b200.weights import hot_path_spec
+    cfg = dict(O.DEFAULT_CFG)
+    cfg.update(inlier_threshold=1.2, nms_radius=1.2, sigma_d=1.2, num_layers=2)
+    sd = synth_state_dict(hot_path_spec(2), seed=3, plain_init=True)
+    sd["sigma_spat"] = torch.tensor([1.2])
+    os.environ["GMF_CHUNK_PAIRS"] = "2"
+    try:
+        eng = make_engine(cfg, sd)
+    finally:
+        del os.environ["GMF_CHUNK_PAIRS"]
+    B = 5                                                      # 3 chunks: 2 + 2 + 1
+    pr = synth_pairs(B, 5000, seed=77, extent=60.0, inlier_ratio=0.4, noise=0.04)
+    p_tok, q_tok = synth_tokens(B, 300, 5), synth_tokens(B, 300, 6)
+    dev = [t.cuda() for t in (pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok)]
+    out = eng.forward(*dev, testing=True)
+    tr = out["final_trans"].cpu()
+    assert float(O.rotation_error_deg(tr[:, :3, :3], pr["gt_trans"][:, :3, :3]).max()) < 0.05
+    assert float((tr[:, :3, 3] - pr["gt_trans"][:, :3, 3]).norm(dim=-1).max()) < 0.05          # metres; noise 4 cm
+    for b in (0, 4):
+        one = eng.forward(*[t[b:b + 1] for t in dev], testing=True)
+        assert torch.equal(one["final_trans"].cpu(), tr[b:b + 1]) and torch.equal(one["final_labels"], out["final_labels"][b:b + 1])
+        assert torch.equal(one["confidence"], out["confidence"][b:b + 1])
+
+
+def test_lomatch_stress_n10000_cfg4():
+    """cfg#4: 10000 correspondences with 5 % inliers — the N x N matrices (400 MB each in the reference) are never materialised;
+    workspace stays linear in N and the pose is still recovered."""
+    from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
+    from gmf_b200.weights import hot_path_spec
+    cfg = dict(O.DEFAULT_CFG)
+    eng = make_engine(cfg, synth_state_dict(hot_path_spec(12), seed=0, plain_init=True))
+    pr = synth_pairs(1, 10000, seed=41, inlier_ratio=0.05, noise=0.002)
+    p_tok, q_tok = synth_tokens(1, 4800, 1), synth_tokens(1, 4800, 2)
+    ws_bytes = eng.workspace(1, 10000, 4800)[1]
+    assert ws_bytes < 3 * 10000 * 10000 * 4 / 4                # far below even one quarter of the reference's three N^2 fp32 matrices
+    out = eng.forward(*[t.cuda() for t in (pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok)], testing=True)
+    tr = out["final_trans"].cpu()
+    assert torch.isfinite(out["confidence"]).all() and out["seeds"].shape[1] == 1000
+    assert float(O.rotation_error_deg(tr[:, :3, :3], pr["gt_trans"][:, :3, :3]).max()) < 0.05
+    assert float((tr[:, :3, 3] - pr["gt_trans"][:, :3, 3]).norm(dim=-1).max()) < 2e-3
+    lab = out["final_labels"].cpu()
+    # labels come from the best seed hypothesis BEFORE post-refinement (PointDSC.py:423-425): at 5 % inliers that pose is coarse
+    assert ((lab == 1) & (pr["gt_labels"] == 0)).float().mean() < 0.01 and lab.sum() >= 40
 
 
 def test_c_abi_error_paths():
