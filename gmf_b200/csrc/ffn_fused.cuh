@@ -34,6 +34,10 @@ struct FfnArgs {
   const float* w2_packed;  // 8 chunks x [128 out rows x 64 hidden] swizzled tf32
   const float* b2;         // [128]
   float* out;              // [B, L, 128]
+  // optional fused tail of NonLocalBlock.forward (PointDSC.py:65,73): out += fc_message.6(m2) = m2 . W3^T + b3
+  const float* m2;         // [B, L, 64] (ReLU(BN(conv(...))) output of fc_message.4) or NULL
+  const float* w3_packed;  // [128 out rows x 64] swizzled tf32
+  const float* b3;         // [128]
 };
 
 __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
@@ -54,6 +58,7 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
   uint64_t* h_ready = bars + 13;       // [2] 256
   uint64_t* h_free = bars + 15;        // [2]
   uint64_t* out_full = bars + 17;      // 1
+  uint64_t* m2_ready = bars + 18;      // 512
   uint32_t* tmem_slot = (uint32_t*)(bars + 21);
   float* sStg = (float*)sA;
 
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
     for (int i = 0; i < 3; ++i) { mbar_init(&full1[i], 1); mbar_init(&empty1[i], 1); }
     mbar_init(&full2[0], 1); mbar_init(&full2[1], 1); mbar_init(&empty2[0], 1); mbar_init(&empty2[1], 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&acc1_free[i], 512); mbar_init(&h_ready[i], 512); mbar_init(&h_free[i], 1); }
-    mbar_init(out_full, 1);
+    mbar_init(out_full, 1); mbar_init(m2_ready, 512);
     fence_mbar_init();
   }
   if (warp == 16) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -96,6 +101,11 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       if (p >= 2) mbar_wait(&empty2[slot], ((p >> 1) - 1) & 1);
       mbar_expect_tx_p(&full2[slot], Cfg::W_BYTES, leader);
       bulk_g2s_p(sW2 + slot * Cfg::W_BYTES, src + (size_t)p * Cfg::W_BYTES, Cfg::W_BYTES, &full2[slot], leader);
+    }
+    if (a.m2) {                                              // ninth chunk: fc_message.6 weight for the fused block tail
+      mbar_wait(&empty2[0], 1);                              // MMA2 of pass 6 (4th use of slot 0) retired
+      mbar_expect_tx_p(&full2[0], Cfg::W_BYTES, leader);
+      bulk_g2s_p(sW2, a.w3_packed, Cfg::W_BYTES, &full2[0], leader);
     }
   } else if (warp == 16) {
     // ------------------------------- MMA1 issuer: ACC1[p&1] = LN(x) . W1_p^T -------------------------------
@@ -143,7 +153,18 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
                          (p | i) ? 1u : 0u);
         tc_commit(&empty2[p & 1]);
         tc_commit(&h_free[p & 1]);
-        if (p == Cfg::PASSES - 1) tc_commit(out_full);
+        if (p == Cfg::PASSES - 1 && !a.m2) tc_commit(out_full);
+      }
+      __syncwarp();
+    }
+    if (a.m2) {                                              // OUT += m2 . W3^T : A operand = m2 (tf32) parked in the idle H[0] columns
+      mbar_wait2(m2_ready, 0, &full2[0], 0);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          tc_mma_tf32_ts(tm + Cfg::COL_OUT, tm + Cfg::COL_H + i * 8, umma_desc_adv(w_desc0, (i >> 2) * 16384 + (i & 3) * 32), idesc, 1u);
+        tc_commit(out_full);
       }
       __syncwarp();
     }
@@ -227,6 +248,24 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       tc_fence_before();
       mbar_arrive(&h_ready[b]);
     }
+    if (a.m2) {
+      // this thread's 16 columns of m2 row r -> H[0] (free once MMA2 of pass 6 has retired: 4th completion of h_free[0])
+      uint32_t mv[16];
+      const int gr = row0 + r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < a.L) x4 = __ldg(reinterpret_cast<const float4*>(a.m2 + ((size_t)pair * a.L + gr) * 64 + cq * 16) + i);
+        x4 = to_tf32(x4);
+        mv[4 * i] = __float_as_uint(x4.x); mv[4 * i + 1] = __float_as_uint(x4.y); mv[4 * i + 2] = __float_as_uint(x4.z); mv[4 * i + 3] = __float_as_uint(x4.w);
+      }
+      mbar_wait(&h_free[0], 1);
+      tc_fence_after();
+      tmem_st16(trow + Cfg::COL_H + cq * 16, mv);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(m2_ready);
+    }
     // ------------------------------- workers: out = OUT + b2 + x (coalesced through a per-warp staging tile) -------------------------------
     mbar_wait(out_full, 0);
     tc_fence_after();
@@ -254,7 +293,8 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 bb = *reinterpret_cast<const float4*>(a.b2 + col0 + 4 * j);
+        float4 bb = *reinterpret_cast<const float4*>(a.b2 + col0 + 4 * j);
+        if (a.m2) { const float4 b3 = *reinterpret_cast<const float4*>(a.b3 + col0 + 4 * j); bb.x += b3.x; bb.y += b3.y; bb.z += b3.z; bb.w += b3.w; }
         float4* slot = reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2));
         const float4 res = *slot;
         *slot = make_float4(__uint_as_float(v[4 * j]) + bb.x + res.x, __uint_as_float(v[4 * j + 1]) + bb.y + res.y,

@@ -199,7 +199,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
-  int ffn_impl = 2;         // 2 = fused GEGLU FFN kernel (hidden activation stays on chip), 1 = two linear kernels
+  int ffn_impl = 3;         // 3 = fused GEGLU FFN kernel + fused fc_message.6 tail, 2 = fused FFN, 1 = two linear kernels
   int fus_impl = 3;         // 3 = gen-2 fusion attention with fused to_out + residual, 2 = gen 2, 1 = gen 1
   int sc_impl = 14;         // gen 9: 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12/13 = 1 thread per row; 8/9/10 = gen 8; 1/2/3 = gen 7; 0 = SIMT distances
   // staging for the host-buffer entry point
@@ -291,7 +291,8 @@ LinArgs lin(const float* x, int L, const float* w, const float* bias) {
 }
 
 // FusionLayer.forward (fusion_layer.py:172-201)
-int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st) {
+int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st,
+               const float* tail_m2 = nullptr, const float* tail_w3 = nullptr, const float* tail_b3 = nullptr) {
   const float* resid0 = xq;
   {  // queries: (CPE) -> LN -> to_q  => bf16 Q tiles (scale folded)
     LinArgs a = lin(xq, Lq, f.wq, nullptr);
@@ -332,6 +333,7 @@ int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, c
     FfnArgs a{};
     a.x = w.x1; a.L = Lq; a.tiles = cdiv(Lq, 128); a.ln_g = f.lnf_g; a.ln_b = f.lnf_b;
     a.w1_packed = f.w1f; a.b1 = f.b1; a.w2_packed = f.w2f; a.b2 = f.b2; a.out = out;
+    a.m2 = tail_m2; a.w3_packed = tail_w3; a.b3 = tail_b3;
     ProfScope ps(CAT_FFN1, st);
     cudaError_t e = launch_ffn_fused(a, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -445,6 +447,10 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     LinArgs a = lin(w.m1, N, lw.fc2_w, lw.fc2_b);
     a.out = w.m2;
     TRY((run_linear<64, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
+  }
+  if (ctx->ffn_impl >= 3) {   // fc_message.6(m2) + fusion_layer_2 output (PointDSC.py:73) folded into the fused FFN kernel's tail
+    TRY(run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, feat_out, st, w.m2, lw.fc3_w, lw.fc3_b));
+    return 0;
   }
   TRY(run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, w.x2, st));
   {
