@@ -199,6 +199,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
+  int sc_fuse_fc = 1;       // fc_message.0/.3 fused into the SC attention kernel's tail
   int ffn_impl = 3;         // 3 = fused GEGLU FFN kernel + fused fc_message.6 tail, 2 = fused FFN, 1 = two linear kernels
   int fus_impl = 3;         // 3 = gen-2 fusion attention with fused to_out + residual, 2 = gen 2, 1 = gen 1
   int sc_impl = 14;         // gen 9: 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12/13 = 1 thread per row; 8/9/10 = gen 8; 1/2/3 = gen 7; 0 = SIMT distances
@@ -400,7 +401,7 @@ cudaError_t launch_sc_dispatch(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, 
 }
 
 // Q/K/V projections + SC-guided attention (PointDSC.py:56-64); feat1 = PointCN output
-int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float* feat1, int B, int N, float* msg, cudaStream_t st) {
+int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float* feat1, int B, int N, float* msg, cudaStream_t st, float* fused_m2 = nullptr) {
   {
     LinArgs a = lin(feat1, N, lw.qkv_w, lw.qkv_b);
     a.t0 = w.qs; a.t1 = w.ks; a.t2 = w.vts;
@@ -411,6 +412,7 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
     sa.q_t = w.qs; sa.k_t = w.ks; sa.vt_t = w.vts; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = msg;
     sa.N = N; sa.tiles = cdiv(N, 128);
     sa.neg_inv_sigma2 = -1.0f / (ctx->sigma_spat * ctx->sigma_spat);
+    if (fused_m2) { sa.fc1_w = lw.fc1_w; sa.fc1_b = lw.fc1_b; sa.fc2_w = lw.fc2_w; sa.fc2_b = lw.fc2_b; sa.m2_out = fused_m2; }
     ProfScope ps(CAT_ATTN_SC, st);
     cudaError_t e = launch_sc_any(ctx, sa, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -437,13 +439,14 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     a.out = w.feat1;
     TRY((run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, B, st, CAT_PCN)));
   }
-  TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st));
-  {
+  const bool fuse_fc = ctx->sc_fuse_fc && ctx->sc_impl >= 11;   // fc_message.0/.3 run as the tail of the gen-9 attention kernel
+  TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st, fuse_fc ? w.m2 : nullptr));
+  if (!fuse_fc) {
     LinArgs a = lin(w.msg, N, lw.fc1_w, lw.fc1_b);
     a.out = w.m1;
     TRY((run_linear<128, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
   }
-  {
+  if (!fuse_fc) {
     LinArgs a = lin(w.m1, N, lw.fc2_w, lw.fc2_b);
     a.out = w.m2;
     TRY((run_linear<64, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
@@ -660,6 +663,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   if (const char* e = getenv("GMF_SC_IMPL")) c->sc_impl = atoi(e);
   if (const char* e = getenv("GMF_FUS_IMPL")) c->fus_impl = atoi(e);
   if (const char* e = getenv("GMF_FFN_IMPL")) c->ffn_impl = atoi(e);
+  if (const char* e = getenv("GMF_SC_FUSE_FC")) c->sc_fuse_fc = atoi(e);
   *out = c;
   return 0;
 }

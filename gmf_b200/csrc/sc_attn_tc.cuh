@@ -32,6 +32,13 @@ struct ScAttnArgs {
   float* out;                 // [pairs][N][128] fp32
   int N, tiles;
   float neg_inv_sigma2;
+  // gen 9 only: fused head of fc_message (PointDSC.py:13-21,65).  fc1_w != NULL switches it on: instead of msg the kernel
+  // writes m2 = ReLU(BN(conv64x64(ReLU(BN(conv128x64(msg))))))  [pairs][N][64]  (BN folded into the packed weights / biases)
+  const float* fc1_w;         // pack_linear(W, 64, 128, 32, 64)
+  const float* fc1_b;
+  const float* fc2_w;         // pack_linear(W, 64, 64, 64, 64)
+  const float* fc2_b;
+  float* m2_out;
   long long* trace;           // optional timeline of CTA (0,0): [role 0..3][tile][4] clock64 stamps (GMF_SC_TRACE)
 };
 

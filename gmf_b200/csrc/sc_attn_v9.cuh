@@ -26,7 +26,8 @@ struct Sc9Cfg {
   static constexpr int KSTAGE_BYTES = K_BYTES + BD_BYTES;
   static constexpr int XCH_BYTES = 2 * 4 * 128 * 4;       // [max | sum][group x row part][row]
   static constexpr int AQ_BYTES = 128 * 64 * 2;
-  static constexpr int SMEM = 1024 + AQ_BYTES + NS * KSTAGE_BYTES + NV * V_BYTES + XCH_BYTES + 256;
+  static constexpr int FC_BYTES = (64 * 128 + 64 * 64) * 4;                                    // fc_message.0 / .3 weights (tf32) for the fused tail
+  static constexpr int SMEM = 1024 + AQ_BYTES + NS * KSTAGE_BYTES + NV * V_BYTES + FC_BYTES + XCH_BYTES + 256;
   static constexpr int COL_Q = 288, COL_P = 352, COL_O = 384;   // P: 16 columns per softmax group
   static constexpr float WINDOW = 80.f;
 };
@@ -113,7 +114,8 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
   uint8_t* sAq = smem;                                   // query-side distance features (SS-mode A operand)
   uint8_t* sK = sAq + Cfg::AQ_BYTES;                     // [NS] x {K, Bd} (64 keys)
   uint8_t* sV = sK + NS * Cfg::KSTAGE_BYTES;             // [NV] x V^T (64 keys)
-  float* sX = (float*)(sV + NV * Cfg::V_BYTES);          // [2][2][128]
+  uint8_t* sFc = sV + NV * Cfg::V_BYTES;                 // fc_message.0 (32 KB) | fc_message.3 (16 KB) weight images
+  float* sX = (float*)(sFc + Cfg::FC_BYTES);             // [2][2][128]
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;        // [NS]
@@ -126,7 +128,12 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
   uint64_t* pv_done = p_ready + 2;    // [2]
   uint64_t* aq_full = pv_done + 2;    // 1
   uint64_t* o_full = aq_full + 1;     // 1
-  uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+  uint64_t* on_ready = o_full + 1;    // fused tail: normalised tf32 O back in TMEM
+  uint64_t* h_ready = on_ready + 1;   //             hidden activation of fc_message in TMEM
+  uint64_t* x1_full = h_ready + 1;
+  uint64_t* x2_full = x1_full + 1;
+  uint64_t* w_full = x2_full + 1;
+  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pair = blockIdx.y, qt = blockIdx.x;
@@ -140,6 +147,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
     for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128 * TPR); }
     for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 128 * TPR); mbar_init(&pv_done[i], 1); }
     mbar_init(o_full, 1); mbar_init(aq_full, 1);
+    mbar_init(on_ready, NW * 32); mbar_init(h_ready, NW * 32); mbar_init(x1_full, 1); mbar_init(x2_full, 1); mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == WP) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -181,6 +189,11 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
       if (pass == 0) {
         mbar_expect_tx_p(aq_full, Cfg::AQ_BYTES, leader);
         bulk_g2s_p(sAq, a.aq_t + ((size_t)pair * a.tiles + qt) * (128 * 64), Cfg::AQ_BYTES, aq_full, leader);
+        if (a.fc1_w) {
+          mbar_expect_tx_p(w_full, Cfg::FC_BYTES, leader);
+          bulk_g2s_p(sFc, a.fc1_w, 64 * 128 * 4, w_full, leader);
+          bulk_g2s_p(sFc + 64 * 128 * 4, a.fc2_w, 64 * 64 * 4, w_full, leader);
+        }
       }
       int wk = 0, wv = 0;
       const int wend = nw;
@@ -312,6 +325,32 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
     __syncthreads();                                         // also: sX is rewritten by the next pass
   }
 
+  const bool fused = a.fc1_w != nullptr;
+  if (fused && warp == WM) {
+    // ------------------------------------ fused fc_message head: two small tf32 GEMMs with the A operand in tensor memory -----------
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc_f = umma_idesc(128, 64, kFmtTF32);
+    const uint64_t w1_desc = umma_desc_sw128(smem_u32(sFc)), w2_desc = umma_desc_sw128(smem_u32(sFc + 64 * 128 * 4));
+    mbar_wait2(on_ready, 0, w_full, 0);
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)                             // X1[128 x 64] = msg . W1^T   (msg = normalised O, columns 384..511)
+        tc_mma_tf32_ts(tm, tm + Cfg::COL_O + i * 8, umma_desc_adv(w1_desc, (i >> 2) * 8192 + (i & 3) * 32), idesc_f, i ? 1u : 0u);
+      tc_commit(x1_full);
+    }
+    __syncwarp();
+    mbar_wait(h_ready, 0);
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)                              // X2[128 x 64] = H . W2^T      (H in columns 64..127, X2 in 128..191)
+        tc_mma_tf32_ts(tm + 128, tm + 64 + i * 8, umma_desc_adv(w2_desc, (i >> 2) * 8192 + (i & 3) * 32), idesc_f, i ? 1u : 0u);
+      tc_commit(x2_full);
+    }
+    __syncwarp();
+  }
   if (warp < NW) {
     sX[512 + part * 128 + r] = l_sum;
     asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
@@ -322,18 +361,58 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
     tc_fence_after();
     const int gq = qt * 128 + r;
     constexpr int OC = D / NPART;                             // output columns per thread
-    float* op = a.out + ((size_t)pair * a.N + gq) * D + part * OC;
+    if (!fused) {
+      float* op = a.out + ((size_t)pair * a.N + gq) * D + part * OC;
 #pragma unroll
-    for (int c = 0; c < OC / 32; ++c) {
-      uint32_t u[32];
-      tmem_ld32(tlane + Cfg::COL_O + part * OC + c * 32, u);
+      for (int c = 0; c < OC / 32; ++c) {
+        uint32_t u[32];
+        tmem_ld32(tlane + Cfg::COL_O + part * OC + c * 32, u);
+        tmem_ld_wait();
+        if (gq < a.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(op + c * 32 + 4 * i) =
+                make_float4(__uint_as_float(u[4 * i]) * inv, __uint_as_float(u[4 * i + 1]) * inv,
+                            __uint_as_float(u[4 * i + 2]) * inv, __uint_as_float(u[4 * i + 3]) * inv);
+        }
+      }
+    } else {
+      // msg = O / l, rounded to tf32, back into its TMEM columns (A operand of fc_message.0)
+#pragma unroll
+      for (int c = 0; c < OC / 32; ++c) {
+        uint32_t u[32];
+        tmem_ld32(tlane + Cfg::COL_O + part * OC + c * 32, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(to_tf32(__uint_as_float(u[i]) * inv));
+        tmem_st32(tlane + Cfg::COL_O + part * OC + c * 32, u);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(on_ready);
+      constexpr int HC1 = 64 / NPART;                         // hidden columns per thread (16 or 32)
+      uint32_t x[HC1];
+      mbar_wait(x1_full, 0);
+      tc_fence_after();
+      if constexpr (HC1 == 16) tmem_ld16(tlane + part * HC1, x); else tmem_ld32(tlane + part * HC1, x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < HC1; ++i) x[i] = __float_as_uint(to_tf32(fmaxf(__uint_as_float(x[i]) + __ldg(a.fc1_b + part * HC1 + i), 0.f)));
+      if constexpr (HC1 == 16) tmem_st16(tlane + 64 + part * HC1, x); else tmem_st32(tlane + 64 + part * HC1, x);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(h_ready);
+      mbar_wait(x2_full, 0);
+      tc_fence_after();
+      if constexpr (HC1 == 16) tmem_ld16(tlane + 128 + part * HC1, x); else tmem_ld32(tlane + 128 + part * HC1, x);
       tmem_ld_wait();
       if (gq < a.N) {
+        float* op = a.m2_out + ((size_t)pair * a.N + gq) * 64 + part * HC1;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(op + c * 32 + 4 * i) =
-              make_float4(__uint_as_float(u[4 * i]) * inv, __uint_as_float(u[4 * i + 1]) * inv,
-                          __uint_as_float(u[4 * i + 2]) * inv, __uint_as_float(u[4 * i + 3]) * inv);
+        for (int i = 0; i < HC1; i += 4)
+          *reinterpret_cast<float4*>(op + i) =
+              make_float4(fmaxf(__uint_as_float(x[i]) + __ldg(a.fc2_b + part * HC1 + i), 0.f), fmaxf(__uint_as_float(x[i + 1]) + __ldg(a.fc2_b + part * HC1 + i + 1), 0.f),
+                          fmaxf(__uint_as_float(x[i + 2]) + __ldg(a.fc2_b + part * HC1 + i + 2), 0.f), fmaxf(__uint_as_float(x[i + 3]) + __ldg(a.fc2_b + part * HC1 + i + 3), 0.f));
       }
     }
   }
