@@ -11,8 +11,7 @@
 // warp per row tile; one producer warp.  21 warps.
 // TMEM (512 columns): S[t][b] at 64 (2t + b) | O[t] at 256 + 64 t | P[t] at 384 + 32 t | Q[t] at 448 + 32 t.
 #pragma once
-#include "attn_tc.cuh"
-#include "sc_attn_v8.cuh"
+#include "attn_args.cuh"
 
 namespace gmf {
 

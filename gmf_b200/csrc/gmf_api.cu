@@ -9,10 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "attn_tc.cuh"
 #include "linear_tc.cuh"
-#include "sc_attn_tc.cuh"
-#include "sc_attn_v8.cuh"
 #include "sc_attn_v9.cuh"
 #include "fus_attn_v2.cuh"
 #include "ffn_fused.cuh"
@@ -201,8 +198,8 @@ struct gmf_ctx {
   int chunk_pairs = 64;
   int sc_fuse_fc = 1;       // fc_message.0/.3 fused into the SC attention kernel's tail
   int ffn_impl = 3;         // 3 = fused GEGLU FFN kernel + fused fc_message.6 tail, 2 = fused FFN, 1 = two linear kernels
-  int fus_impl = 3;         // 3 = gen-2 fusion attention with fused to_out + residual, 2 = gen 2, 1 = gen 1
-  int sc_impl = 14;         // gen 9: 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12/13 = 1 thread per row; 8/9/10 = gen 8; 1/2/3 = gen 7; 0 = SIMT distances
+  int fus_impl = 3;         // 3 = fusion attention with fused to_out + residual, 2 = separate to_out kernel
+  int sc_impl = 14;         // 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12 = 1 thread per row
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
@@ -321,7 +318,7 @@ int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, c
     a.Lq = Lq; a.Lk = Lk; a.q_tiles = cdiv(Lq, 128); a.k_tiles = cdiv(Lk, 128);
     if (ctx->fus_impl >= 3) { a.wo_packed = f.wo; a.bo = f.bo; a.resid = resid0; a.xout = w.x1; }   // to_out + bias + residual fused
     ProfScope ps(CAT_ATTN_FUS, st);
-    cudaError_t e = ctx->fus_impl >= 2 ? launch_fus_attn_v2(a, B, st) : launch_attn<64, false>(a, B, st);
+    cudaError_t e = launch_fus_attn_v2(a, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "fusion attention launch");
   }
@@ -359,44 +356,18 @@ int run_prep(const gmf_ctx* ctx, Work& w, const float* src, const float* tgt, in
   const int Np = cdiv(N, 128) * 128;
   prep_points_kernel<<<B, 256, 0, st>>>(src, tgt, N, Np, w.kpts, w.src4, w.tgt4);
   LAUNCHED();
-  if (ctx->sc_impl >= 8) dist_feature_scaled_kernel<<<dim3(Np / 128, B), 128, 0, st>>>(w.kpts, Np, 1.0f / (sigma_d > 0.f ? sigma_d : ctx->sigma_spat), w.aq, w.bd);
-  else dist_feature_kernel<<<dim3(Np / 128, B), 128, 0, st>>>(w.kpts, Np, w.aq, w.bd);
+  dist_feature_scaled_kernel<<<dim3(Np / 128, B), 128, 0, st>>>(w.kpts, Np, 1.0f / (sigma_d > 0.f ? sigma_d : ctx->sigma_spat), w.aq, w.bd);
   LAUNCHED();
   return 0;
 }
 
-cudaError_t launch_sc_dispatch(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, cudaStream_t st);
-cudaError_t launch_sc_any(const gmf_ctx* ctx, const ScAttnArgs& sa_in, int B, cudaStream_t st) {
-  // GMF_SC_TRACE=<file>: the second launch of the process records the role timeline of CTA (0,0) (tools/sc_trace.py reads it)
-  static int n_launch = 0;
-  const char* tf = getenv("GMF_SC_TRACE");
-  if (!tf || ++n_launch != 2) return launch_sc_dispatch(ctx, sa_in, B, st);
-  ScAttnArgs sa = sa_in;
-  const size_t bytes = 4 * 256 * 4 * sizeof(long long);
-  cudaMalloc(&sa.trace, bytes);
-  cudaMemsetAsync(sa.trace, 0, bytes, st);
-  cudaError_t e = launch_sc_dispatch(ctx, sa, B, st);
-  cudaStreamSynchronize(st);
-  std::vector<long long> h(4 * 256 * 4);
-  cudaMemcpy(h.data(), sa.trace, bytes, cudaMemcpyDeviceToHost);
-  cudaFree(sa.trace);
-  if (FILE* f = fopen(tf, "wb")) { fwrite(h.data(), 1, bytes, f); fclose(f); }
-  return e;
-}
-cudaError_t launch_sc_dispatch(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, cudaStream_t st) {
-  switch (ctx->sc_impl) {
+cudaError_t launch_sc_any(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, cudaStream_t st) {
+  switch (ctx->sc_impl) {   // GMF_SC_IMPL: threads per score row / exponentials per 4 evaluated on the FMA pipe (profiles/r01_sc_attention.md)
     case 11: return launch_sc_attn_v9<0, 1>(sa, B, st);
     case 12: return launch_sc_attn_v9<1, 1>(sa, B, st);
-    case 13: return launch_sc_attn_v9<2, 1>(sa, B, st);
-    case 14: return launch_sc_attn_v9<0, 2>(sa, B, st);
     case 15: return launch_sc_attn_v9<1, 2>(sa, B, st);
     case 16: return launch_sc_attn_v9<2, 2>(sa, B, st);
-    case 8: return launch_sc_attn_v8<0>(sa, B, st);
-    case 9: return launch_sc_attn_v8<1>(sa, B, st);
-    case 10: return launch_sc_attn_v8<2>(sa, B, st);
-    case 3: return launch_sc_attn<1, 4>(sa, B, st);
-    case 2: return launch_sc_attn<2, 2>(sa, B, st);
-    default: return launch_sc_attn<1, 2>(sa, B, st);
+    default: return launch_sc_attn_v9<0, 2>(sa, B, st);
   }
 }
 
@@ -407,26 +378,14 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
     a.t0 = w.qs; a.t1 = w.ks; a.t2 = w.vts;
     TRY((run_linear<128, 384, PRO_NONE, EPI_QKV_SC>(a, B, st, CAT_QKV)));
   }
-  if (ctx->sc_impl >= 1) {
-    ScAttnArgs sa{};
-    sa.q_t = w.qs; sa.k_t = w.ks; sa.vt_t = w.vts; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = msg;
-    sa.N = N; sa.tiles = cdiv(N, 128);
-    sa.neg_inv_sigma2 = -1.0f / (ctx->sigma_spat * ctx->sigma_spat);
-    if (fused_m2) { sa.fc1_w = lw.fc1_w; sa.fc1_b = lw.fc1_b; sa.fc2_w = lw.fc2_w; sa.fc2_b = lw.fc2_b; sa.m2_out = fused_m2; }
-    ProfScope ps(CAT_ATTN_SC, st);
-    cudaError_t e = launch_sc_any(ctx, sa, B, st);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (e != cudaSuccess) return fail_cuda(e, "sc_attn_tc launch");
-    return 0;
-  }
-  AttnArgs a{};
-  a.q_t = w.qs; a.k_t = w.ks; a.vt_t = w.vts; a.kpts = w.kpts; a.out = msg;
-  a.Lq = N; a.Lk = N; a.q_tiles = a.k_tiles = cdiv(N, 128);
-  a.neg_inv_sigma2 = -1.0f / (ctx->sigma_spat * ctx->sigma_spat);
+  ScAttnArgs sa{};
+  sa.q_t = w.qs; sa.k_t = w.ks; sa.vt_t = w.vts; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = msg;
+  sa.N = N; sa.tiles = cdiv(N, 128);
+  if (fused_m2) { sa.fc1_w = lw.fc1_w; sa.fc1_b = lw.fc1_b; sa.fc2_w = lw.fc2_w; sa.fc2_b = lw.fc2_b; sa.m2_out = fused_m2; }
   ProfScope ps(CAT_ATTN_SC, st);
-  cudaError_t e = launch_attn<128, true>(a, B, st);
+  cudaError_t e = launch_sc_any(ctx, sa, B, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (e != cudaSuccess) return fail_cuda(e, "attn_tc<128,SC> launch");
+  if (e != cudaSuccess) return fail_cuda(e, "sc_attn_v9 launch");
   return 0;
 }
 
@@ -439,7 +398,7 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     a.out = w.feat1;
     TRY((run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, B, st, CAT_PCN)));
   }
-  const bool fuse_fc = ctx->sc_fuse_fc && ctx->sc_impl >= 11;   // fc_message.0/.3 run as the tail of the gen-9 attention kernel
+  const bool fuse_fc = ctx->sc_fuse_fc != 0;   // fc_message.0/.3 run as the tail of the gen-9 attention kernel
   TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st, fuse_fc ? w.m2 : nullptr));
   if (!fuse_fc) {
     LinArgs a = lin(w.msg, N, lw.fc1_w, lw.fc1_b);
@@ -1030,17 +989,11 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
   cudaError_t e;
   if (sc) {
     TRY(run_prep(ctx, w, src, tgt, B, Lk, st, sigma_d));
-    if (ctx->sc_impl >= 1) {
-      ScAttnArgs sa{};
-      sa.q_t = Q; sa.k_t = K; sa.vt_t = V; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = out; sa.N = Lk; sa.tiles = kt;
-      sa.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
-      e = launch_sc_any(ctx, sa, B, st);
-    } else {
-      a.kpts = w.kpts; a.neg_inv_sigma2 = -1.0f / (sigma_d * sigma_d);
-      e = launch_attn<128, true>(a, B, st);
-    }
+    ScAttnArgs sa{};
+    sa.q_t = Q; sa.k_t = K; sa.vt_t = V; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = out; sa.N = Lk; sa.tiles = kt;
+    e = launch_sc_any(ctx, sa, B, st);
   } else {
-    e = ctx->fus_impl >= 2 ? launch_fus_attn_v2(a, B, st) : launch_attn<64, false>(a, B, st);
+    e = launch_fus_attn_v2(a, B, st);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail_cuda(e, "attn launch");

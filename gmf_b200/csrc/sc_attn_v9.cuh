@@ -1,7 +1,12 @@
-// Spatial-consistency guided non-local attention, generation 9 (PointDSC.py:56-64, 216-221).  Same math as gen 8
-// (sc_attn_v8.cuh: S, DA = |ds|^2/sigma^2, DB = 1 - |dt|^2/sigma^2 from the tensor pipe; c = sat(2 sqrt(DA (1 - DB)) + DB - DA);
-// fixed softmax reference with a block-wide "repeat once with the exact row maxima" vote), re-pipelined around the two facts the
-// gen-8 profile exposed (profiles/r01_sc_attention.md):
+// Spatial-consistency guided non-local attention, generation 9 (PointDSC.py:56-64, 216-221):
+//     msg_i = softmax_j( c_ij * q_i.k_j / sqrt(128) ) v_j,    c_ij = max(0, 1 - (|s_i-s_j| - |t_i-t_j|)^2 / sigma_d^2)
+// The N x N matrices never exist in HBM: per 128-query x 32-key tile the tensor pipe produces THREE fp32 accumulators in TMEM,
+//     S = Q K^T (log2 units), DA = |s_i - s_j|^2 / sigma^2, DB = 1 - |t_i - t_j|^2 / sigma^2   (sc_common.cuh: split-bf16 feature rows)
+// and the softmax threads evaluate  c = sat(2 sqrt(DA (1 - DB)) + DB - DA),  p = exp2(S c - ref)  in ~8 issue slots per element.
+// The softmax reference is FIXED per pass (0 first): floating point is scale invariant, so any reference within 2^+-80 of the row
+// maximum gives the same result; each thread tracks its row maximum and, if any row of the CTA leaves the window, the CTA repeats
+// the key loop once with the exact row maxima (block-wide vote, all roles take part).  No per-tile maximum exchange, no rescale.
+// Pipeline shaped by the measured rates (profiles/r01_sc_attention.md, tools/ubench/sm_rates.cu):
 //   * with ONE score buffer per softmax group the chain  softmax(v) -> PV_v -> S_{v+2} -> softmax(v+2)  is serial, the two groups
 //     drift into lock step and wait 43 % of the time for the tensor pipe;
 //   * SS-mode MMAs re-read the 128 x 128 Q tile from shared memory for every key tile and are shared-memory bound (48 clk for an
@@ -16,7 +21,8 @@
 // Warps 0-3 / 4-7: softmax groups (even / odd tiles, one thread per score row); 8: producer; 9: P V issuer; 10: score issuer
 // (two issuing warps: a single one spends ~800 cycles per 32-key tile on its serial chain of barrier waits, MMA issue and commits).
 #pragma once
-#include "sc_attn_v8.cuh"
+#include <type_traits>
+#include "sc_common.cuh"
 
 namespace gmf {
 
