@@ -13,6 +13,7 @@
 #include "sc_attn_v9.cuh"
 #include "fus_attn_v2.cuh"
 #include "ffn_fused.cuh"
+#include "pcn_qkv.cuh"
 #include "tail.cuh"
 
 using namespace gmf;
@@ -180,6 +181,7 @@ struct FusionW {
 };
 struct LayerW {
   const float *pcn_w, *pcn_b, *qkv_w, *qkv_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
+  const float* pq_w;        // PointCN + QKV weight chunks for the chained kernel (pcn_qkv.cuh)
   FusionW f2;
 };
 
@@ -196,6 +198,7 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
+  int pcn_qkv = 1;          // PointCN + QKV projection chained in one kernel
   int sc_fuse_fc = 1;       // fc_message.0/.3 fused into the SC attention kernel's tail
   int ffn_impl = 3;         // 3 = fused GEGLU FFN kernel + fused fc_message.6 tail, 2 = fused FFN, 1 = two linear kernels
   int fus_impl = 3;         // 3 = fusion attention with fused to_out + residual, 2 = separate to_out kernel
@@ -372,8 +375,9 @@ cudaError_t launch_sc_any(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, cudaS
 }
 
 // Q/K/V projections + SC-guided attention (PointDSC.py:56-64); feat1 = PointCN output
-int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float* feat1, int B, int N, float* msg, cudaStream_t st, float* fused_m2 = nullptr) {
-  {
+int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float* feat1, int B, int N, float* msg, cudaStream_t st, float* fused_m2 = nullptr,
+                     bool qkv_done = false) {
+  if (!qkv_done) {
     LinArgs a = lin(feat1, N, lw.qkv_w, lw.qkv_b);
     a.t0 = w.qs; a.t1 = w.ks; a.t2 = w.vts;
     TRY((run_linear<128, 384, PRO_NONE, EPI_QKV_SC>(a, B, st, CAT_QKV)));
@@ -393,13 +397,22 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
 int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in, const float* image_feat, int B, int N, int T,
                       float* feat_out, cudaStream_t st) {
   const LayerW& lw = ctx->layers[li];
-  {
+  const bool chain = ctx->pcn_qkv != 0;                        // PointCN + QKV projection as one chained-GEMM kernel
+  if (chain) {
+    PcnQkvArgs a{};
+    a.x = feat_in; a.L = N; a.tiles = cdiv(N, 128); a.w_packed = lw.pq_w; a.pcn_bias = lw.pcn_b; a.qkv_bias = lw.qkv_b;
+    a.feat1 = w.feat1; a.tq = w.qs; a.tk = w.ks; a.tv = w.vts;
+    ProfScope ps(CAT_QKV, st);
+    cudaError_t e = launch_pcn_qkv(a, B, st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail_cuda(e, "pcn_qkv launch");
+  } else {
     LinArgs a = lin(feat_in, N, lw.pcn_w, lw.pcn_b);
     a.out = w.feat1;
     TRY((run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, B, st, CAT_PCN)));
   }
   const bool fuse_fc = ctx->sc_fuse_fc != 0;   // fc_message.0/.3 run as the tail of the gen-9 attention kernel
-  TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st, fuse_fc ? w.m2 : nullptr));
+  TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st, fuse_fc ? w.m2 : nullptr, chain));
   if (!fuse_fc) {
     LinArgs a = lin(w.msg, N, lw.fc1_w, lw.fc1_b);
     a.out = w.m1;
@@ -623,6 +636,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   if (const char* e = getenv("GMF_FUS_IMPL")) c->fus_impl = atoi(e);
   if (const char* e = getenv("GMF_FFN_IMPL")) c->ffn_impl = atoi(e);
   if (const char* e = getenv("GMF_SC_FUSE_FC")) c->sc_fuse_fc = atoi(e);
+  if (const char* e = getenv("GMF_PCN_QKV")) c->pcn_qkv = atoi(e);
   *out = c;
   return 0;
 }
@@ -706,15 +720,17 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
   const float sigma_spat = *next("sigma_spat");
   const size_t l0w = blob.push(next("layer0.weight"), 768), l0b = blob.push(next("layer0.bias"), 128);
   const FusionOff f1 = pack_fusion(false);
-  struct LayerOff { size_t pw, pb, qw, qb, f1w, f1b, f2w, f2b, f3w, f3b; FusionOff f2; };
+  struct LayerOff { size_t pw, pb, qw, qb, f1w, f1b, f2w, f2b, f3w, f3b, pqw; FusionOff f2; };
   std::vector<LayerOff> lo(L);
   for (int i = 0; i < L; ++i) {
     LayerOff& o = lo[i];
+    std::vector<float> pcn64;
     {
       std::vector<float> W = vec(next("0.weight"), 128 * 128), b = vec(next("0.bias"), 128);
       const float *g = next("1.weight"), *be = next("1.bias"), *mu = next("1.running_mean"), *va = next("1.running_var");
       fold_bn(W, b, 128, 128, g, be, mu, va);
       o.pw = blob.push(pack_linear(W, 128, 128, 32, 128)); o.pb = blob.push(b);
+      pcn64 = pack_linear(W, 128, 128, 64, 128);
     }
     {
       std::vector<float> W = vec(next("fc_message.0.weight"), 64 * 128), b = vec(next("fc_message.0.bias"), 64);
@@ -742,7 +758,10 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
         for (int j = 0; j < 128 * 128; ++j) W[(size_t)q * 128 * 128 + j] = wq[j] * s;
         for (int j = 0; j < 128; ++j) b[q * 128 + j] = bq[j] * s;
       }
-      o.qw = blob.push(pack_linear(W, 384, 128, 64, 128)); o.qb = blob.push(b);
+      const std::vector<float> qkv64 = pack_linear(W, 384, 128, 64, 128);
+      o.qw = blob.push(qkv64); o.qb = blob.push(b);
+      pcn64.insert(pcn64.end(), qkv64.begin(), qkv64.end());
+      o.pqw = blob.push(pcn64);
     }
     o.f2 = pack_fusion(true);
   }
@@ -772,7 +791,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
   for (int i = 0; i < L; ++i) {
     LayerW& w = ctx->layers[i];
     const LayerOff& o = lo[i];
-    w.pcn_w = d + o.pw; w.pcn_b = d + o.pb; w.qkv_w = d + o.qw; w.qkv_b = d + o.qb;
+    w.pcn_w = d + o.pw; w.pcn_b = d + o.pb; w.qkv_w = d + o.qw; w.qkv_b = d + o.qb; w.pq_w = d + o.pqw;
     w.fc1_w = d + o.f1w; w.fc1_b = d + o.f1b; w.fc2_w = d + o.f2w; w.fc2_b = d + o.f2b; w.fc3_w = d + o.f3w; w.fc3_b = d + o.f3b;
     w.f2 = fuse(o.f2);
   }
