@@ -206,6 +206,9 @@ struct gmf_ctx {
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
+  cudaStream_t copy_stream = nullptr;   // uploads of the next chunk overlap the current chunk's kernels
+  cudaEvent_t copy_ev[64] = {};
+  cudaEvent_t start_ev = nullptr;
   Prof prof;
 };
 
@@ -646,6 +649,11 @@ void gmf_destroy(gmf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->blob) cudaFree(ctx->blob);
   if (ctx->stage) cudaFree(ctx->stage);
+  if (ctx->copy_stream) {
+    cudaStreamDestroy(ctx->copy_stream);
+    for (auto e : ctx->copy_ev) if (e) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->start_ev);
+  }
   for (auto e : ctx->prof.ev) cudaEventDestroy(e);
   if (g_prof == &ctx->prof) g_prof = nullptr;
   delete ctx;
@@ -860,12 +868,37 @@ int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* 
   }
   Bump bb{(uint8_t*)(((uintptr_t)ctx->stage + 1023) & ~(uintptr_t)1023)};
   layout(bb, d_corr, d_src, d_tgt, d_p, d_q, d_tr, d_lab, d_conf, d_seeds, d_ws);
-  CU(cudaMemcpyAsync(d_corr, corr_pos, (size_t)B * N * 6 * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_src, src, (size_t)B * N * 3 * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_tgt, tgt, (size_t)B * N * 3 * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_p, p_tok, (size_t)B * T * 128 * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_q, q_tok, (size_t)B * T * 128 * 4, cudaMemcpyHostToDevice, st));
-  TRY(gmf_pointdsc_forward(ctx, d_corr, d_src, d_tgt, d_p, d_q, B, N, T, testing, d_tr, d_lab, d_conf, d_seeds, nullptr, d_ws, ws, stream));
+  // Pipelined in chunks of pairs: the inputs of chunk c+1 travel on a copy stream while chunk c computes, so only the first
+  // (small) chunk's upload is exposed.  Chunk sizes: 16 pairs first, then up to 48 (13.0 / 6.5 waves of attention CTAs on 148 SMs).
+  if (!ctx->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->copy_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming));
+  }
+  cudaStream_t cs = ctx->copy_stream;
+  CU(cudaEventRecord(ctx->start_ev, st));                      // the staging buffers may still be read by earlier work on `st`
+  CU(cudaStreamWaitEvent(cs, ctx->start_ev, 0));
+  std::vector<int> cuts;                                       // chunk boundaries
+  for (int b0 = 0; b0 < B;) { cuts.push_back(b0); b0 += (b0 == 0 && B > 16) ? 16 : std::min(48, ctx->chunk_pairs); }
+  cuts.push_back(B);
+  const int nchunk = (int)cuts.size() - 1;
+  if (nchunk > (int)(sizeof(ctx->copy_ev) / sizeof(ctx->copy_ev[0]))) return fail(GMF_ERR_INVALID, "batch too large for the host entry point (max 64 chunks)");
+  for (int c = 0; c < nchunk; ++c) {
+    const size_t b0 = cuts[c], nb = cuts[c + 1] - cuts[c];
+    CU(cudaMemcpyAsync(d_corr + b0 * N * 6, corr_pos + b0 * N * 6, nb * N * 6 * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(d_src + b0 * N * 3, src + b0 * N * 3, nb * N * 3 * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(d_tgt + b0 * N * 3, tgt + b0 * N * 3, nb * N * 3 * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(d_p + b0 * T * 128, p_tok + b0 * T * 128, nb * T * 128 * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(d_q + b0 * T * 128, q_tok + b0 * T * 128, nb * T * 128 * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(ctx->copy_ev[c], cs));
+  }
+  for (int c = 0; c < nchunk; ++c) {
+    const size_t b0 = cuts[c];
+    const int nb = cuts[c + 1] - cuts[c];
+    CU(cudaStreamWaitEvent(st, ctx->copy_ev[c], 0));
+    TRY(gmf_pointdsc_forward(ctx, d_corr + b0 * N * 6, d_src + b0 * N * 3, d_tgt + b0 * N * 3, d_p + b0 * T * 128, d_q + b0 * T * 128, nb, N, T, testing,
+                             d_tr + b0 * 16, d_lab + b0 * N, d_conf + b0 * N, d_seeds + b0 * S, nullptr, d_ws, ws, stream));
+  }
   CU(cudaMemcpyAsync(final_trans, d_tr, (size_t)B * 16 * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(final_labels, d_lab, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   if (confidence) CU(cudaMemcpyAsync(confidence, d_conf, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));

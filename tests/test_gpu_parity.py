@@ -361,6 +361,24 @@ def test_lomatch_stress_n10000_cfg4():
     assert ((lab == 1) & (pr["gt_labels"] == 0)).float().mean() < 0.01 and lab.sum() >= 40
 
 
+def test_host_entry_pipelined_chunks_match_device_entry():
+    """gmf_pointdsc_forward_host uploads in chunks (16 pairs, then up to 48) on a copy stream while the previous chunk computes;
+    results must be bit-identical to the device-pointer entry point on the whole batch."""
+    from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
+    from gmf_b200.weights import hot_path_spec
+    cfg = dict(O.DEFAULT_CFG)
+    cfg.update(num_layers=1)
+    eng = make_engine(cfg, synth_state_dict(hot_path_spec(1), seed=5, plain_init=True))
+    B, N, T = 70, 256, 96                                      # 3 chunks: 16 + 48 + 6
+    pr = synth_pairs(B, N, seed=9, noise=0.002)
+    args = [pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], synth_tokens(B, T, 1), synth_tokens(B, T, 2)]
+    dev = eng.forward(*[t.cuda() for t in args], testing=True)
+    h_tr, h_lab, h_conf = torch.empty(B, 4, 4).pin_memory(), torch.empty(B, N).pin_memory(), torch.empty(B, N).pin_memory()
+    eng.forward_host(*[t.pin_memory() for t in args], h_tr, h_lab, h_conf, testing=True)
+    assert torch.equal(h_tr, dev["final_trans"].cpu()) and torch.equal(h_lab, dev["final_labels"].cpu())
+    assert torch.equal(h_conf, dev["confidence"].cpu())
+
+
 def test_c_abi_error_paths():
     from gmf_b200._lib import GmfError
     from gmf_b200.engine import Engine
