@@ -34,6 +34,9 @@ struct FfnArgs {
   const float* w2_packed;  // 8 chunks x [128 out rows x 64 hidden] swizzled tf32
   const float* b2;         // [128]
   float* out;              // [B, L, 128]
+#ifdef GMF_FFN_TRACE
+  long long* trace;
+#endif
   // optional fused tail of NonLocalBlock.forward (PointDSC.py:65,73): out += fc_message.6(m2) = m2 . W3^T + b3
   const float* m2;         // [B, L, 64] (ReLU(BN(conv(...))) output of fc_message.4) or NULL
   const float* w3_packed;  // [128 out rows x 64] swizzled tf32
@@ -65,6 +68,13 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, pair = blockIdx.y;
   const int row0 = tile * 128;
+#ifdef GMF_FFN_TRACE
+  const bool trc = a.trace && blockIdx.x == 3 && blockIdx.y == 1;
+#define TR(role, idx) do { if (trc && lane == 0) a.trace[(role) * 64 + (idx)] = clock64(); } while (0)
+#else
+#define TR(role, idx) do {} while (0)
+#endif
+  TR(0, 0);
 
   if (tid == 0) {
     mbar_init(a_ready, 512);
@@ -117,7 +127,9 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
     mbar_wait(a_ready, 0);
 #pragma unroll
     for (int p = 0; p < Cfg::PASSES; ++p) {
+      TR(1, 4 * p);
       if (p >= 2) mbar_wait(&acc1_free[p & 1], ((p >> 1) - 1) & 1);
+      TR(1, 4 * p + 1);
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
         const int s = 2 * p + kc, slot = s % Cfg::N1;
@@ -134,6 +146,7 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
           if (kc == 1) tc_commit(&acc1_full[p & 1]);
         }
         __syncwarp();
+        TR(1, 4 * p + 2 + kc);
       }
     }
   } else if (warp == 17) {
@@ -144,8 +157,10 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
     const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW2));
 #pragma unroll
     for (int p = 0; p < Cfg::PASSES; ++p) {
+      TR(2, 2 * p);
       mbar_wait2(&h_ready[p & 1], (p >> 1) & 1, &full2[p & 1], (p >> 1) & 1);
       tc_fence_after();
+      TR(2, 2 * p + 1);
       if (leader) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -211,6 +226,7 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       }
       fence_proxy_async();
       mbar_arrive(a_ready);
+      if (warp == 0) TR(0, 1);
     }
     // ------------------------------- workers: GEGLU between the two GEMMs (16 warps: 4 lane quadrants x 4 column quarters) -----------
     const int q = warp & 3, cq = warp >> 2;
@@ -226,8 +242,10 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
         b1v[i] = __ldg(reinterpret_cast<const float4*>(a.b1 + hc0) + i);
         b1g[i] = __ldg(reinterpret_cast<const float4*>(a.b1 + 512 + hc0) + i);
       }
+      if (warp == 0) TR(3, 4 * p);
       mbar_wait(&acc1_full[b], (p >> 1) & 1);
       tc_fence_after();
+      if (warp == 0) TR(3, 4 * p + 1);
       uint32_t v[16], g[16];
       tmem_ld16(trow + b * 128 + cq * 16, v);
       tmem_ld16(trow + b * 128 + 64 + cq * 16, g);
@@ -242,7 +260,9 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
         v[4 * i + 2] = __float_as_uint(to_tf32((__uint_as_float(v[4 * i + 2]) + b1.z) * gelu_erf(__uint_as_float(g[4 * i + 2]) + b2.z)));
         v[4 * i + 3] = __float_as_uint(to_tf32((__uint_as_float(v[4 * i + 3]) + b1.w) * gelu_erf(__uint_as_float(g[4 * i + 3]) + b2.w)));
       }
+      if (warp == 0) TR(3, 4 * p + 2);
       if (p >= 2) { mbar_wait(&h_free[b], ((p >> 1) - 1) & 1); tc_fence_after(); }   // MMA2 of pass p - 2 has read H[b]
+      if (warp == 0) TR(3, 4 * p + 3);
       tmem_st16(trow + Cfg::COL_H + b * 64 + cq * 16, v);
       tmem_st_wait();
       tc_fence_before();
@@ -267,8 +287,10 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       mbar_arrive(m2_ready);
     }
     // ------------------------------- workers: out = OUT + b2 + x (coalesced through a per-warp staging tile) -------------------------------
+    if (warp == 0) TR(0, 2);
     mbar_wait(out_full, 0);
     tc_fence_after();
+    if (warp == 0) TR(0, 3);
     float* stg = sStg + warp * 1024;                           // the A image is dead: every MMA1 retired long ago
     const int srow = lane >> 3, sj = lane & 7;
     {
@@ -310,6 +332,7 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       __syncwarp();
     }
   }
+  if (warp == 0) TR(0, 4);
   tc_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem, 512);

@@ -338,8 +338,21 @@ int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, c
     a.x = w.x1; a.L = Lq; a.tiles = cdiv(Lq, 128); a.ln_g = f.lnf_g; a.ln_b = f.lnf_b;
     a.w1_packed = f.w1f; a.b1 = f.b1; a.w2_packed = f.w2f; a.b2 = f.b2; a.out = out;
     a.m2 = tail_m2; a.w3_packed = tail_w3; a.b3 = tail_b3;
+#ifdef GMF_FFN_TRACE
+    static int n_ffn = 0;
+    const bool do_trace = (++n_ffn == 20);
+    if (do_trace) { cudaMalloc(&a.trace, 256 * 8); cudaMemsetAsync(a.trace, 0, 256 * 8, st); }
+#endif
     ProfScope ps(CAT_FFN1, st);
     cudaError_t e = launch_ffn_fused(a, B, st);
+#ifdef GMF_FFN_TRACE
+    if (do_trace) {
+      cudaStreamSynchronize(st);
+      long long h[256];
+      cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen("gpurun_out/ffn_trace.bin", "wb")) { fwrite(h, 1, sizeof(h), f); fclose(f); }
+    }
+#endif
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "ffn_fused launch");
     return 0;

@@ -231,7 +231,7 @@ void run_mma_rate(long long* d_out) {
 // T6: bulk-async (TMA engine) L2 -> shared streaming rate: every CTA streams the same `span` bytes (L2 resident) in `chunk`-byte
 // copies through a DEPTH-deep ring, like the K/V stream of the attention kernels.
 template <int DEPTH>
-__global__ void __launch_bounds__(64, 1) k_tma_stream(const uint8_t* src, size_t span, int chunk, int iters, int ctas_per_region, long long* out) {
+__global__ void __launch_bounds__(64, 1) k_tma_stream(const uint8_t* src, size_t span, int chunk, int iters, int ctas_per_region, long long* out, int skew = 0) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t full[DEPTH];
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(64, 1) k_tma_stream(const uint8_t* src, size_t
       if (it >= DEPTH) mbar_wait(&full[s], ((it / DEPTH) - 1) & 1);
       if (it < iters) {
         mbar_expect_tx(&full[s], chunk);
-        bulk_g2s(smem + (size_t)s * chunk, base + (size_t)(it % per) * chunk, chunk, &full[s]);
+        bulk_g2s(smem + (size_t)s * chunk, base + (size_t)((it + skew * (int)blockIdx.x * 7) % per) * chunk, chunk, &full[s]);
       }
     }
     out[blockIdx.x] = clock64() - t0;
@@ -324,6 +324,21 @@ int main() {
       long long mx = 0; for (int i = 0; i < 148; ++i) mx = ho[i] > mx ? ho[i] : mx;
       const double bpc = 148.0 * iters * chunk / mx;
       printf("  chunk %5d B, %3d CTAs per 3.2 MB region: %.0f B/clk chip-wide, %.1f B/clk/SM  (%.2f TB/s at %d MHz nominal)\n", chunk, cpr, bpc, bpc / 148, bpc * clk_khz * 1e3 / 1e12, clk_khz / 1000);
+    }
+  }
+  {
+    printf("== T6b same, but every CTA starts at a different offset of its region (desynchronised streams, no L2 request merging)\n");
+    const size_t span = 3276800;
+    uint8_t* d_src; CK(cudaMalloc(&d_src, span * 8)); CK(cudaMemset(d_src, 1, span * 8));
+    long long* d_o; CK(cudaMalloc(&d_o, 148 * 8));
+    long long ho[148];
+    for (int chunk : {16384, 32768}) for (int cpr : {148, 37}) {
+      const int iters = 4000;
+      for (int rep = 0; rep < 2; ++rep) { k_tma_stream<4><<<148, 64, 4 * chunk + 2048>>>(d_src, span, chunk, iters, cpr, d_o, 1); CK(cudaDeviceSynchronize()); }
+      CK(cudaMemcpy(ho, d_o, sizeof(ho), cudaMemcpyDeviceToHost));
+      long long mx = 0; for (int i = 0; i < 148; ++i) mx = ho[i] > mx ? ho[i] : mx;
+      const double bpc = 148.0 * iters * chunk / mx;
+      printf("  chunk %5d B, %3d CTAs per 3.2 MB region: %.0f B/clk chip-wide, %.1f B/clk/SM (%.2f TB/s at 1965 MHz)\n", chunk, cpr, bpc, bpc / 148, bpc * 1.965e9 / 1e12);
     }
   }
   printf("== T5 MMA rate by shape and A-operand source\n");
