@@ -246,6 +246,34 @@ def test_forward_matches_reference_golden(name):
     assert len(set(out["seeds"][0].tolist()) & set(fx["seeds"][0].tolist())) >= 0.85 * fx["seeds"].shape[1]
 
 
+@pytest.mark.parametrize("n,t", [(1000, 4800), (5000, 4800)])
+def test_baseline_sizes_match_live_oracle(n, t):
+    """BASELINE.json configs[0] (1000 correspondences, 480x640 image tokens) and configs[1] (5000) against the oracle run live on the
+    host cores with the same state_dict: logits within 1e-2, final pose within 0.01 deg / 1 mm, labels equal, and the teacher-forced
+    stages (seed picking on the oracle's logits) identical."""
+    from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
+    from gmf_b200.weights import hot_path_spec
+    cfg = dict(O.DEFAULT_CFG)
+    sd = synth_state_dict(hot_path_spec(12), seed=0, plain_init=False)
+    eng = make_engine(cfg, sd)
+    pr = synth_pairs(1, n, seed=100 + n, noise=0.002)
+    p_tok, q_tok = synth_tokens(1, t, 1), synth_tokens(1, t, 2)
+    args = [pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok]
+    ref = O.forward_testing(sd, cfg, *args, capture=True)
+    ref_seeds = ref["capture"][0]["seeds"]
+    out = eng.forward(*[x.cuda() for x in args], testing=True)
+    assert (out["confidence"].cpu() - ref["confidence"]).abs().max() < 1e-2
+    tr = out["final_trans"].cpu()
+    assert float(O.rotation_error_deg(tr[:, :3, :3], ref["final_trans"][:, :3, :3]).max()) < 0.01
+    assert float((tr[:, :3, 3] - ref["final_trans"][:, :3, 3]).norm(dim=-1).max()) < 1e-3
+    assert (out["final_labels"].cpu() != ref["final_labels"]).float().mean() < 0.002      # points within bf16 noise of the threshold
+    seeds = eng.pick_seeds(pr["src_keypts"].cuda(), ref["confidence"].cuda(), use_nms=True).cpu().long()
+    d = torch.norm(pr["src_keypts"][:, :, None] - pr["src_keypts"][:, None], dim=-1)
+    rel = (ref["confidence"].T >= ref["confidence"]) | (d[0] >= cfg["nms_radius"])
+    key = (ref["confidence"] * rel.min(-1)[0].float())[0]
+    assert _tie_groups_equal(seeds[0], ref_seeds.reshape(-1), key)
+
+
 def test_batched_forward_equals_per_pair_loop_and_is_deterministic():
     from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
     from gmf_b200.weights import hot_path_spec
