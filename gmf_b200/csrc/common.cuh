@@ -327,6 +327,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 #endif
 }
+// packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100: two lanes of fp32 per 64-bit register pair, one issue slot)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits)
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;

@@ -1,8 +1,9 @@
 // Spatial-consistency guided non-local attention, generation 9 (PointDSC.py:56-64, 216-221):
 //     msg_i = softmax_j( c_ij * q_i.k_j / sqrt(128) ) v_j,    c_ij = max(0, 1 - (|s_i-s_j| - |t_i-t_j|)^2 / sigma_d^2)
 // The N x N matrices never exist in HBM: per 128-query x 32-key tile the tensor pipe produces THREE fp32 accumulators in TMEM,
-//     S = Q K^T (log2 units), DA = |s_i - s_j|^2 / sigma^2, DB = 1 - |t_i - t_j|^2 / sigma^2   (sc_common.cuh: split-bf16 feature rows)
-// and the softmax threads evaluate  c = sat(2 sqrt(DA (1 - DB)) + DB - DA),  p = exp2(S c - ref)  in ~8 issue slots per element.
+//     S = Q K^T (log2 units), DA = |s_i - s_j|^2 / sigma^2, Y = |t_i - t_j|^2 / sigma^2 - 1   (sc_common.cuh: split-bf16 feature rows)
+// and the softmax threads evaluate  c = sat(2 sqrt(DA (Y + 1)) - (DA + Y)),  p = exp2(S c - ref)  in ~6 issue slots per element
+// (packed fp32x2 FFMA2 / FADD2 for the products and sums).
 // The softmax reference is FIXED per pass (0 first): floating point is scale invariant, so any reference within 2^+-80 of the row
 // maximum gives the same result; each thread tracks its row maximum and, if any row of the CTA leaves the window, the CTA repeats
 // the key loop once with the exact row maxima (block-wide vote, all roles take part).  No per-tile maximum exchange, no rescale.
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
       }
     } else {
       // ------------------------------------ softmax group g: virtual tiles v with (v & 1) == g ------------------------------------
-      float ps0 = 0.f, ps1 = 0.f;
+      uint64_t psum2 = pack2(0.f, 0.f);
       for (int j = g; j < nt; j += 2) {
         const int b = j % 3;
         const uint32_t tbuf = tlane + (uint32_t)b * 96u;
@@ -269,21 +270,20 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&s_free[b]);                             // the score issuer may refill this buffer with tile j + 3
+        const uint64_t nref2 = pack2(-ref, -ref);
         auto tile_body = [&](auto ragged_tag) {
           constexpr bool RAGGED = decltype(ragged_tag)::value;
 #pragma unroll
           for (int c = 0; c < HC; c += 2) {
-            float t0, t1;
-            {
-              const float da = __uint_as_float(ua[c]), db = __uint_as_float(ub[c]);
-              const float rt = sqrt_approx(fabsf(fmaf(-da, db, da)));
-              t0 = fmaf(__uint_as_float(us[c]), __saturatef(fmaf(rt, 2.f, db - da)), -ref);
-            }
-            {
-              const float da = __uint_as_float(ua[c + 1]), db = __uint_as_float(ub[c + 1]);
-              const float rt = sqrt_approx(fabsf(fmaf(-da, db, da)));
-              t1 = fmaf(__uint_as_float(us[c + 1]), __saturatef(fmaf(rt, 2.f, db - da)), -ref);
-            }
+            // two score elements per step on packed fp32x2 instructions (FFMA2 / FADD2): DA = |ds|^2/s^2, Y = |dt|^2/s^2 - 1
+            const uint64_t A2 = pack2(__uint_as_float(ua[c]), __uint_as_float(ua[c + 1]));
+            const uint64_t Y2 = pack2(__uint_as_float(ub[c]), __uint_as_float(ub[c + 1]));
+            float q0, q1, u0, u1, t0, t1;
+            unpack2(ffma2(A2, Y2, A2), q0, q1);                // |ds|^2 |dt|^2 / s^4
+            unpack2(fadd2(A2, Y2), u0, u1);                    // (|ds|^2 + |dt|^2) / s^2 - 1
+            const float c0 = __saturatef(fmaf(sqrt_approx(fabsf(q0)), 2.f, -u0));   // 1 - (|ds| - |dt|)^2 / s^2, clamped
+            const float c1 = __saturatef(fmaf(sqrt_approx(fabsf(q1)), 2.f, -u1));
+            unpack2(ffma2(pack2(__uint_as_float(us[c]), __uint_as_float(us[c + 1])), pack2(c0, c1), nref2), t0, t1);
             if (RAGGED) {
               if (h * HC + c >= nvalid) t0 = -INFINITY;
               if (h * HC + c + 1 >= nvalid) t1 = -INFINITY;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
             rmax = fmaxf(rmax, fmaxf(t0, t1));
             const float p0 = (!RAGGED && (c & 3) < POLY) ? ex2_poly(t0) : ex2_approx(t0);
             const float p1 = (!RAGGED && ((c + 1) & 3) < POLY) ? ex2_poly(t1) : ex2_approx(t1);
-            ps0 += p0; ps1 += p1;
+            psum2 = fadd2(psum2, pack2(p0, p1));
             pk[c >> 1] = pack_bf16(p0, p1);
           }
         };
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
         tc_fence_before();
         mbar_arrive(&p_ready[g]);
       }
-      l_sum += ps0 + ps1;
+      { float ps0, ps1; unpack2(psum2, ps0, ps1); l_sum += ps0 + ps1; }
       sX[part * 128 + r] = rmax;
       asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
       float comb = rmax;

@@ -44,10 +44,10 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 
 
-// distance-feature tiles: coordinates are pre-divided by sigma_d, the t-part carries the flipped sign and the
-// constant so that the accumulators are  DA = |ds|^2 / sigma^2  and  DB = 1 - |dt|^2 / sigma^2.
-//   s-part A: per coord (-2u0,-2u0,-2u1,-2u1,-2u0,-2u2), |u|^2 split (n0,n1,n2), (1,1,1)       B: (w0,w1,w0,w1,w2,w0), (1,1,1), |w|^2 split
-//   t-part A: per coord (+2u0,...),                       -|u|^2 split,          (-1,-1,-1), 1  B: same as s-part,                         , 1
+// distance-feature tiles: coordinates are pre-divided by sigma_d and the t-part carries a constant so that the accumulators are
+//   DA = |ds|^2 / sigma^2  and  Y = |dt|^2 / sigma^2 - 1   (the softmax needs DA (Y + 1) and DA + Y: no negations, packed fp32x2 friendly).
+//   A (query side): per coord (-2u0,-2u0,-2u1,-2u1,-2u0,-2u2), |u|^2 split (n0,n1,n2), (1,1,1) [, -1 in the t-part]
+//   B (key side):   per coord (  w0,  w1,  w0,  w1,  w2,  w0), (1,1,1), |w|^2 split             [,  1 in the t-part]
 __global__ void dist_feature_scaled_kernel(const float* __restrict__ kpts, int Np, float inv_sigma, __nv_bfloat16* __restrict__ aq_t,
                                            __nv_bfloat16* __restrict__ bd_t) {
   const int pair = blockIdx.y;
@@ -66,7 +66,7 @@ __global__ void dist_feature_scaled_kernel(const float* __restrict__ kpts, int N
 #pragma unroll
   for (int part = 0; part < 2; ++part) {
     const int o = part * 32;
-    const float sg = part ? 2.f : -2.f;
+    const float sg = -2.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       __nv_bfloat16 h0, h1, h2;
@@ -81,13 +81,13 @@ __global__ void dist_feature_scaled_kernel(const float* __restrict__ kpts, int N
       A[o + 6 * c + 5] = m2; B[o + 6 * c + 5] = h0;
     }
     __nv_bfloat16 n0, n1, n2;
-    split3(part ? -pts[part][3] : pts[part][3], n0, n1, n2);           // A side: +-|u|^2
+    split3(pts[part][3], n0, n1, n2);                                   // A side: |u|^2
     __nv_bfloat16 w0, w1, w2;
     split3(pts[part][3], w0, w1, w2);                                   // B side: |w|^2, multiplied by +-1 from the A side
-    const __nv_bfloat16 sgn1 = part ? mone : one;
+    const __nv_bfloat16 sgn1 = one;
     A[o + 18] = n0; A[o + 19] = n1; A[o + 20] = n2; B[o + 18] = one; B[o + 19] = one; B[o + 20] = one;
     A[o + 21] = sgn1; A[o + 22] = sgn1; A[o + 23] = sgn1; B[o + 21] = w0; B[o + 22] = w1; B[o + 23] = w2;
-    if (part) { A[o + 24] = one; B[o + 24] = one; }
+    if (part) { A[o + 24] = mone; B[o + 24] = one; }
   }
   const int tile = i >> 7, r = i & 127;
   const size_t tbase = ((size_t)pair * (Np >> 7) + tile) * (128 * 64);
