@@ -206,6 +206,10 @@ struct gmf_ctx {
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
+  int overlap = 1;                      // context K/V and query projections run on side streams next to the SC attention
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_img = nullptr, ev_f1 = nullptr, ev_q = nullptr;
+  std::vector<cudaEvent_t> ev_kv;
   cudaStream_t copy_stream = nullptr;   // uploads of the next chunk overlap the current chunk's kernels
   cudaEvent_t copy_ev[64] = {};
   cudaEvent_t start_ev = nullptr;
@@ -221,6 +225,8 @@ struct Work {
   float *kpts; float4 *src4, *tgt4;
   float *imgfeat, *featA, *feat1, *x0, *x1, *x2, *of, *g_t, *msg, *m1, *m2;
   __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts, *aq, *bd;
+  __nv_bfloat16 *kf_all, *vtf_all;   // [layers] context K / V^T tiles of every encoder layer (projected up front on a side stream)
+  size_t kv_stride;
   float *normed, *conf, *key, *seed_w, *seed_trans, *pre_refine, *dist, *seedM;
   int *seeds, *knn, *counts, *best;
   unsigned* pair_mask;
@@ -236,7 +242,7 @@ struct Bump {
 };
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k) {
+size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k, int layers) {
   Bump b{base};
   const int nt = cdiv(N, 128), tt = cdiv(std::max(T, 1), 128);
   const size_t Lm = (size_t)std::max(N, T), tm = (size_t)std::max(nt, tt);
@@ -250,6 +256,8 @@ size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k) {
   w.msg = b.take<float>((size_t)B * N * 128); w.m1 = b.take<float>((size_t)B * N * 64); w.m2 = b.take<float>((size_t)B * N * 64);
   w.qf = b.take<__nv_bfloat16>(B * tm * 128 * 64);
   w.kf = b.take<__nv_bfloat16>(B * tm * 128 * 64); w.vtf = b.take<__nv_bfloat16>(B * tm * 128 * 64);
+  w.kv_stride = (size_t)B * tt * 128 * 64;
+  w.kf_all = b.take<__nv_bfloat16>(w.kv_stride * layers); w.vtf_all = b.take<__nv_bfloat16>(w.kv_stride * layers);
   w.qs = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128);
   w.ks = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128); w.vts = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128);
   w.aq = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 64); w.bd = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 64);
@@ -269,10 +277,10 @@ inline int eff_k(const gmf_ctx* c, int N) { return std::min(c->cfg.k, N - 1); }
 int check_ws(const gmf_ctx* ctx, Work& w, void* ws, size_t bytes, int B, int N, int T) {
   if (!ws) return fail(GMF_ERR_INVALID, "workspace is NULL");
   const int S = std::max(num_seeds(ctx, N), 1), k = std::max(eff_k(ctx, N), 1);
-  const size_t need = carve(w, nullptr, B, N, T, S, k);
+  const size_t need = carve(w, nullptr, B, N, T, S, k, ctx->cfg.num_layers);
   if (bytes < need) return fail(GMF_ERR_STATE, "workspace too small: need " + std::to_string(need) + " bytes");
   uint8_t* base = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
-  carve(w, base, B, N, T, S, k);
+  carve(w, base, B, N, T, S, k, ctx->cfg.num_layers);
   return 0;
 }
 
@@ -294,33 +302,49 @@ LinArgs lin(const float* x, int L, const float* w, const float* bias) {
   return a;
 }
 
-// FusionLayer.forward (fusion_layer.py:172-201)
+// queries: (CPE) -> LN -> to_q => bf16 Q tiles (scale folded); returns the residual stream (x, or x + dwconv(x) when pe)
+int run_fusion_q(const FusionW& f, Work& w, const float* xq, int B, int Lq, const float** resid0, cudaStream_t st) {
+  *resid0 = xq;
+  LinArgs a = lin(xq, Lq, f.wq, nullptr);
+  a.ln_g = f.lnq_g; a.ln_b = f.lnq_b; a.t0 = w.qf;
+  if (f.pe) {
+    a.cpe_w = f.cpe_q_w; a.cpe_b = f.cpe_q_b; a.x0_out = w.x0; *resid0 = w.x0;
+    TRY((run_linear<128, 64, PRO_CPE_LN, EPI_Q_FUS>(a, B, st, CAT_QFUS)));
+  } else {
+    TRY((run_linear<128, 64, PRO_LN, EPI_Q_FUS>(a, B, st, CAT_QFUS)));
+  }
+  return 0;
+}
+// context: (CPE) -> LN_ctx -> to_kv => bf16 K tiles, V^T tiles
+int run_fusion_kv(const FusionW& f, const float* ctxk, int B, int Lk, __nv_bfloat16* kf, __nv_bfloat16* vtf, cudaStream_t st) {
+  LinArgs a = lin(ctxk, Lk, f.wkv, nullptr);
+  a.ln_g = f.lnc_g; a.ln_b = f.lnc_b; a.t1 = kf; a.t2 = vtf;
+  if (f.pe) {
+    a.cpe_w = f.cpe_c_w; a.cpe_b = f.cpe_c_b; a.x0_out = nullptr;
+    TRY((run_linear<128, 128, PRO_CPE_LN, EPI_KV_FUS>(a, B, st, CAT_KVFUS)));
+  } else {
+    TRY((run_linear<128, 128, PRO_LN, EPI_KV_FUS>(a, B, st, CAT_KVFUS)));
+  }
+  return 0;
+}
+int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* resid0, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
+                    float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3);
+
+// FusionLayer.forward (fusion_layer.py:172-201), everything on one stream
 int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st,
                const float* tail_m2 = nullptr, const float* tail_w3 = nullptr, const float* tail_b3 = nullptr) {
-  const float* resid0 = xq;
-  {  // queries: (CPE) -> LN -> to_q  => bf16 Q tiles (scale folded)
-    LinArgs a = lin(xq, Lq, f.wq, nullptr);
-    a.ln_g = f.lnq_g; a.ln_b = f.lnq_b; a.t0 = w.qf;
-    if (f.pe) {
-      a.cpe_w = f.cpe_q_w; a.cpe_b = f.cpe_q_b; a.x0_out = w.x0; resid0 = w.x0;
-      TRY((run_linear<128, 64, PRO_CPE_LN, EPI_Q_FUS>(a, B, st, CAT_QFUS)));
-    } else {
-      TRY((run_linear<128, 64, PRO_LN, EPI_Q_FUS>(a, B, st, CAT_QFUS)));
-    }
-  }
-  {  // context: (CPE) -> LN_ctx -> to_kv => bf16 K tiles, V^T tiles
-    LinArgs a = lin(ctxk, Lk, f.wkv, nullptr);
-    a.ln_g = f.lnc_g; a.ln_b = f.lnc_b; a.t1 = w.kf; a.t2 = w.vtf;
-    if (f.pe) {
-      a.cpe_w = f.cpe_c_w; a.cpe_b = f.cpe_c_b; a.x0_out = nullptr;
-      TRY((run_linear<128, 128, PRO_CPE_LN, EPI_KV_FUS>(a, B, st, CAT_KVFUS)));
-    } else {
-      TRY((run_linear<128, 128, PRO_LN, EPI_KV_FUS>(a, B, st, CAT_KVFUS)));
-    }
-  }
+  const float* resid0 = nullptr;
+  TRY(run_fusion_q(f, w, xq, B, Lq, &resid0, st));
+  TRY(run_fusion_kv(f, ctxk, B, Lk, w.kf, w.vtf, st));
+  return run_fusion_core(ctx, f, w, resid0, w.kf, w.vtf, B, Lq, Lk, out, st, tail_m2, tail_w3, tail_b3);
+}
+
+// attention (+ to_out + residual) and the GEGLU feed-forward block
+int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* resid0, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
+                    float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3) {
   {
     AttnArgs a{};
-    a.q_t = w.qf; a.k_t = w.kf; a.vt_t = w.vtf; a.out = w.of;
+    a.q_t = w.qf; a.k_t = kf; a.vt_t = vtf; a.out = w.of;
     a.Lq = Lq; a.Lk = Lk; a.q_tiles = cdiv(Lq, 128); a.k_tiles = cdiv(Lk, 128);
     if (ctx->fus_impl >= 3) { a.wo_packed = f.wo; a.bo = f.bo; a.resid = resid0; a.xout = w.x1; }   // to_out + bias + residual fused
     ProfScope ps(CAT_ATTN_FUS, st);
@@ -411,7 +435,7 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
 
 // PointCN_layer_i + NonLocal_layer_i (PointDSC.py:140-142, 40-74)
 int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in, const float* image_feat, int B, int N, int T,
-                      float* feat_out, cudaStream_t st) {
+                      float* feat_out, cudaStream_t st, bool overlapped = false) {
   const LayerW& lw = ctx->layers[li];
   const bool chain = ctx->pcn_qkv != 0;                        // PointCN + QKV projection as one chained-GEMM kernel
   if (chain) {
@@ -428,6 +452,15 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     TRY((run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, B, st, CAT_PCN)));
   }
   const bool fuse_fc = ctx->sc_fuse_fc != 0;   // fc_message.0/.3 run as the tail of the gen-9 attention kernel
+  const float* resid0 = nullptr;
+  if (overlapped) {
+    // the Fusion-2 query projection only needs feat1: it runs on a side stream next to the SC attention (whose last, partial wave
+    // of CTAs leaves most SMs idle); the context K / V^T of this layer were projected up front (forward_chunk)
+    CU(cudaEventRecord(ctx->ev_f1, st));
+    CU(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_f1, 0));
+    TRY(run_fusion_q(lw.f2, w, w.feat1, B, N, &resid0, ctx->aux[1]));
+    CU(cudaEventRecord(ctx->ev_q, ctx->aux[1]));
+  }
   TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st, fuse_fc ? w.m2 : nullptr, chain));
   if (!fuse_fc) {
     LinArgs a = lin(w.msg, N, lw.fc1_w, lw.fc1_b);
@@ -438,6 +471,12 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     LinArgs a = lin(w.m1, N, lw.fc2_w, lw.fc2_b);
     a.out = w.m2;
     TRY((run_linear<64, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
+  }
+  if (overlapped) {
+    CU(cudaStreamWaitEvent(st, ctx->ev_q, 0));
+    CU(cudaStreamWaitEvent(st, ctx->ev_kv[li], 0));
+    return run_fusion_core(ctx, lw.f2, w, resid0, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
+                           lw.fc3_w, lw.fc3_b);
   }
   if (ctx->ffn_impl >= 3) {   // fc_message.6(m2) + fusion_layer_2 output (PointDSC.py:73) folded into the fused FFN kernel's tail
     TRY(run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, feat_out, st, w.m2, lw.fc3_w, lw.fc3_b));
@@ -545,7 +584,25 @@ int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, co
   }
   // Fusion-1: queries = q-image tokens, context = p-image tokens (PointDSC.py:137)
   TRY(run_fusion(ctx, ctx->f1, w, q_tok, p_tok, B, T, T, w.imgfeat, st));
-  for (int li = 0; li < ctx->cfg.num_layers; ++li) TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st));
+  const int L = ctx->cfg.num_layers;
+  const bool overlapped = ctx->overlap && ctx->sc_fuse_fc && ctx->ffn_impl >= 3 && ctx->fus_impl >= 3;
+  if (overlapped) {
+    if (!ctx->aux[0]) {
+      for (auto& a : ctx->aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ctx->ev_img, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ctx->ev_f1, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ctx->ev_q, cudaEventDisableTiming));
+    }
+    while ((int)ctx->ev_kv.size() < L) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_kv.push_back(e); }
+    // every layer's context K / V^T depends only on the Fusion-1 output: project them all on a side stream, behind the encoder
+    CU(cudaEventRecord(ctx->ev_img, st));
+    CU(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_img, 0));
+    for (int li = 0; li < L; ++li) {
+      TRY(run_fusion_kv(ctx->layers[li].f2, w.imgfeat, B, T, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, ctx->aux[0]));
+      CU(cudaEventRecord(ctx->ev_kv[li], ctx->aux[0]));
+    }
+  }
+  for (int li = 0; li < L; ++li) TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped));
   if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
   TRY(run_classify(ctx, w.featA, (long long)B * N, w.normed, conf_out, st));
   TRY(run_pick_seeds(ctx, w, conf_out, B, N, S, testing ? 1 : 0, seeds_out, st));
@@ -653,6 +710,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   if (const char* e = getenv("GMF_FFN_IMPL")) c->ffn_impl = atoi(e);
   if (const char* e = getenv("GMF_SC_FUSE_FC")) c->sc_fuse_fc = atoi(e);
   if (const char* e = getenv("GMF_PCN_QKV")) c->pcn_qkv = atoi(e);
+  if (const char* e = getenv("GMF_OVERLAP")) c->overlap = atoi(e);
   *out = c;
   return 0;
 }
@@ -662,6 +720,11 @@ void gmf_destroy(gmf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->blob) cudaFree(ctx->blob);
   if (ctx->stage) cudaFree(ctx->stage);
+  if (ctx->aux[0]) {
+    cudaStreamDestroy(ctx->aux[0]); cudaStreamDestroy(ctx->aux[1]);
+    cudaEventDestroy(ctx->ev_img); cudaEventDestroy(ctx->ev_f1); cudaEventDestroy(ctx->ev_q);
+    for (auto e : ctx->ev_kv) cudaEventDestroy(e);
+  }
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);
     for (auto e : ctx->copy_ev) if (e) cudaEventDestroy(e);
@@ -825,7 +888,7 @@ size_t gmf_workspace_bytes(const gmf_ctx* ctx, int B, int N, int T) {
   if (!ctx || B < 1 || N < 2) return 0;
   Work w;
   const int Bc = std::min(B, ctx->chunk_pairs);
-  return carve(w, nullptr, Bc, N, T, std::max(num_seeds(ctx, N), 1), std::max(eff_k(ctx, N), 1)) + 1024;
+  return carve(w, nullptr, Bc, N, T, std::max(num_seeds(ctx, N), 1), std::max(eff_k(ctx, N), 1), ctx->cfg.num_layers) + 1024;
 }
 
 int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
