@@ -206,10 +206,17 @@ struct gmf_ctx {
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
-  int overlap = 1;                      // context K/V and query projections run on side streams next to the SC attention
-  cudaStream_t aux[2] = {nullptr, nullptr};
-  cudaEvent_t ev_img = nullptr, ev_f1 = nullptr, ev_q = nullptr;
-  std::vector<cudaEvent_t> ev_kv;
+  // overlap: (1) inside a lane the context K/V and query projections run on side streams next to the SC attention; (2) a chunk of
+  // pairs is split into two lanes that run the whole path concurrently, so one lane's partial waves and small tail kernels
+  // (sort, spectral matching, refinement) are filled by the other lane's attention CTAs.
+  int overlap = 1;                      // 0 = single stream, 1 = side streams, 2 = side streams + two lanes
+  struct Lane {
+    cudaStream_t main = nullptr;          // lane 0 runs on the caller's stream, lane 1 on this one
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_img = nullptr, ev_f1 = nullptr, ev_q = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> ev_kv;
+  } lanes[2];
+  cudaEvent_t ev_fork = nullptr;
   cudaStream_t copy_stream = nullptr;   // uploads of the next chunk overlap the current chunk's kernels
   cudaEvent_t copy_ev[64] = {};
   cudaEvent_t start_ev = nullptr;
@@ -435,7 +442,8 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
 
 // PointCN_layer_i + NonLocal_layer_i (PointDSC.py:140-142, 40-74)
 int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in, const float* image_feat, int B, int N, int T,
-                      float* feat_out, cudaStream_t st, bool overlapped = false) {
+                      float* feat_out, cudaStream_t st, const gmf_ctx::Lane* lane = nullptr) {
+  const bool overlapped = lane != nullptr;
   const LayerW& lw = ctx->layers[li];
   const bool chain = ctx->pcn_qkv != 0;                        // PointCN + QKV projection as one chained-GEMM kernel
   if (chain) {
@@ -456,10 +464,10 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
   if (overlapped) {
     // the Fusion-2 query projection only needs feat1: it runs on a side stream next to the SC attention (whose last, partial wave
     // of CTAs leaves most SMs idle); the context K / V^T of this layer were projected up front (forward_chunk)
-    CU(cudaEventRecord(ctx->ev_f1, st));
-    CU(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_f1, 0));
-    TRY(run_fusion_q(lw.f2, w, w.feat1, B, N, &resid0, ctx->aux[1]));
-    CU(cudaEventRecord(ctx->ev_q, ctx->aux[1]));
+    CU(cudaEventRecord(lane->ev_f1, st));
+    CU(cudaStreamWaitEvent(lane->aux[1], lane->ev_f1, 0));
+    TRY(run_fusion_q(lw.f2, w, w.feat1, B, N, &resid0, lane->aux[1]));
+    CU(cudaEventRecord(lane->ev_q, lane->aux[1]));
   }
   TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st, fuse_fc ? w.m2 : nullptr, chain));
   if (!fuse_fc) {
@@ -473,8 +481,8 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     TRY((run_linear<64, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
   }
   if (overlapped) {
-    CU(cudaStreamWaitEvent(st, ctx->ev_q, 0));
-    CU(cudaStreamWaitEvent(st, ctx->ev_kv[li], 0));
+    CU(cudaStreamWaitEvent(st, lane->ev_q, 0));
+    CU(cudaStreamWaitEvent(st, lane->ev_kv[li], 0));
     return run_fusion_core(ctx, lw.f2, w, resid0, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
                            lw.fc3_w, lw.fc3_b);
   }
@@ -571,7 +579,7 @@ int run_score(const gmf_ctx* ctx, Work& w, const float* seed_trans, int B, int N
   return 0;
 }
 
-int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
+int forward_chunk(gmf_ctx* ctx, gmf_ctx::Lane* lane, Work& w, const float* corr, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
                   int B, int N, int T, int testing, float* final_trans, float* labels, float* conf_out, int* seeds_out, float* feat_out,
                   cudaStream_t st) {
   const int S = num_seeds(ctx, N), k = eff_k(ctx, N);
@@ -585,24 +593,18 @@ int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, co
   // Fusion-1: queries = q-image tokens, context = p-image tokens (PointDSC.py:137)
   TRY(run_fusion(ctx, ctx->f1, w, q_tok, p_tok, B, T, T, w.imgfeat, st));
   const int L = ctx->cfg.num_layers;
-  const bool overlapped = ctx->overlap && ctx->sc_fuse_fc && ctx->ffn_impl >= 3 && ctx->fus_impl >= 3;
+  // per-launch profiling (gmf_profile_enable) times every kernel alone: it uses the single-stream schedule
+  const bool overlapped = lane && !ctx->prof.on && ctx->sc_fuse_fc && ctx->ffn_impl >= 3 && ctx->fus_impl >= 3;
   if (overlapped) {
-    if (!ctx->aux[0]) {
-      for (auto& a : ctx->aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&ctx->ev_img, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&ctx->ev_f1, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&ctx->ev_q, cudaEventDisableTiming));
-    }
-    while ((int)ctx->ev_kv.size() < L) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_kv.push_back(e); }
     // every layer's context K / V^T depends only on the Fusion-1 output: project them all on a side stream, behind the encoder
-    CU(cudaEventRecord(ctx->ev_img, st));
-    CU(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_img, 0));
+    CU(cudaEventRecord(lane->ev_img, st));
+    CU(cudaStreamWaitEvent(lane->aux[0], lane->ev_img, 0));
     for (int li = 0; li < L; ++li) {
-      TRY(run_fusion_kv(ctx->layers[li].f2, w.imgfeat, B, T, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, ctx->aux[0]));
-      CU(cudaEventRecord(ctx->ev_kv[li], ctx->aux[0]));
+      TRY(run_fusion_kv(ctx->layers[li].f2, w.imgfeat, B, T, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, lane->aux[0]));
+      CU(cudaEventRecord(lane->ev_kv[li], lane->aux[0]));
     }
   }
-  for (int li = 0; li < L; ++li) TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped));
+  for (int li = 0; li < L; ++li) TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped ? lane : nullptr));
   if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
   TRY(run_classify(ctx, w.featA, (long long)B * N, w.normed, conf_out, st));
   TRY(run_pick_seeds(ctx, w, conf_out, B, N, S, testing ? 1 : 0, seeds_out, st));
@@ -720,11 +722,13 @@ void gmf_destroy(gmf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->blob) cudaFree(ctx->blob);
   if (ctx->stage) cudaFree(ctx->stage);
-  if (ctx->aux[0]) {
-    cudaStreamDestroy(ctx->aux[0]); cudaStreamDestroy(ctx->aux[1]);
-    cudaEventDestroy(ctx->ev_img); cudaEventDestroy(ctx->ev_f1); cudaEventDestroy(ctx->ev_q);
-    for (auto e : ctx->ev_kv) cudaEventDestroy(e);
+  for (auto& ln : ctx->lanes) {
+    if (!ln.aux[0]) continue;
+    cudaStreamDestroy(ln.main); cudaStreamDestroy(ln.aux[0]); cudaStreamDestroy(ln.aux[1]);
+    cudaEventDestroy(ln.ev_img); cudaEventDestroy(ln.ev_f1); cudaEventDestroy(ln.ev_q); cudaEventDestroy(ln.ev_done);
+    for (auto e : ln.ev_kv) cudaEventDestroy(e);
   }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);
     for (auto e : ctx->copy_ev) if (e) cudaEventDestroy(e);
@@ -888,7 +892,10 @@ size_t gmf_workspace_bytes(const gmf_ctx* ctx, int B, int N, int T) {
   if (!ctx || B < 1 || N < 2) return 0;
   Work w;
   const int Bc = std::min(B, ctx->chunk_pairs);
-  return carve(w, nullptr, Bc, N, T, std::max(num_seeds(ctx, N), 1), std::max(eff_k(ctx, N), 1), ctx->cfg.num_layers) + 1024;
+  const int S = std::max(num_seeds(ctx, N), 1), k = std::max(eff_k(ctx, N), 1), L = ctx->cfg.num_layers;
+  const size_t whole = carve(w, nullptr, Bc, N, T, S, k, L);
+  const size_t lanes = 2 * ((carve(w, nullptr, (Bc + 1) / 2, N, T, S, k, L) + 1023) & ~(size_t)1023);   // two concurrent half-chunks
+  return std::max(whole, lanes) + 2048;
 }
 
 int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
@@ -903,14 +910,51 @@ int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, 
   cudaStream_t st = (cudaStream_t)stream;
   const int S = num_seeds(ctx, N);
   const int Bc = std::min(B, ctx->chunk_pairs);
-  Work w;
-  TRY(check_ws(ctx, w, workspace, workspace_bytes, Bc, N, T));
+  const int L = ctx->cfg.num_layers;
+  if (ctx->overlap) {
+    for (auto& ln : ctx->lanes) {
+      if (!ln.aux[0]) {
+        CU(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
+        for (auto& a : ln.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&ln.ev_img, &ln.ev_f1, &ln.ev_q, &ln.ev_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+      }
+      while ((int)ln.ev_kv.size() < L) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.ev_kv.push_back(e); }
+    }
+    if (!ctx->ev_fork) CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  }
+  const bool two_lanes = ctx->overlap >= 2 && Bc >= 8;         // GMF_OVERLAP=2: measured slightly slower than side streams alone (36.6 vs 36.2 ms)
+  const int Bl = two_lanes ? (Bc + 1) / 2 : Bc;                // pairs per lane
+  Work w[2];
+  {
+    if (!workspace) return fail(GMF_ERR_INVALID, "workspace is NULL");
+    const int Sw = std::max(S, 1), kw = std::max(eff_k(ctx, N), 1);
+    const size_t lane_bytes = (carve(w[0], nullptr, Bl, N, T, Sw, kw, L) + 1023) & ~(size_t)1023;
+    if (workspace_bytes < lane_bytes * (two_lanes ? 2 : 1) + 1024)
+      return fail(GMF_ERR_STATE, "workspace too small: need " + std::to_string(lane_bytes * (two_lanes ? 2 : 1) + 1024) + " bytes");
+    uint8_t* base = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    carve(w[0], base, Bl, N, T, Sw, kw, L);
+    if (two_lanes) carve(w[1], base + lane_bytes, Bl, N, T, Sw, kw, L);
+  }
+  auto run = [&](int lane_id, cudaStream_t ls, int b0, int nb) -> int {
+    return forward_chunk(ctx, ctx->overlap ? &ctx->lanes[lane_id] : nullptr, w[lane_id], corr_pos + (size_t)b0 * N * 6, src + (size_t)b0 * N * 3,
+                         tgt + (size_t)b0 * N * 3, p_tok + (size_t)b0 * T * 128, q_tok + (size_t)b0 * T * 128, nb, N, T, testing,
+                         final_trans + (size_t)b0 * 16, final_labels + (size_t)b0 * N, confidence + (size_t)b0 * N, seeds + (size_t)b0 * S,
+                         feat ? feat + (size_t)b0 * N * 128 : nullptr, ls);
+  };
   for (int b0 = 0; b0 < B; b0 += Bc) {
     const int nb = std::min(Bc, B - b0);
-    TRY(forward_chunk(ctx, w, corr_pos + (size_t)b0 * N * 6, src + (size_t)b0 * N * 3, tgt + (size_t)b0 * N * 3,
-                      p_tok + (size_t)b0 * T * 128, q_tok + (size_t)b0 * T * 128, nb, N, T, testing, final_trans + (size_t)b0 * 16,
-                      final_labels + (size_t)b0 * N, confidence + (size_t)b0 * N, seeds + (size_t)b0 * S,
-                      feat ? feat + (size_t)b0 * N * 128 : nullptr, st));
+    if (two_lanes && nb >= 2) {
+      const int n0 = (nb + 1) / 2;
+      cudaStream_t s1 = ctx->lanes[1].main;
+      CU(cudaEventRecord(ctx->ev_fork, st));                   // lane 1 starts after everything already queued on the caller's stream
+      CU(cudaStreamWaitEvent(s1, ctx->ev_fork, 0));
+      TRY(run(1, s1, b0 + n0, nb - n0));
+      CU(cudaEventRecord(ctx->lanes[1].ev_done, s1));
+      TRY(run(0, st, b0, n0));
+      CU(cudaStreamWaitEvent(st, ctx->lanes[1].ev_done, 0));   // join
+    } else {
+      TRY(run(0, st, b0, nb));
+    }
   }
   return 0;
 }
