@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
       }
     } else if (softmax_role) {
       // ------------------------------------ softmax: row tile t, column half h ------------------------------------
-      float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+      float ps0 = 0.f, ps1 = 0.f;
+      uint64_t psA = pack2(0.f, 0.f), psB = psA;
       for (int j = 0; j < nt; ++j) {
         const int b = j & 1;
         mbar_wait(&s_full[2 * t + b], (j >> 1) & 1);
@@ -227,13 +228,16 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
         mbar_arrive(&s_free[2 * t + b]);                     // the score issuer may refill this buffer with tile j + 2
         const int nvalid = a.Lk - j * BN - h * 32;
         if (nvalid >= 32) {
+          // packed fp32x2 adds (FADD2) for the reference shift and the row sums: 3 issue slots per element besides the MUFU
+          const uint64_t nref2 = pack2(-ref, -ref);
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            const float t0 = __uint_as_float(us[c]) - ref, t1 = __uint_as_float(us[c + 1]) - ref;
-            const float t2 = __uint_as_float(us[c + 2]) - ref, t3 = __uint_as_float(us[c + 3]) - ref;
+            float t0, t1, t2, t3;
+            unpack2(fadd2(pack2(__uint_as_float(us[c]), __uint_as_float(us[c + 1])), nref2), t0, t1);
+            unpack2(fadd2(pack2(__uint_as_float(us[c + 2]), __uint_as_float(us[c + 3])), nref2), t2, t3);
             rmax = fmaxf(rmax, fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)));
             const float p0 = ex2_approx(t0), p1 = ex2_approx(t1), p2 = ex2_approx(t2), p3 = ex2_approx(t3);
-            ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+            psA = fadd2(psA, pack2(p0, p1)); psB = fadd2(psB, pack2(p2, p3));
             pk[c >> 1] = pack_bf16(p0, p1); pk[(c >> 1) + 1] = pack_bf16(p2, p3);
           }
         } else {                                             // ragged last key tile (warp-uniform)
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
         tc_fence_before();
         mbar_arrive(&p_ready[t]);
       }
-      l_sum += (ps0 + ps1) + (ps2 + ps3);
+      { float a0, a1, b0, b1; unpack2(psA, a0, a1); unpack2(psB, b0, b1); l_sum += (ps0 + ps1) + ((a0 + a1) + (b0 + b1)); }
       sX[(t * 2 + h) * 128 + r] = rmax;
       asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
       const float comb = fmaxf(rmax, sX[(t * 2 + (h ^ 1)) * 128 + r]);
