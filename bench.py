@@ -67,6 +67,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None            # wall-clock bounds of the timed region (rows are stamped on arrival)
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
@@ -80,7 +87,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def __exit__(self, *exc):
         if self.proc:
@@ -91,8 +98,17 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        # samples inside the timed region; nvidia-smi reports every 100 ms, so a region of a few steps holds only a handful: the
+        # sample taken just before it (same load: the last warm-up step) is kept as well so that there is always at least one
+        rows = self.rows
+        if self.t0 is not None and self.t1 is not None:
+            inside = [r for t, r in rows if self.t0 <= t <= self.t1 + 0.12]
+            before = [r for t, r in rows if self.t0 - 0.25 <= t < self.t0]
+            rows = inside + before[-1:]
+        else:
+            rows = [r for _, r in rows]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
@@ -210,12 +226,15 @@ def main():
     step_dev = lambda: eng.forward(*devt, testing=True)                                    # noqa: E731
     step_host = lambda: eng.forward_host(*host, h_trans, h_lab, h_conf, testing=True)      # noqa: E731
 
-    for _ in range(max(a.warmup, a.min_warmup)):
-        out = step_dev()
-    torch.cuda.synchronize()
-    eng.launch_count(reset=True)
-    with ClockSampler(local) as cs:
+    with ClockSampler(local) as cs:                              # started before the warm-up: nvidia-smi needs ~0.2 s to come up
+        for _ in range(max(a.warmup, a.min_warmup)):
+            out = step_dev()
+        torch.cuda.synchronize()
+        eng.launch_count(reset=True)
+        cs.mark_start()
         ms = timed(step_dev, a.steps)
+        cs.mark_end()
+        time.sleep(0.12)                                         # let the sample that covers the end of the region arrive
     launches = eng.launch_count(reset=True)
     clocks = cs.summary()
     value = world * a.pairs * a.steps / (ms / 1000.0)
