@@ -528,15 +528,9 @@ int run_pick_seeds(const gmf_ctx* ctx, Work& w, const float* conf, int B, int N,
   return 0;
 }
 
-template <int SPC>
 int launch_select(const float* dist, int B, int N, int S, int k, int* knn, cudaStream_t st) {
-  const size_t smem = (size_t)SPC * N * 4 + (size_t)SPC * 2 * kSelCap * 4;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU(cudaFuncSetAttribute(seed_select_kernel<SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  seed_select_kernel<SPC><<<dim3(cdiv(S, SPC), B), SPC * 32, smem, st>>>(dist, N, S, k, knn);
+  constexpr int SPC = 8;
+  seed_select_kernel<SPC><<<dim3(cdiv(S, SPC), B), SPC * 32, 0, st>>>(dist, N, S, k, knn);
   LAUNCHED();
   return 0;
 }
@@ -548,12 +542,7 @@ int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const 
     ProfScope ps(CAT_KNN, st);
     seed_dist_kernel<<<dim3(cdiv(N, 128), cdiv(S, 128), B), 256, 0, st>>>(normed, seeds, N, S, w.dist);
     LAUNCHED();
-    const size_t budget = 200 * 1024 - 8 * 2 * kSelCap * 4;
-    if ((size_t)8 * N * 4 <= budget) TRY(launch_select<8>(w.dist, B, N, S, k, knn, st));
-    else if ((size_t)4 * N * 4 <= budget) TRY(launch_select<4>(w.dist, B, N, S, k, knn, st));
-    else if ((size_t)2 * N * 4 <= budget) TRY(launch_select<2>(w.dist, B, N, S, k, knn, st));
-    else if ((size_t)N * 4 <= budget) TRY(launch_select<1>(w.dist, B, N, S, k, knn, st));
-    else return fail(GMF_ERR_INVALID, "seed kNN supports N <= 51200");
+    TRY(launch_select(w.dist, B, N, S, k, knn, st));
   }
   ProfScope ps(CAT_SPECTRAL, st);
   CU(cudaMemsetAsync(w.pair_mask, 0xff, (size_t)B * sizeof(unsigned), st));

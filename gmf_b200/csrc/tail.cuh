@@ -376,23 +376,27 @@ __global__ void __launch_bounds__(256) seed_dist_kernel(const float* __restrict_
 // into a candidate list, from which the k+1 smallest are extracted by repeated (value, index) arg-min.  Rows with too many
 // candidates (massive ties) or fewer than 64 entries take the plain k+1 full scans.
 constexpr int kSelCap = 256;
-template <int SPC>   // seeds (warps) per CTA
+// SPC seeds (warps) per CTA.  The distance row is streamed from global memory twice (float4 per lane; the second pass hits L1/L2)
+// instead of being staged in shared memory: 2 KB of shared memory per warp (the candidate list) keeps the SM fully occupied.
+template <int SPC>
 __global__ void __launch_bounds__(SPC * 32) seed_select_kernel(const float* __restrict__ dist, int N, int S, int k, int* __restrict__ knn_idx) {
-  extern __shared__ float sm[];
+  __shared__ float s_cv[SPC][kSelCap];
+  __shared__ int s_ci[SPC][kSelCap];
   const int pair = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * SPC + warp;
   if (s >= S) return;
-  float* d = sm + (size_t)warp * N;
-  float* cv = sm + (size_t)SPC * N + (size_t)warp * 2 * kSelCap;
-  int* ci = reinterpret_cast<int*>(cv + kSelCap);
+  float* cv = s_cv[warp];
+  int* ci = s_ci[warp];
   const float* src = dist + ((size_t)pair * S + s) * N;
+  const bool vec = (N & 3) == 0;                                // rows are 16-byte aligned when N % 4 == 0
+  const int nv = vec ? N >> 2 : 0;
   float m1 = INFINITY, m2 = INFINITY;
-  for (int j = lane; j < N; j += 32) {
-    const float v = src[j];
-    d[j] = v;
-    if (v < m1) { m2 = m1; m1 = v; } else if (v < m2) m2 = v;
+  auto upd = [&](float v) { if (v < m1) { m2 = m1; m1 = v; } else if (v < m2) m2 = v; };
+  for (int q = lane; q < nv; q += 32) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+    upd(v.x); upd(v.y); upd(v.z); upd(v.w);
   }
-  __syncwarp();
+  for (int j = nv * 4 + lane; j < N; j += 32) upd(__ldg(src + j));
   int ncand = -1;
   if (N >= 64 && k + 1 <= 64) {
     // rank of m1 / m2 among the 64 lane minima (ties broken by slot number): the value of rank k is the threshold
@@ -404,14 +408,27 @@ __global__ void __launch_bounds__(SPC * 32) seed_select_kernel(const float* __re
     }
     const unsigned h1 = __ballot_sync(0xffffffffu, r1 == k), h2 = __ballot_sync(0xffffffffu, r2 == k);
     const float T = h1 ? __shfl_sync(0xffffffffu, m1, __ffs(h1) - 1) : __shfl_sync(0xffffffffu, m2, __ffs(h2) - 1);
+    // second pass: compact every entry <= T (index order is not needed: the extraction below orders by (value, index))
     ncand = 0;
-    for (int j0 = 0; j0 < N; j0 += 32) {
-      const int j = j0 + lane;
-      const float v = j < N ? d[j] : INFINITY;
-      const unsigned mk = __ballot_sync(0xffffffffu, v <= T);
+    auto push = [&](float v, int j, bool ok) {
+      const unsigned mk = __ballot_sync(0xffffffffu, ok);
       const int pos = ncand + __popc(mk & ((1u << lane) - 1u));
-      if (v <= T && pos < kSelCap) { cv[pos] = v; ci[pos] = j; }
+      if (ok && pos < kSelCap) { cv[pos] = v; ci[pos] = j; }
       ncand += __popc(mk);
+    };
+    for (int q0 = 0; q0 < nv; q0 += 32) {
+      const int q = q0 + lane;
+      float4 v = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+      if (q < nv) v = __ldg(reinterpret_cast<const float4*>(src) + q);
+      const bool any4 = fminf(fminf(v.x, v.y), fminf(v.z, v.w)) <= T;
+      if (__any_sync(0xffffffffu, any4)) {
+        push(v.x, 4 * q, v.x <= T); push(v.y, 4 * q + 1, v.y <= T); push(v.z, 4 * q + 2, v.z <= T); push(v.w, 4 * q + 3, v.w <= T);
+      }
+    }
+    for (int j0 = nv * 4; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      const float v = j < N ? __ldg(src + j) : INFINITY;
+      push(v, j, v <= T);
     }
     __syncwarp();
     if (ncand > kSelCap) ncand = -1;
@@ -439,12 +456,16 @@ __global__ void __launch_bounds__(SPC * 32) seed_select_kernel(const float* __re
     }
     return;
   }
+  // fallback (tiny rows or massive ties): k + 1 full scans of the global row, excluding the indices already taken
+  float last_v = -INFINITY;
+  int last_i = -1;
   for (int rnk = 0; rnk <= k; ++rnk) {
     float bv = INFINITY;
     int bi = 0x7fffffff;
     for (int j = lane; j < N; j += 32) {
-      const float v = d[j];
-      if (v < bv) { bv = v; bi = j; }
+      const float v = __ldg(src + j);
+      const bool after = v > last_v || (v == last_v && j > last_i);   // strictly after the previous pick in (value, index) order
+      if (after && (v < bv || (v == bv && j < bi))) { bv = v; bi = j; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -452,11 +473,8 @@ __global__ void __launch_bounds__(SPC * 32) seed_select_kernel(const float* __re
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    if (lane == 0) {
-      if (bi < N) d[bi] = INFINITY;
-      if (rnk > 0) knn_idx[((size_t)pair * S + s) * k + rnk - 1] = bi < N ? bi : 0;
-    }
-    __syncwarp();
+    last_v = bv; last_i = bi;
+    if (lane == 0 && rnk > 0) knn_idx[((size_t)pair * S + s) * k + rnk - 1] = bi < N ? bi : 0;
   }
 }
 
