@@ -549,7 +549,7 @@ int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const 
   seed_spectral_kernel<0><<<dim3(S, B), 128, 0, st>>>(normed, src, tgt, knn, N, S, k, ctx->sigma, ctx->sigma_spat,
                                                      ctx->cfg.num_iterations, w.pair_mask, nullptr, nullptr, w.seedM);
   LAUNCHED();
-  seed_spectral_kernel<1><<<dim3(S, B), 128, 0, st>>>(normed, src, tgt, knn, N, S, k, ctx->sigma, ctx->sigma_spat,
+  seed_spectral_kernel<1><<<dim3(S, B), 32, 0, st>>>(normed, src, tgt, knn, N, S, k, ctx->sigma, ctx->sigma_spat,
                                                      ctx->cfg.num_iterations, w.pair_mask, seed_w, seed_trans, w.seedM);
   LAUNCHED();
   return 0;

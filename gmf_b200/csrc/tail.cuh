@@ -499,14 +499,16 @@ __global__ void __launch_bounds__(128) seed_spectral_kernel(const float* __restr
   __shared__ int idx[KM];
   const int sidx = blockIdx.x, pair = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t sg = (size_t)pair * S + sidx;
-  if (tid < k) idx[tid] = knn_idx[sg * k + tid];
+  for (int e = tid; e < k; e += blockDim.x) idx[e] = knn_idx[sg * k + e];
   __syncthreads();
-  if (tid < k * 3) {
-    const int r = tid / 3, c = tid % 3;
+  for (int e = tid; e < k * 3; e += blockDim.x) {
+    const int r = e / 3, c = e % 3;
     ks[r][c] = src[((size_t)pair * N + idx[r]) * 3 + c];
     kt[r][c] = tgt[((size_t)pair * N + idx[r]) * 3 + c];
   }
-  float* Mg = seedM + sg * (KM * KM);                   // pass 0 publishes M, pass 1 reloads it (L2) instead of recomputing
+  // pass 0 publishes the eigenvector estimate after every iteration; pass 1 (one warp per seed) only picks the iterate at which
+  // the reference's global allclose test stopped, so neither M nor the iterations are recomputed
+  float* vh = seedM + sg * (KM * KM);
   if (PASS == 0) {
     const float* F = normed + (size_t)pair * N * 128;
     for (int r = warp; r < k; r += 4) {
@@ -555,20 +557,20 @@ __global__ void __launch_bounds__(128) seed_spectral_kernel(const float* __restr
           const float ms = fmaxf(1.0f - dd * dd * inv_d2, 0.f);                          // :351
           const float m = (i == j) ? 0.f : mf * ms;                                      // :360-361
           M[i][j] = m; M[j][i] = m;
-          Mg[i * KM + j] = m; Mg[j * KM + i] = m;
         }
       }
     }
-  } else {
-    for (int e = tid; e < k * k; e += 128) M[e / k][e % k] = Mg[(e / k) * KM + (e % k)];
   }
-  if (tid < k) v[tid] = 1.0f;
-  __syncthreads();
-  int n_iter = iters;
   if (PASS == 1) {
+    int n_iter = iters;
     const unsigned m = pair_mask[pair] & ((iters >= 32) ? 0xffffffffu : ((1u << iters) - 1u));
     if (m) n_iter = __ffs(m);       // first iteration (1-based) at which every seed was close -> break after it
-  }
+    for (int e = tid; e < k; e += blockDim.x) v[e] = vh[(n_iter - 1) * KM + e];
+    __syncthreads();
+  } else {
+  if (tid < k) v[tid] = 1.0f;
+  __syncthreads();
+  const int n_iter = iters;
   unsigned close_mask = 0;
   for (int it = 0; it < n_iter; ++it) {
     float acc = 0.f;
@@ -584,6 +586,7 @@ __global__ void __launch_bounds__(128) seed_spectral_kernel(const float* __restr
     int bad = 0;
     if (tid < k) {
       vn[tid] = nv;
+      vh[it * KM + tid] = nv;
       bad = !(fabsf(nv - v[tid]) <= 1e-8f + 1e-5f * fabsf(v[tid]));                  // torch.allclose defaults (:444)
     }
     const int any_bad = __syncthreads_or(bad);
@@ -591,9 +594,8 @@ __global__ void __launch_bounds__(128) seed_spectral_kernel(const float* __restr
     if (tid < k) v[tid] = vn[tid];
     __syncthreads();
   }
-  if (PASS == 0) {
-    if (tid == 0) atomicAnd(&pair_mask[pair], close_mask);
-    return;
+  if (tid == 0) atomicAnd(&pair_mask[pair], close_mask);
+  return;
   }
   // weights (:365) and weighted Kabsch on the k neighbours
   if (warp == 0) {
