@@ -41,6 +41,9 @@ struct FfnArgs {
   const float* m2;         // [B, L, 64] (ReLU(BN(conv(...))) output of fc_message.4) or NULL
   const float* w3_packed;  // [128 out rows x 64] swizzled tf32
   const float* b3;         // [128]
+  // out_img != NULL: instead of the row-major `out`, write the tf32 K-major tile image [B][tiles][128 x 128] that the next layer's
+  // chained PointCN/QKV kernel loads with one bulk copy (the per-warp staging tiles already are 32-row blocks of that image)
+  float* out_img;
 };
 
 __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
@@ -319,17 +322,30 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
         if (a.m2) { const float4 b3 = *reinterpret_cast<const float4*>(a.b3 + col0 + 4 * j); bb.x += b3.x; bb.y += b3.y; bb.z += b3.z; bb.w += b3.w; }
         float4* slot = reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2));
         const float4 res = *slot;
-        *slot = make_float4(__uint_as_float(v[4 * j]) + bb.x + res.x, __uint_as_float(v[4 * j + 1]) + bb.y + res.y,
-                            __uint_as_float(v[4 * j + 2]) + bb.z + res.z, __uint_as_float(v[4 * j + 3]) + bb.w + res.w);
+        float4 o = make_float4(__uint_as_float(v[4 * j]) + bb.x + res.x, __uint_as_float(v[4 * j + 1]) + bb.y + res.y,
+                               __uint_as_float(v[4 * j + 2]) + bb.z + res.z, __uint_as_float(v[4 * j + 3]) + bb.w + res.w);
+        if (a.out_img) o = (row0 + r < a.L) ? to_tf32(o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *slot = o;
       }
       __syncwarp();
+      if (!a.out_img) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rw = i * 4 + srow;
-        if (row0 + q * 32 + rw < a.L)
-          *reinterpret_cast<float4*>(a.out + gbase + (size_t)rw * 128 + sj * 4) = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
+        for (int i = 0; i < 8; ++i) {
+          const int rw = i * 4 + srow;
+          if (row0 + q * 32 + rw < a.L)
+            *reinterpret_cast<float4*>(a.out + gbase + (size_t)rw * 128 + sj * 4) = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
+        }
+        __syncwarp();
       }
-      __syncwarp();
+    }
+    if (a.out_img) {
+      // warp (q, cq) owns rows 32q.. of swizzle atom cq: its 4 KB staging tile sits exactly where that block lives in the image
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (tid == 0) {
+        bulk_s2g(a.out_img + (size_t)(pair * a.tiles + tile) * (128 * 128), sStg, 65536);
+        bulk_commit_wait_read();
+      }
     }
   }
   if (warp == 0) TR(0, 4);

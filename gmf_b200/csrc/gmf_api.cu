@@ -230,6 +230,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 struct Work {
   float *kpts; float4 *src4, *tgt4;
+  float *feat_img;   // tf32 tile image of the layer output (handed from the FFN kernel to the next layer's PointCN/QKV kernel)
   float *imgfeat, *featA, *feat1, *x0, *x1, *x2, *of, *g_t, *msg, *m1, *m2;
   __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts, *aq, *bd;
   __nv_bfloat16 *kf_all, *vtf_all;   // [layers] context K / V^T tiles of every encoder layer (projected up front on a side stream)
@@ -257,6 +258,7 @@ size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k, int laye
   w.src4 = b.take<float4>((size_t)B * N); w.tgt4 = b.take<float4>((size_t)B * N);
   w.imgfeat = b.take<float>((size_t)B * std::max(T, 1) * 128);
   w.featA = b.take<float>((size_t)B * N * 128); w.feat1 = b.take<float>((size_t)B * N * 128);
+  w.feat_img = b.take<float>((size_t)B * nt * 128 * 128);
   w.x0 = b.take<float>(B * Lm * 128); w.x1 = b.take<float>(B * Lm * 128); w.x2 = b.take<float>(B * Lm * 128);
   w.of = b.take<float>(B * Lm * 64);
   w.g_t = b.take<float>(B * tm * 128 * 512);
@@ -335,7 +337,7 @@ int run_fusion_kv(const FusionW& f, const float* ctxk, int B, int Lk, __nv_bfloa
   return 0;
 }
 int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* resid0, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
-                    float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3);
+                    float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3, float* out_img = nullptr);
 
 // FusionLayer.forward (fusion_layer.py:172-201), everything on one stream
 int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st,
@@ -348,7 +350,7 @@ int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, c
 
 // attention (+ to_out + residual) and the GEGLU feed-forward block
 int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* resid0, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
-                    float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3) {
+                    float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3, float* out_img) {
   {
     AttnArgs a{};
     a.q_t = w.qf; a.k_t = kf; a.vt_t = vtf; a.out = w.of;
@@ -368,7 +370,7 @@ int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* 
     FfnArgs a{};
     a.x = w.x1; a.L = Lq; a.tiles = cdiv(Lq, 128); a.ln_g = f.lnf_g; a.ln_b = f.lnf_b;
     a.w1_packed = f.w1f; a.b1 = f.b1; a.w2_packed = f.w2f; a.b2 = f.b2; a.out = out;
-    a.m2 = tail_m2; a.w3_packed = tail_w3; a.b3 = tail_b3;
+    a.m2 = tail_m2; a.w3_packed = tail_w3; a.b3 = tail_b3; a.out_img = out_img;
 #ifdef GMF_FFN_TRACE
     static int n_ffn = 0;
     const bool do_trace = (++n_ffn == 20);
@@ -442,13 +444,13 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
 
 // PointCN_layer_i + NonLocal_layer_i (PointDSC.py:140-142, 40-74)
 int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in, const float* image_feat, int B, int N, int T,
-                      float* feat_out, cudaStream_t st, const gmf_ctx::Lane* lane = nullptr) {
+                      float* feat_out, cudaStream_t st, const gmf_ctx::Lane* lane = nullptr, bool in_img = false, bool out_img = false) {
   const bool overlapped = lane != nullptr;
   const LayerW& lw = ctx->layers[li];
   const bool chain = ctx->pcn_qkv != 0;                        // PointCN + QKV projection as one chained-GEMM kernel
   if (chain) {
     PcnQkvArgs a{};
-    a.x = feat_in; a.L = N; a.tiles = cdiv(N, 128); a.w_packed = lw.pq_w; a.pcn_bias = lw.pcn_b; a.qkv_bias = lw.qkv_b;
+    a.x = feat_in; a.x_img = in_img ? w.feat_img : nullptr; a.L = N; a.tiles = cdiv(N, 128); a.w_packed = lw.pq_w; a.pcn_bias = lw.pcn_b; a.qkv_bias = lw.qkv_b;
     a.feat1 = w.feat1; a.tq = w.qs; a.tk = w.ks; a.tv = w.vts;
     ProfScope ps(CAT_QKV, st);
     cudaError_t e = launch_pcn_qkv(a, B, st);
@@ -484,7 +486,7 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     CU(cudaStreamWaitEvent(st, lane->ev_q, 0));
     CU(cudaStreamWaitEvent(st, lane->ev_kv[li], 0));
     return run_fusion_core(ctx, lw.f2, w, resid0, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
-                           lw.fc3_w, lw.fc3_b);
+                           lw.fc3_w, lw.fc3_b, out_img ? w.feat_img : nullptr);
   }
   if (ctx->ffn_impl >= 3) {   // fc_message.6(m2) + fusion_layer_2 output (PointDSC.py:73) folded into the fused FFN kernel's tail
     TRY(run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, feat_out, st, w.m2, lw.fc3_w, lw.fc3_b));
@@ -593,7 +595,10 @@ int forward_chunk(gmf_ctx* ctx, gmf_ctx::Lane* lane, Work& w, const float* corr,
       CU(cudaEventRecord(lane->ev_kv[li], lane->aux[0]));
     }
   }
-  for (int li = 0; li < L; ++li) TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped ? lane : nullptr));
+  // between layers the features travel as the tf32 tile image the next PointCN/QKV kernel consumes (last layer: row-major)
+  const bool img = overlapped && ctx->pcn_qkv;
+  for (int li = 0; li < L; ++li)
+    TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped ? lane : nullptr, img && li > 0, img && li + 1 < L));
   if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
   TRY(run_classify(ctx, w.featA, (long long)B * N, w.normed, conf_out, st));
   TRY(run_pick_seeds(ctx, w, conf_out, B, N, S, testing ? 1 : 0, seeds_out, st));

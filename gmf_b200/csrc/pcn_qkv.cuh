@@ -18,6 +18,7 @@ struct PcnQkvCfg {
 
 struct PcnQkvArgs {
   const float* x;          // [B, L, 128] layer input
+  const float* x_img;      // or (preferred) its tf32 tile image [B][tiles][128 x 128] written by the previous layer's FFN kernel
   int L, tiles;
   const float* w_packed;   // 8 chunks of [128 rows x 64 k] tf32: PointCN (BN folded) k-halves, then q, k, v blocks x k-halves
   const float* pcn_bias;   // [128] (BN folded)
@@ -39,7 +40,8 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
   uint64_t* acc0_full = bars + 9;
   uint64_t* f1_ready = bars + 10;  // 256
   uint64_t* acc_full = bars + 11;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  uint64_t* img_full = bars + 13;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);   // (bars + 13 is img_full)
   float* sStg = (float*)(sB + Cfg::NBUF * Cfg::W_BYTES + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&mma_done[i], 1); }
-    mbar_init(a_ready, 256); mbar_init(acc0_full, 1); mbar_init(f1_ready, 256); mbar_init(acc_full, 1);
+    mbar_init(a_ready, 256); mbar_init(acc0_full, 1); mbar_init(f1_ready, 256); mbar_init(acc_full, 1); mbar_init(img_full, 1);
     fence_mbar_init();
   }
   if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -70,6 +72,10 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
       mbar_expect_tx_p(&full[buf], Cfg::W_BYTES, leader);
       bulk_g2s_p(sB + buf * Cfg::W_BYTES, wsrc + (size_t)it * Cfg::W_BYTES, Cfg::W_BYTES, &full[buf], leader);
     };
+    if (a.x_img) {
+      mbar_expect_tx_p(img_full, Cfg::A_BYTES, leader);
+      bulk_g2s_p(sA, a.x_img + (size_t)(pair * a.tiles + tile) * (128 * 128), Cfg::A_BYTES, img_full, leader);
+    }
 #pragma unroll
     for (int it = 0; it < Cfg::NBUF - 1; ++it) issue_load(it);
 #pragma unroll
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
         if (nxt >= Cfg::NBUF) mbar_wait(&mma_done[nxt % Cfg::NBUF], ((nxt / Cfg::NBUF) - 1) & 1);
         issue_load(nxt);
       }
-      if (it == 0) mbar_wait(a_ready, 0);
+      if (it == 0) { if (a.x_img) mbar_wait(img_full, 0); else mbar_wait(a_ready, 0); }
       if (it == 2) mbar_wait(f1_ready, 0);                     // feat1 (tf32) is back in TMEM columns 0..127
       mbar_wait(&full[buf], (it / Cfg::NBUF) & 1);
       tc_fence_after();
@@ -107,8 +113,8 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
       __syncwarp();
     }
   } else {
-    // ------------------------------- workers: A operand (tf32, swizzled) -------------------------------
-    {
+    // ------------------------------- workers: A operand (tf32, swizzled) unless the producer kernel already wrote the image ------
+    if (!a.x_img) {
       const int c4 = lane * 4;
       const float* xp = a.x + (size_t)pair * a.L * 128;
       constexpr int RPW = 16;
