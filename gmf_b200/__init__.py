@@ -9,4 +9,7 @@ def __getattr__(name):
     if name in ("Engine",):
         from .engine import Engine
         return Engine
+    if name in ("PerceiverIO", "DgrHeadEngine"):
+        from . import dgr_head
+        return getattr(dgr_head, name)
     raise AttributeError(name)

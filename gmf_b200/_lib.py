@@ -17,6 +17,8 @@ EXPORTS = [
     "gmf_fusion_layer", "gmf_sc_attention", "gmf_encoder_layer", "gmf_classify", "gmf_pick_seeds",
     "gmf_seed_hypotheses", "gmf_score_hypotheses", "gmf_rigid_transform_3d", "gmf_launch_count",
     "gmf_debug_linear", "gmf_debug_attention", "gmf_profile_enable", "gmf_profile_read",
+    "gmf_dgr_head_create", "gmf_dgr_head_destroy", "gmf_dgr_head_weight_count", "gmf_dgr_head_weight_spec",
+    "gmf_dgr_head_load_weights", "gmf_dgr_head_forward",
 ]
 
 
@@ -68,6 +70,13 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.gmf_debug_attention.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, vp, vp, sz, vp]
     lib.gmf_profile_enable.argtypes = [vp, i]
     lib.gmf_profile_read.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.gmf_dgr_head_create.argtypes = [C.POINTER(C.c_void_p), i, i, i, i, i]
+    lib.gmf_dgr_head_destroy.argtypes = [vp]
+    lib.gmf_dgr_head_destroy.restype = None
+    lib.gmf_dgr_head_weight_count.argtypes = [i]
+    lib.gmf_dgr_head_weight_spec.argtypes = [i, i, C.c_char_p, i, C.POINTER(C.c_int64)]
+    lib.gmf_dgr_head_load_weights.argtypes = [vp, vp, C.c_int64]
+    lib.gmf_dgr_head_forward.argtypes = [vp, vp, vp, i, i, vp, vp]
     _lib = lib
     return lib
 

@@ -15,6 +15,7 @@
 #include "ffn_fused.cuh"
 #include "pcn_qkv.cuh"
 #include "tail.cuh"
+#include "dgr_head.cuh"
 
 using namespace gmf;
 
@@ -1167,3 +1168,5 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
 }
 
 }  // extern "C"
+
+#include "dgr_head_api.inl"

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
   const int pair = blockIdx.y, qt = blockIdx.x;
   const int nt = (a.N + BT - 1) / BT;                     // 32-key tiles
   const int nw = (a.N + 63) / 64;                         // 64-key stages
+  const int Nq = a.Nq ? a.Nq : a.N, qtiles = a.Nq ? a.q_tiles : a.tiles;
 
   if (tid == 0) {
     mbar_init(q_full, NW * 32);
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
 
   if (warp < NW) {
     // this thread's share of Q row r -> tensor memory, two bf16 per 32-bit column (atom g of the swizzled tile image)
-    const size_t tq = (size_t)pair * a.tiles + qt;
+    const size_t tq = (size_t)pair * qtiles + qt;
     const uint8_t* qsrc = (const uint8_t*)(a.q_t + tq * (128 * D)) + g * 16384;
     uint32_t w[HC];
 #pragma unroll
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
       const uint32_t leader = elect_one() ? 1u : 0u;
       if (pass == 0) {
         mbar_expect_tx_p(aq_full, Cfg::AQ_BYTES, leader);
-        bulk_g2s_p(sAq, a.aq_t + ((size_t)pair * a.tiles + qt) * (128 * 64), Cfg::AQ_BYTES, aq_full, leader);
+        bulk_g2s_p(sAq, a.aq_t + ((size_t)pair * qtiles + qt) * (128 * 64), Cfg::AQ_BYTES, aq_full, leader);
         if (a.fc1_w) {
           mbar_expect_tx_p(w_full, Cfg::FC_BYTES, leader);
           bulk_g2s_p(sFc, a.fc1_w, 64 * 128 * 4, w_full, leader);
@@ -368,13 +369,13 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
     const int gq = qt * 128 + r;
     constexpr int OC = D / NPART;                             // output columns per thread
     if (!fused) {
-      float* op = a.out + ((size_t)pair * a.N + gq) * D + part * OC;
+      float* op = a.out + ((size_t)pair * Nq + gq) * D + part * OC;
 #pragma unroll
       for (int c = 0; c < OC / 32; ++c) {
         uint32_t u[32];
         tmem_ld32(tlane + Cfg::COL_O + part * OC + c * 32, u);
         tmem_ld_wait();
-        if (gq < a.N) {
+        if (gq < Nq) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(op + c * 32 + 4 * i) =
@@ -412,8 +413,8 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
       tc_fence_after();
       if constexpr (HC1 == 16) tmem_ld16(tlane + 128 + part * HC1, x); else tmem_ld32(tlane + 128 + part * HC1, x);
       tmem_ld_wait();
-      if (gq < a.N) {
-        float* op = a.m2_out + ((size_t)pair * a.N + gq) * 64 + part * HC1;
+      if (gq < Nq) {
+        float* op = a.m2_out + ((size_t)pair * Nq + gq) * 64 + part * HC1;
 #pragma unroll
         for (int i = 0; i < HC1; i += 4)
           *reinterpret_cast<float4*>(op + i) =
@@ -436,7 +437,7 @@ inline cudaError_t launch_sc_attn_v9(const ScAttnArgs& a, int pairs, cudaStream_
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<dim3(a.tiles, pairs), 256 * TPR + 96, Sc9Cfg::SMEM, st>>>(a);
+  kern<<<dim3(a.Nq ? a.q_tiles : a.tiles, pairs), 256 * TPR + 96, Sc9Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -13,7 +13,7 @@ struct ScAttnArgs {
   const __nv_bfloat16* aq_t;  // [pairs][tiles][128*64]    query-side distance features (s-part | t-part)
   const __nv_bfloat16* bd_t;  // [pairs][tiles][128*64]    key-side distance features
   float* out;                 // [pairs][N][128] fp32
-  int N, tiles;
+  int N, tiles;               // keys (and queries unless Nq is set)
   // gen 9 only: fused head of fc_message (PointDSC.py:13-21,65).  fc1_w != NULL switches it on: instead of msg the kernel
   // writes m2 = ReLU(BN(conv64x64(ReLU(BN(conv128x64(msg))))))  [pairs][N][64]  (BN folded into the packed weights / biases)
   const float* fc1_w;         // pack_linear(W, 64, 128, 32, 64)
@@ -21,6 +21,8 @@ struct ScAttnArgs {
   const float* fc2_w;         // pack_linear(W, 64, 64, 64, 64)
   const float* fc2_b;
   float* m2_out;
+  // cross-attention use (DGR head): Nq != 0 gives the query side its own length / tile count (q_t, aq_t, out are indexed with it)
+  int Nq, q_tiles;
 };
 
 

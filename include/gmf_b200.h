@@ -113,6 +113,25 @@ int gmf_score_hypotheses(gmf_ctx* ctx, const float* seed_trans, const float* src
 /* rigid_transform_3d (models/common.py:10-50): A,B [M,k,3], weights [M,k] or NULL -> T [M,4,4]. */
 int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* B, const float* weights, int M, int k, float* T, void* stream);
 
+/* ---- DGR bottleneck fusion head --------------------------------------------- */
+/* PerceiverIO(depth=0, dim=128, latent_dim=256, cross_heads=1, cross_dim_head=128, pe) of the DGR inlier network
+ * (GMF_DeepGlobalRegistration_fcgf/model/perceiver_io.py:140-221; built at model/resunet_new.py:516-525, called from
+ * ResUNet2.transformer :694-705).  Replaces `self.perceiver_io(image, queries_encoder=P_att)`: ConvPosEnc on latents and
+ * context, PreNorm cross-attention (1 head, d=128) + to_out + residual, PreNorm GEGLU feed-forward (256 -> 2048 -> 256) +
+ * residual.  The handle owns its packed weights and a grow-on-demand device workspace; one handle per device/thread.
+ * (The other PerceiverIO instance of that network, `image_fusion` (latent_dim=128, cross_dim_head=64, pe=False,
+ * resunet_new.py:618-626), has the shape of PointDSC's fusion_layer_1 and runs through gmf_fusion_layer.) */
+typedef struct gmf_dgr_head gmf_dgr_head;
+int gmf_dgr_head_create(gmf_dgr_head** out, int device, int latent_dim /*256*/, int context_dim /*128*/, int head_dim /*128*/, int pe);
+void gmf_dgr_head_destroy(gmf_dgr_head* h);
+/* state_dict tensors of that module in canonical order (gmf_b200/dgr_head.py mirrors the table) */
+int gmf_dgr_head_weight_count(int pe);
+int gmf_dgr_head_weight_spec(int pe, int index, char* name, int cap, int64_t* numel);
+/* host pointer: the tensors concatenated in that order (fp32) */
+int gmf_dgr_head_load_weights(gmf_dgr_head* h, const float* host_flat, int64_t numel);
+/* latents [M,256] (all active bottleneck voxels of the batch as one sequence), image_feat [T,128] -> out [M,256]; device pointers */
+int gmf_dgr_head_forward(gmf_dgr_head* h, const float* latents, const float* image_feat, int M, int T, float* out, void* stream);
+
 /* ---- introspection / debugging ------------------------------------------------------------- */
 /* Per-launch CUDA-event timing (bench.py's roofline leg).  While enabled every kernel launch is bracketed by events on
  * the launching stream; gmf_profile_read synchronises the device and returns the summed device time and launch count
