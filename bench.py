@@ -264,9 +264,9 @@ def main():
         sc_flops = 4.0 * a.corr * a.corr * 128 * a.pairs * a.layers * a.steps           # 4 N^2 C per pair-layer
         ach = sc_flops / (sc_ms / 1000.0) / 1e12
         # DRAM bytes of one launch from the committed `ncu --set full` capture of this configuration
-        # (profiles/r01_top3_cfg2_ncu_raw.csv: dram__bytes_read.sum 333.03 MB + dram__bytes_write.sum 70.37 MB at 64 pairs, N=5000;
+        # (profiles/r01_top3_cfg2_ncu_raw.csv: dram__bytes_read.sum 333.43 MB + dram__bytes_write.sum 69.53 MB at 64 pairs, N=5000;
         #  algorithmic: Q/K/V^T bf16 + distance features 5.8 MB in, m2 fp32 1.3 MB out per pair = 454 MB)
-        traffic = 403.40e6 if (a.pairs == 64 and a.corr == 5000) else None
+        traffic = 402.96e6 if (a.pairs == 64 and a.corr == 5000) else None
         # co-limit: every score element costs one MUFU.SQRT and one MUFU.EX2 at the measured 16 MUFU/clk/SM (tools/ubench/sm_rates.cu)
         mufu_floor_ms = 2.0 * a.corr * a.corr * a.pairs / (16.0 * 148 * 1.965e9) * 1e3
         roof = {"kernel": "sc_attn_v9_kernel<0,2> (SC-guided non-local flash attention, compat on the fly, gen 9)", "bound": "tensor",

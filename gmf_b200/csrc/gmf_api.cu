@@ -16,6 +16,7 @@
 #include "pcn_qkv.cuh"
 #include "tail.cuh"
 #include "dgr_head.cuh"
+#include "matcher.cuh"
 
 using namespace gmf;
 
@@ -1170,3 +1171,4 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
 }  // extern "C"
 
 #include "dgr_head_api.inl"
+#include "matcher_api.inl"

@@ -132,6 +132,20 @@ int gmf_dgr_head_load_weights(gmf_dgr_head* h, const float* host_flat, int64_t n
 /* latents [M,256] (all active bottleneck voxels of the batch as one sequence), image_feat [T,128] -> out [M,256]; device pointers */
 int gmf_dgr_head_forward(gmf_dgr_head* h, const float* latents, const float* image_feat, int M, int T, float* out, void* stream);
 
+/* ---- correspondence construction (the step right before the path) ------------- */
+/* Nearest-neighbour matcher in descriptor space + network input assembly, NumPy in the reference's datasets
+ * (GMF_PointDSC/datasets/ThreeDMatch.py:384-391, 401-402, 411-414; datasets/KITTI.py:94-102):
+ *   distance = sqrt(2 - 2 * src_desc @ tgt_desc.T + 1e-6); source_idx = argmin(distance, axis=1);
+ *   use_mutual: keep i only if argmin(distance, axis=0)[source_idx[i]] == i;  corr = [i, source_idx[i]] in increasing i;
+ *   src_sel = src_keypts[corr[:,0]], tgt_sel = tgt_keypts[corr[:,1]], corr_pos = [src_sel | tgt_sel] - mean over rows.
+ * src_desc [B,Ns,D], tgt_desc [B,Nt,D] (unit-norm descriptors), src_keypts [B,Ns,3], tgt_keypts [B,Nt,3]  ->
+ * source_idx [B,Ns] int32, corr [B,Ns,2] int32, n_corr [B] int32, src_sel / tgt_sel [B,Ns,3], corr_pos [B,Ns,6]; rows at and past
+ * n_corr[b] are zero (corr: -1).  The Ns x Nt distance matrix is never materialised.  All pointers device. */
+size_t gmf_match_workspace_bytes(int B, int Ns, int Nt);
+int gmf_build_correspondences(gmf_ctx* ctx, const float* src_desc, const float* tgt_desc, const float* src_keypts, const float* tgt_keypts,
+                              int B, int Ns, int Nt, int D, int use_mutual, int32_t* source_idx, int32_t* corr, int32_t* n_corr,
+                              float* src_sel, float* tgt_sel, float* corr_pos, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- introspection / debugging ------------------------------------------------------------- */
 /* Per-launch CUDA-event timing (bench.py's roofline leg).  While enabled every kernel launch is bracketed by events on
  * the launching stream; gmf_profile_read synchronises the device and returns the summed device time and launch count
