@@ -29,8 +29,9 @@ __global__ void __launch_bounds__(256) nn_argmin_kernel(const float* __restrict_
   const int ct0 = blockIdx.y * tiles_per_chunk, ct1 = min(ct0 + tiles_per_chunk, ctiles);
   if (tid < kNnTile) sbest[tid] = ~0ull;
   unsigned long long mine[8];
+  float top[8];                                          // largest dot product this thread has seen per row
 #pragma unroll
-  for (int i = 0; i < 8; ++i) mine[i] = ~0ull;
+  for (int i = 0; i < 8; ++i) { mine[i] = ~0ull; top[i] = -INFINITY; }
 
   auto load_tile = [&](float (*S)[kNnLd], const float* P, int n, int r0, int k0) {
     // 128 rows x 32 k values, transposed into [k][row]; rows / k past the end read as zero
@@ -53,8 +54,9 @@ __global__ void __launch_bounds__(256) nn_argmin_kernel(const float* __restrict_
       if (nkb > 1 || ct == ct0) load_tile(As, Ap, Na, row0, kb * kNnKb);
       load_tile(Bs, Bp, Nb, ct * kNnTile, kb * kNnKb);
       __syncthreads();
+      const int kcount = min(kNnKb, D - kb * kNnKb);       // D = 33 (FPFH): the second block is one step, not 32
 #pragma unroll 8
-      for (int k = 0; k < kNnKb; ++k) {
+      for (int k = 0; k < kcount; ++k) {
         const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]), a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
         const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]), b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
         const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -71,10 +73,16 @@ __global__ void __launch_bounds__(256) nn_argmin_kernel(const float* __restrict_
       if (col < Nb) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          // np.sqrt(2 - 2 * dot + 1e-6) in fp32, one rounding per operation (ThreeDMatch.py:384)
-          const float d = __fsqrt_rn(__fadd_rn(__fsub_rn(2.0f, __fmul_rn(2.0f, acc[i][j])), 1e-6f));
-          const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)col;
-          mine[i] = key < mine[i] ? key : mine[i];
+          // The distance is a monotone (non-increasing) function of the dot product, and a thread visits its columns in increasing
+          // order, so only a dot product above the thread's running maximum can lower the distance or win a tie: the exact
+          // expression is evaluated on that rare path only.
+          if (acc[i][j] > top[i]) {
+            top[i] = acc[i][j];
+            // np.sqrt(2 - 2 * dot + 1e-6) in fp32, one rounding per operation (ThreeDMatch.py:384)
+            const float d = __fsqrt_rn(__fadd_rn(__fsub_rn(2.0f, __fmul_rn(2.0f, acc[i][j])), 1e-6f));
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)col;
+            mine[i] = key < mine[i] ? key : mine[i];
+          }
         }
       }
     }
