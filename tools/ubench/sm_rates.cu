@@ -176,6 +176,50 @@ __global__ void k_mufu(int iters, long long* out, float* sink) {
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
 }
 
+// T8: does packing two fp32 into bf16x2 (cvt.rn.bf16x2.f32, SASS F2FP) share the MUFU (XU) pipe?  MODE 0: 16 cvt per iteration;
+// MODE 1: 16 ex2 + 8 cvt per iteration (the softmax mix: one pack per two exponentials); MODE 2: 16 ex2 + 8 PRMT-style truncating packs
+template <int MODE>
+__global__ void k_cvt(int iters, long long* out, float* sink) {
+  float x[16];
+  unsigned pk[8];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = 0.001f * (threadIdx.x + i);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pk[i] = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        unsigned r;
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x[i]), "f"(x[(i + 1) & 15]));
+        pk[i & 7] ^= r;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        unsigned r;
+        if (MODE == 1) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x[2 * i + 1]), "f"(x[2 * i]));
+        else asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(r) : "r"(__float_as_uint(x[2 * i])), "r"(__float_as_uint(x[2 * i + 1])));
+        pk[i] ^= r;
+      }
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  float s = 0;
+  unsigned u = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u ^= pk[i];
+  if (s == 123.456f || u == 0x12345678u) sink[threadIdx.x] = s + u;
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+}
+
 // back-to-back MMAs of one shape: M=128, N, K=16 (bf16), A from shared memory (TS=0) or tensor memory (TS=1)
 template <int N, int TS>
 __global__ void __launch_bounds__(128, 1) k_mma_rate(int iters, long long* out) {
@@ -291,6 +335,22 @@ int main() {
     k_ex2_h2<<<148, 32 * w>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
     printf("  warps=%2d  ex2.approx.f16x2: %.1f instr-lanes/clk/SM = %.1f exponentials/clk/SM\n", w, (double)w * 32 * 16 * iters / h, 2.0 * w * 32 * 16 * iters / h);
+  }
+  printf("== T8 fp32x2 -> bf16x2 packing vs the MUFU pipe (16 warps)\n");
+  {
+    const int w = 16;
+    k_cvt<0><<<148, 32 * w>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
+    printf("  cvt.rn.bf16x2.f32 alone: %.1f /clk/SM\n", (double)w * 32 * 16 * iters / h);
+    k_mufu<0><<<148, 32 * w>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
+    const double base = (double)h / iters;
+    k_cvt<1><<<148, 32 * w>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
+    printf("  16 ex2 per thread-iteration: %.1f clk;  16 ex2 + 8 cvt: %.1f clk", base, (double)h / iters);
+    k_cvt<2><<<148, 32 * w>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
+    printf(";  16 ex2 + 8 prmt: %.1f clk\n", (double)h / iters);
   }
   printf("== T3 MMA sequence, cycles per key tile (tensor floor: all 640, S 256, PV 256, S128 512 @ 8192 flop/clk)\n");
   {
