@@ -955,6 +955,46 @@ int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, 
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+// Chunk boundaries of the host entry point.  The first chunk is small (its upload is the only exposed one), later chunks double
+// (the forward of a chunk takes ~2.6x its upload at cfg#2, so the copy stream stays ahead); within +25 % of each target the size is
+// chosen so that the attention grids (cdiv(N,128) and cdiv(N,256) CTAs per pair) fill whole waves of the SMs.
+std::vector<int> plan_host_chunks(int B, int N, int cap, int sms) {
+  std::vector<int> cuts{0};
+  cap = std::max(cap, 1);
+  if (B <= 8) {
+    for (int b0 = 0; b0 < B; b0 += cap) if (b0) cuts.push_back(b0);
+    cuts.push_back(B);
+    return cuts;
+  }
+  const int tp = cdiv(N, 128), tp2 = cdiv(tp, 2);
+  auto eff = [&](int k) {
+    const double w = (double)tp * k / sms, w2 = (double)tp2 * k / sms;
+    return (w / std::ceil(w)) * (w2 / std::ceil(w2));
+  };
+  int done = 0, target = std::max(1, B / 9);
+  while (done < B) {
+    const int rem = B - done;
+    const int hi = std::min(std::min(rem, cap), target + target / 4 + 1), lo = std::min(target, hi);
+    int best = lo;
+    double be = -1.0;
+    for (int k = lo; k <= hi; ++k) {
+      const double e = eff(k);
+      if (e > be + 1e-9) { be = e; best = k; }
+    }
+    if (rem - best < target) best = std::min(rem, cap);      // no short tail chunk
+    done += best;
+    cuts.push_back(done);
+    target = std::min(2 * target, cap);
+  }
+  return cuts;
+}
+}  // namespace
+
+extern "C" {
+
 int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
                               const float* q_tok, int B, int N, int T, int testing, float* final_trans, float* final_labels,
                               float* confidence, void* stream) {
@@ -985,7 +1025,7 @@ int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* 
   Bump bb{(uint8_t*)(((uintptr_t)ctx->stage + 1023) & ~(uintptr_t)1023)};
   layout(bb, d_corr, d_src, d_tgt, d_p, d_q, d_tr, d_lab, d_conf, d_seeds, d_ws);
   // Pipelined in chunks of pairs: the inputs of chunk c+1 travel on a copy stream while chunk c computes, so only the first
-  // (small) chunk's upload is exposed.  Chunk sizes: 16 pairs first, then up to 48 (13.0 / 6.5 waves of attention CTAs on 148 SMs).
+  // (small) chunk's upload is exposed (plan_host_chunks: ~B/9 pairs first, then doubling, sizes snapped to whole waves of attention CTAs).
   if (!ctx->copy_stream) {
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->copy_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -994,9 +1034,9 @@ int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* 
   cudaStream_t cs = ctx->copy_stream;
   CU(cudaEventRecord(ctx->start_ev, st));                      // the staging buffers may still be read by earlier work on `st`
   CU(cudaStreamWaitEvent(cs, ctx->start_ev, 0));
-  std::vector<int> cuts;                                       // chunk boundaries
-  for (int b0 = 0; b0 < B;) { cuts.push_back(b0); b0 += (b0 == 0 && B > 16) ? 16 : std::min(48, ctx->chunk_pairs); }
-  cuts.push_back(B);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const std::vector<int> cuts = plan_host_chunks(B, N, std::min(48, ctx->chunk_pairs), sms);     // chunk boundaries
   const int nchunk = (int)cuts.size() - 1;
   if (nchunk > (int)(sizeof(ctx->copy_ev) / sizeof(ctx->copy_ev[0]))) return fail(GMF_ERR_INVALID, "batch too large for the host entry point (max 64 chunks)");
   for (int c = 0; c < nchunk; ++c) {
