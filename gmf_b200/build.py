@@ -23,7 +23,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DGMF_SC_DBG=" + os.environ.get("GMF_SC_DBG", "0"),] + (["-DGMF_FFN_TRACE"] if os.environ.get("GMF_FFN_TRACE") else []) + [
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DGMF_SC_DBG=" + os.environ.get("GMF_SC_DBG", "0"),] + (["-DGMF_FFN_TRACE"] if os.environ.get("GMF_FFN_TRACE") else []) + (["-DGMF_PCN_TRACE"] if os.environ.get("GMF_PCN_TRACE") else []) + [
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")

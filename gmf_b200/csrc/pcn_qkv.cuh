@@ -4,7 +4,8 @@
 // The second GEMM takes its A operand straight from tensor memory (TS-mode tf32 MMA on the accumulator columns of the first),
 // so feat1 is neither re-read from HBM nor staged in shared memory; one launch and one exposed prologue instead of two.
 // TMEM (512 columns): feat1 0..127 | Q 128..255 | K 256..383 | V 384..511.  Shared memory: feat tile image 64 KB, weight ring
-// 4 x 32 KB (8 chunks: 2 PointCN + 6 QKV, the three bf16 tile images reuse the ring once the MMAs have retired), staging 32 KB.
+// 4 x 32 KB (8 chunks: 2 PointCN + 6 QKV).  The feat tile area doubles as fp32 staging for feat1 and then holds the Q image; the K and V
+// images are assembled in ring buffers whose MMAs have retired, so each image leaves as a bulk store while the next block is computed.
 #pragma once
 #include "linear_tc.cuh"
 
@@ -12,8 +13,8 @@ namespace gmf {
 
 struct PcnQkvCfg {
   static constexpr int A_BYTES = 128 * 128 * 4, W_BYTES = 128 * 64 * 4, NBUF = 4, NSTAGE = 8;
-  static constexpr int STG_BYTES = 8 * 32 * 32 * 4;
-  static constexpr int SMEM = 1024 + A_BYTES + NBUF * W_BYTES + 256 + STG_BYTES;
+  static constexpr int BIAS_BYTES = 512 * 4;
+  static constexpr int SMEM = 1024 + A_BYTES + NBUF * W_BYTES + 256 + BIAS_BYTES;
 };
 
 struct PcnQkvArgs {
@@ -27,7 +28,8 @@ struct PcnQkvArgs {
   __nv_bfloat16 *tq, *tk, *tv;   // [B][tiles][128*128] tile images
 };
 
-__global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
+// 17 warps: 16 workers (TMEM lane quadrant = warp & 3, 32-column chunk = warp >> 2) + one control warp
+__global__ void __launch_bounds__(544, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
   using Cfg = PcnQkvCfg;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -36,30 +38,41 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
   uint64_t* bars = (uint64_t*)(sB + Cfg::NBUF * Cfg::W_BYTES);
   uint64_t* full = bars;           // [4]
   uint64_t* mma_done = bars + 4;   // [4]
-  uint64_t* a_ready = bars + 8;    // 256
+  uint64_t* a_ready = bars + 8;    // 512
   uint64_t* acc0_full = bars + 9;
-  uint64_t* f1_ready = bars + 10;  // 256
+  uint64_t* f1_ready = bars + 10;  // 512
   uint64_t* acc_full = bars + 11;
   uint64_t* img_full = bars + 13;
+  uint64_t* accq_full = bars + 14;  // Q block of the second GEMM complete (stage 3), K block (stage 5): their epilogues overlap the rest
+  uint64_t* acck_full = bars + 15;
   uint32_t* tmem_slot = (uint32_t*)(bars + 12);   // (bars + 13 is img_full)
-  float* sStg = (float*)(sB + Cfg::NBUF * Cfg::W_BYTES + 256);
+  float* sBias = (float*)(sB + Cfg::NBUF * Cfg::W_BYTES + 256);   // PointCN bias [128] | Q,K,V biases [384]: read once, not per chunk from L2
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, pair = blockIdx.y;
   const int row0 = tile * 128;
+  if (tid < 512) sBias[tid] = tid < 128 ? a.pcn_bias[tid] : a.qkv_bias[tid - 128];
+#ifdef GMF_PCN_TRACE
+  __shared__ long long tr_[16];
+  const bool tr_on = blockIdx.x == 7 && (blockIdx.y == 3 || blockIdx.y == 40);
+#define PTR(i) do { if (tr_on) tr_[i] = clock64(); } while (0)
+  if (tid == 0) PTR(0);
+#else
+#define PTR(i) do { } while (0)
+#endif
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&mma_done[i], 1); }
-    mbar_init(a_ready, 256); mbar_init(acc0_full, 1); mbar_init(f1_ready, 256); mbar_init(acc_full, 1); mbar_init(img_full, 1);
+    mbar_init(a_ready, 512); mbar_init(acc0_full, 1); mbar_init(f1_ready, 512); mbar_init(acc_full, 1); mbar_init(img_full, 1); mbar_init(accq_full, 1); mbar_init(acck_full, 1);
     fence_mbar_init();
   }
-  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 16) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ------------------------------- control warp: weight stream + both GEMMs (fully unrolled, uniform operands) -------------------
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
@@ -80,14 +93,23 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
     for (int it = 0; it < Cfg::NBUF - 1; ++it) issue_load(it);
 #pragma unroll
     for (int it = 0; it < Cfg::NSTAGE; ++it) {
-      const int buf = it % Cfg::NBUF, nxt = it + Cfg::NBUF - 1;
-      if (nxt < Cfg::NSTAGE) {
+      const int buf = it % Cfg::NBUF;
+      // refill schedule: chunk 3 right away; chunks 4 and 5 as soon as the PointCN MMAs have retired (i.e. BEFORE waiting for feat1 to
+      // come back into tensor memory - a bulk copy takes ~1.7k cycles to land and the Q/K/V MMAs of a chunk only ~0.65k), then 6 and 7
+      // behind the MMAs of chunks 2 and 3
+      auto refill = [&](int nxt) {
         if (nxt >= Cfg::NBUF) mbar_wait(&mma_done[nxt % Cfg::NBUF], ((nxt / Cfg::NBUF) - 1) & 1);
         issue_load(nxt);
-      }
-      if (it == 0) { if (a.x_img) mbar_wait(img_full, 0); else mbar_wait(a_ready, 0); }
-      if (it == 2) mbar_wait(f1_ready, 0);                     // feat1 (tf32) is back in TMEM columns 0..127
+      };
+      if (it == 0) refill(3);
+      if (it == 2) { refill(4); refill(5); }
+      if (it == 3) refill(6);
+      if (it == 4) refill(7);
+      if (it == 0) { if (leader) PTR(1); if (a.x_img) mbar_wait(img_full, 0); else mbar_wait(a_ready, 0); if (leader) PTR(2); }
+      if (it == 2) { mbar_wait(f1_ready, 0); if (leader) PTR(5); }                     // feat1 (tf32) is back in TMEM columns 0..127
       mbar_wait(&full[buf], (it / Cfg::NBUF) & 1);
+      if (leader && it == 0) PTR(3);
+      if (leader && it == 7) PTR(6);
       tc_fence_after();
       if (leader) {
         const uint64_t bd = umma_desc_adv(b_desc0, buf * Cfg::W_BYTES);
@@ -108,6 +130,8 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
         }
         tc_commit(&mma_done[buf]);
         if (it == 1) tc_commit(acc0_full);
+        if (it == 3) tc_commit(accq_full);
+        if (it == 5) tc_commit(acck_full);
         if (it == Cfg::NSTAGE - 1) tc_commit(acc_full);
       }
       __syncwarp();
@@ -117,7 +141,7 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
     if (!a.x_img) {
       const int c4 = lane * 4;
       const float* xp = a.x + (size_t)pair * a.L * 128;
-      constexpr int RPW = 16;
+      constexpr int RPW = 8;
       const int rbase = warp * RPW;
       float4 rv[RPW];
 #pragma unroll
@@ -131,26 +155,28 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
       fence_proxy_async();
       mbar_arrive(a_ready);
     }
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;
     const int r = q * 32 + lane;
     const bool valid = row0 + r < a.L;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     // ------------------------------- epilogue 0: feat1 = ReLU(acc + b) -> HBM (coalesced) and back to TMEM as tf32 -------------------
     mbar_wait(acc0_full, 0);
+    if (tid == 0) PTR(4);
     tc_fence_after();
     {
-      float* stg = sStg + warp * 1024;
+      // the feat tile image is dead once acc0_full fired: its 64 KB hold both chunks of every warp, so the TMEM round trip (which the
+      // second GEMM waits for) finishes before any global store is issued; the stores then overlap the Q MMAs
       const int srow = lane >> 3, sj = lane & 7;
-#pragma unroll 1
-      for (int c = half; c < 4; c += 2) {
+      {
+        const int c = part;
+        float* stg = (float*)sA + warp * 1024;
         uint32_t v[32];
         tmem_ld32(trow + c * 32, v);
         tmem_ld_wait();
         const int col0 = c * 32;
-        const size_t gbase = ((size_t)pair * a.L + row0 + q * 32) * 128 + col0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 bb = *reinterpret_cast<const float4*>(a.pcn_bias + col0 + 4 * j);
+          const float4 bb = *reinterpret_cast<const float4*>(sBias + col0 + 4 * j);
           const float4 o = make_float4(fmaxf(__uint_as_float(v[4 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f),
                                        fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f));
           *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
@@ -158,68 +184,86 @@ __global__ void __launch_bounds__(288, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
           v[4 * j] = __float_as_uint(t4.x); v[4 * j + 1] = __float_as_uint(t4.y); v[4 * j + 2] = __float_as_uint(t4.z); v[4 * j + 3] = __float_as_uint(t4.w);
         }
         tmem_st32(trow + c * 32, v);
-        __syncwarp();
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(f1_ready);
+      __syncwarp();
+      {
+        const int col0 = part * 32;
+        const float* stg = (const float*)sA + warp * 1024;
+        const size_t gbase = ((size_t)pair * a.L + row0 + q * 32) * 128 + col0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rw = i * 4 + srow;
           if (row0 + q * 32 + rw < a.L)
             *reinterpret_cast<float4*>(a.feat1 + gbase + (size_t)rw * 128 + sj * 4) = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
         }
-        __syncwarp();
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(f1_ready);
+      asm volatile("bar.sync 1, 512;" ::: "memory");            // every warp has read its staging tile: the area is reused for the Q image
     }
     // ------------------------------- epilogue 1: bf16 Q / K / V^T tile images (assembled in the dead weight ring) ------------------
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
 #pragma unroll 1
-    for (int c = half; c < 12; c += 2) {
-      uint32_t v[32];
-      tmem_ld32(trow + 128 + c * 32, v);
-      tmem_ld_wait();
-      const int col0 = c * 32, which = col0 >> 7, dcol0 = col0 & 127;
-      float o[32];
+    for (int which = 0; which < 3; ++which) {                  // 0 = Q, 1 = K (row-major tiles), 2 = V (transposed tile)
+      mbar_wait(which == 0 ? accq_full : which == 1 ? acck_full : acc_full, 0);
+      if (tid == 0 && which == 2) PTR(7);
+      tc_fence_after();
+      // Q is assembled in the (dead) feat tile / staging area; K and V in ring buffers 0 and 1, whose last MMAs (stages 4, 5) have retired
+      uint8_t* img = which == 0 ? sA : sB + (which - 1) * 32768;
+      {
+        const int cw = part;                                     // 32-column chunk within the block
+        uint32_t v[32];
+        tmem_ld32(trow + 128 + which * 128 + cw * 32, v);
+        tmem_ld_wait();
+        const int col0 = which * 128 + cw * 32, dcol0 = cw * 32;
+        float o[32];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.qkv_bias + col0) + i);
-        o[4 * i] = valid ? __uint_as_float(v[4 * i]) + b4.x : 0.f;
-        o[4 * i + 1] = valid ? __uint_as_float(v[4 * i + 1]) + b4.y : 0.f;
-        o[4 * i + 2] = valid ? __uint_as_float(v[4 * i + 2]) + b4.z : 0.f;
-        o[4 * i + 3] = valid ? __uint_as_float(v[4 * i + 3]) + b4.w : 0.f;
-      }
-      uint8_t* img = sB + which * 32768;
-      if (which < 2) {
-        uint8_t* dst = img + (dcol0 >> 6) * 16384;
-        const int cc0 = (dcol0 & 63) >> 3;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 pk;
-          pk.x = pack_bf16(o[8 * j], o[8 * j + 1]); pk.y = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
-          pk.z = pack_bf16(o[8 * j + 4], o[8 * j + 5]); pk.w = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
-          *reinterpret_cast<uint4*>(dst + swz_off(r, cc0 + j)) = pk;
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sBias + 128 + col0 + 4 * i);
+          o[4 * i] = valid ? __uint_as_float(v[4 * i]) + b4.x : 0.f;
+          o[4 * i + 1] = valid ? __uint_as_float(v[4 * i + 1]) + b4.y : 0.f;
+          o[4 * i + 2] = valid ? __uint_as_float(v[4 * i + 2]) + b4.z : 0.f;
+          o[4 * i + 3] = valid ? __uint_as_float(v[4 * i + 3]) + b4.w : 0.f;
         }
-      } else {
-        uint8_t* dst = img + (r >> 6) * (128 * 128) + (r & 7) * 2;
-        const int kchunk = (r & 63) >> 3;
+        if (which < 2) {
+          uint8_t* dst = img + (dcol0 >> 6) * 16384;
+          const int cc0 = (dcol0 & 63) >> 3;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) *reinterpret_cast<__nv_bfloat16*>(dst + swz_off(dcol0 + i, kchunk)) = __float2bfloat16_rn(o[i]);
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16(o[8 * j], o[8 * j + 1]); pk.y = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
+            pk.z = pack_bf16(o[8 * j + 4], o[8 * j + 5]); pk.w = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
+            *reinterpret_cast<uint4*>(dst + swz_off(r, cc0 + j)) = pk;
+          }
+        } else {
+          uint8_t* dst = img + (r >> 6) * (128 * 128) + (r & 7) * 2;
+          const int kchunk = (r & 63) >> 3;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) *reinterpret_cast<__nv_bfloat16*>(dst + swz_off(dcol0 + i, kchunk)) = __float2bfloat16_rn(o[i]);
+        }
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (tid == 0) {
+        if (which == 2) PTR(8);
+        const size_t tix = (size_t)(pair * a.tiles + tile) * (128 * 128);
+        bulk_s2g((which == 0 ? a.tq : which == 1 ? a.tk : a.tv) + tix, img, 32768);
+        bulk_commit();                                           // leaves while the next block's epilogue runs
       }
     }
-    fence_proxy_async();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (tid == 0) {
-      const size_t tix = (size_t)(pair * a.tiles + tile) * (128 * 128);
-      bulk_s2g(a.tq + tix, sB, 32768);
-      bulk_s2g(a.tk + tix, sB + 32768, 32768);
-      bulk_s2g(a.tv + tix, sB + 65536, 32768);
-      bulk_commit_wait_read();
-    }
+    if (tid == 0) { bulk_wait_read(); PTR(9); }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+#ifdef GMF_PCN_TRACE
+  if (tr_on && tid == 0) {
+    const long long e = clock64();
+    printf("pcn_qkv trace blk(%d,%d): setup %lld | img wait start %lld | img landed %lld | W0 landed %lld | acc0 %lld | f1 back %lld | last W landed %lld | acc_full %lld | images built %lld | stores read %lld | end %lld\n",
+           blockIdx.x, blockIdx.y, tr_[1] - tr_[0], tr_[1] - tr_[0], tr_[2] - tr_[0], tr_[3] - tr_[0], tr_[4] - tr_[0], tr_[5] - tr_[0], tr_[6] - tr_[0], tr_[7] - tr_[0],
+           tr_[8] - tr_[0], tr_[9] - tr_[0], e - tr_[0]);
+  }
+#endif
+  if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 inline cudaError_t launch_pcn_qkv(const PcnQkvArgs& a, int pairs, cudaStream_t st) {
@@ -229,7 +273,7 @@ inline cudaError_t launch_pcn_qkv(const PcnQkvArgs& a, int pairs, cudaStream_t s
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  pcn_qkv_kernel<<<dim3(a.tiles, pairs), 288, PcnQkvCfg::SMEM, st>>>(a);
+  pcn_qkv_kernel<<<dim3(a.tiles, pairs), 544, PcnQkvCfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
