@@ -580,7 +580,7 @@ int forward_chunk(gmf_ctx* ctx, gmf_ctx::Lane* lane, Work& w, const float* corr,
   {
     ProfScope ps(CAT_PREP, st);
     const long long rows = (long long)B * N;
-    layer0_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(corr, ctx->l0_w, ctx->l0_b, w.featA, rows, 6);
+    layer0_kernel<<<(unsigned)std::min<long long>((rows + 7) / 8, 148 * 16), 256, 0, st>>>(corr, ctx->l0_w, ctx->l0_b, w.featA, rows, 6);
     LAUNCHED();
   }
   // Fusion-1: queries = q-image tokens, context = p-image tokens (PointDSC.py:137)
