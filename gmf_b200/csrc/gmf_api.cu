@@ -237,6 +237,7 @@ struct Work {
   __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts, *aq, *bd;
   __nv_bfloat16 *kf_all, *vtf_all;   // [layers] context K / V^T tiles of every encoder layer (projected up front on a side stream)
   size_t kv_stride;
+  int *perm;          // points of each pair in descending-x order (windowed NMS)
   float *normed, *conf, *key, *seed_w, *seed_trans, *pre_refine, *dist, *seedM;
   int *seeds, *knn, *counts, *best;
   unsigned* pair_mask;
@@ -272,7 +273,7 @@ size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k, int laye
   w.qs = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128);
   w.ks = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128); w.vts = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 128);
   w.aq = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 64); w.bd = b.take<__nv_bfloat16>((size_t)B * nt * 128 * 64);
-  w.normed = b.take<float>((size_t)B * N * 128); w.conf = b.take<float>((size_t)B * N); w.key = b.take<float>((size_t)B * N);
+  w.normed = b.take<float>((size_t)B * N * 128); w.conf = b.take<float>((size_t)B * N); w.key = b.take<float>((size_t)B * N); w.perm = b.take<int>((size_t)B * N);
   w.seed_w = b.take<float>((size_t)B * S * k); w.seed_trans = b.take<float>((size_t)B * S * 16);
   w.pre_refine = b.take<float>((size_t)B * 16);
   w.dist = b.take<float>((size_t)B * S * N);
@@ -520,14 +521,19 @@ int run_pick_seeds(const gmf_ctx* ctx, Work& w, const float* conf, int B, int N,
   while (np2 < N) np2 <<= 1;
   if (np2 > 16384) return fail(GMF_ERR_INVALID, "pick_seeds supports N <= 16384");
   ProfScope ps(CAT_SEEDS, st);
-  nms_key_kernel<<<dim3(cdiv(N, 256), B), 256, 0, st>>>(w.src4, conf, N, ctx->cfg.nms_radius, use_nms, w.key);
-  LAUNCHED();
   static bool configured = false;
   if (!configured) {
     CU(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     configured = true;
   }
-  topk_sort_kernel<<<B, 1024, (size_t)np2 * 8, st>>>(w.key, N, np2, S, seeds);
+  const bool windowed = use_nms && N >= 1024;              // x-sorted sweep: far tiles are skipped (tail.cuh, nms_key_kernel)
+  if (windowed) {
+    topk_sort_kernel<<<B, 1024, (size_t)np2 * 8, st>>>(reinterpret_cast<const float*>(w.src4), 4, N, np2, N, w.perm);
+    LAUNCHED();
+  }
+  nms_key_kernel<<<dim3(cdiv(N, 256), B), 256, 0, st>>>(w.src4, conf, N, ctx->cfg.nms_radius, use_nms, windowed ? w.perm : nullptr, w.key);
+  LAUNCHED();
+  topk_sort_kernel<<<B, 1024, (size_t)np2 * 8, st>>>(w.key, 1, N, np2, S, seeds);
   LAUNCHED();
   return 0;
 }

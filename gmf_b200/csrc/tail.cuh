@@ -256,23 +256,42 @@ __device__ __forceinline__ float sqrt_threshold(float radius) {
   return t;
 }
 
+// perm (optional): the points of each pair in descending-x order.  Thread i then owns point perm[i] and tile j0 holds points
+// perm[j0 .. j0+255], so both the block and the tile cover a narrow x interval and a tile whose interval is at least the radius away
+// from the block's is skipped as a whole (|dx| alone already gives d2 >= T2 for every pair in it: fl is monotone, the other two squares
+// only add).  The AND over j is order independent, so the keys are bit-identical to the unsorted sweep.
 __global__ void __launch_bounds__(256) nms_key_kernel(const float4* __restrict__ src4, const float* __restrict__ score, int N,
-                                                      float radius, int use_nms, float* __restrict__ key) {
+                                                      float radius, int use_nms, const int* __restrict__ perm, float* __restrict__ key) {
   __shared__ float4 tp[256];
+  __shared__ float xr[2];
   const int pair = blockIdx.y;
   const int i = blockIdx.x * 256 + threadIdx.x;
   const float4* P = src4 + (size_t)pair * N;
   const float* S = score + (size_t)pair * N;
+  const int* Q = perm ? perm + (size_t)pair * N : nullptr;
+  const int pi = (i < N && Q) ? Q[i] : i;
   float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
   float ms = 0.f;
-  if (i < N) { me = P[i]; ms = S[i]; }
+  if (i < N) { me = P[pi]; ms = S[pi]; }
   bool ismax = true;
   if (use_nms) {
     const float t2 = sqrt_threshold(radius);
+    float bmax = 0.f, bmin = 0.f;
+    if (Q) {                                                 // x interval of this block's points (descending order)
+      if (threadIdx.x == 0) xr[0] = me.x;
+      if (i == min(blockIdx.x * 256 + 255, N - 1)) xr[1] = me.x;
+      __syncthreads();
+      bmax = xr[0]; bmin = xr[1];
+    }
     for (int j0 = 0; j0 < N; j0 += 256) {
+      if (Q) {
+        const float tmax = P[Q[j0]].x, tmin = P[Q[min(j0 + 255, N - 1)]].x;      // block-uniform loads
+        const float gap = fmaxf(__fsub_rn(tmin, bmax), __fsub_rn(bmin, tmax));     // > 0: the intervals are disjoint
+        if (gap > 0.f && __fmul_rn(gap, gap) >= t2) continue;
+      }
       const int j = j0 + threadIdx.x;
       float4 v = make_float4(0.f, 0.f, 0.f, -INFINITY);     // padding never suppresses: its score is -inf
-      if (j < N) { v = P[j]; v.w = S[j]; }
+      if (j < N) { const int pj = Q ? Q[j] : j; v = P[pj]; v.w = S[pj]; }
       __syncthreads();
       tp[threadIdx.x] = v;
       __syncthreads();
@@ -285,18 +304,18 @@ __global__ void __launch_bounds__(256) nms_key_kernel(const float4* __restrict__
       }
     }
   }
-  if (i < N) key[(size_t)pair * N + i] = __fmul_rn(ms, ismax ? 1.0f : 0.0f) + 0.0f;   // +0 canonicalises -0
+  if (i < N) key[(size_t)pair * N + pi] = __fmul_rn(ms, ismax ? 1.0f : 0.0f) + 0.0f;   // +0 canonicalises -0
 }
 
 // descending stable sort of key (ties -> lower index first) in one CTA per pair; writes the first S indices
-__global__ void __launch_bounds__(1024) topk_sort_kernel(const float* __restrict__ key, int N, int npow2, int S, int* __restrict__ seeds) {
+__global__ void __launch_bounds__(1024) topk_sort_kernel(const float* __restrict__ key, int stride, int N, int npow2, int S, int* __restrict__ seeds) {
   extern __shared__ unsigned long long sk[];
   const int pair = blockIdx.x;
-  const float* K = key + (size_t)pair * N;
+  const float* K = key + (size_t)pair * N * stride;
   for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
     unsigned long long v = ~0ull;
     if (i < N) {
-      unsigned u = __float_as_uint(K[i]);
+      unsigned u = __float_as_uint(K[(size_t)i * stride]);
       u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending-orderable
       v = ((unsigned long long)(~u) << 32) | (unsigned)i; // descending value, then ascending index
     }
