@@ -77,7 +77,32 @@ __global__ void __launch_bounds__(256) rows_to_img_kernel(const float* __restric
   }
 }
 
-enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3 };
+// Operands of the seed kNN distance GEMM (models/common.py:53-75 restricted to the seed rows) for the tensor pipe at fp32 accuracy:
+// x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  <a, b> ~ a_hi b_hi + a_hi b_lo + a_lo b_hi  (the dropped lo*lo term is 2^-22
+// relative), written as ONE K = 384 product:  A row = [a_hi | a_hi | a_lo],  B row = [b_hi | b_lo | b_hi].
+// rows: idx == NULL -> row r of x (B side), else row idx[r] (A side, the seeds).  One warp per row; image layout as above, 12 chunks.
+__global__ void __launch_bounds__(256) knn_operand_kernel(const float* __restrict__ x, const int* __restrict__ idx, int L, int nrows, int tiles,
+                                                          float* __restrict__ img) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp, pair = blockIdx.y;
+  if (r >= tiles * 128) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < nrows) {
+    const int src = idx ? idx[(size_t)pair * nrows + r] : r;
+    v = *reinterpret_cast<const float4*>(x + ((size_t)pair * L + src) * 128 + lane * 4);
+  }
+  const float4 hi = to_tf32(v);
+  const float4 lo = to_tf32(make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
+  const int tile = r >> 7, rr = r & 127;
+  float* base = img + ((size_t)pair * tiles + tile) * (12 * 4096);
+  const uint32_t off = swz_off(rr, lane & 7);
+  const int ch = lane >> 3;
+  *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)ch * 4096) + off) = hi;
+  *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)(4 + ch) * 4096) + off) = idx ? hi : lo;
+  *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)(8 + ch) * 4096) + off) = idx ? lo : hi;
+}
+
+enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4 };
 
 struct ImgGemmArgs {
   const float* a_img;      // [tiles][K/32][128 x 32] tf32 chunks (rows_to_img_kernel / DE_GEGLU epilogue)
@@ -91,6 +116,9 @@ struct ImgGemmArgs {
   int out_chunks, hidden;
   __nv_bfloat16* t0;       // DE_QIMG: Q tiles; DE_KVIMG: K tiles        [tiles][128 x 128] bf16
   __nv_bfloat16* t1;       // DE_KVIMG: V^T tiles
+  // batched use (blockIdx.z = pair): element strides of a_img / w_packed / out between pairs; DE_DIST: valid output columns
+  size_t a_pair_stride, w_pair_stride, out_pair_stride;
+  int ncols;
 };
 
 template <int NB, int EPI>
@@ -99,7 +127,7 @@ struct IgCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = NB * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = (EPI == DE_RES) ? 4 * 4096 : 0;
+  static constexpr int STG_BYTES = (EPI == DE_RES || EPI == DE_DIST) ? 4 * 4096 : 0;
   static constexpr int SMEM = 1024 + NSTG * STAGE + 256 + STG_BYTES;
 };
 
@@ -134,8 +162,8 @@ __global__ void __launch_bounds__(192) img_gemm_kernel(const ImgGemmArgs a) {
 
   if (warp == 0) {
     const uint32_t leader = elect_one() ? 1u : 0u;
-    const float* asrc = a.a_img + (size_t)tile * nkc * 4096;
-    const float* wsrc = a.w_packed + (size_t)cb * nkc * (NB * 32);
+    const float* asrc = a.a_img + blockIdx.z * a.a_pair_stride + (size_t)tile * nkc * 4096;
+    const float* wsrc = a.w_packed + blockIdx.z * a.w_pair_stride + (size_t)cb * nkc * (NB * 32);
 #pragma unroll 1
     for (int kc = 0; kc < nkc; ++kc) {
       const int st = kc % Cfg::NSTG;
@@ -193,6 +221,36 @@ __global__ void __launch_bounds__(192) img_gemm_kernel(const ImgGemmArgs a) {
                                  (__uint_as_float(v[4 * j + 3]) + b1.w) * gelu_erf(__uint_as_float(gt[4 * j + 3]) + b2.w));
           *reinterpret_cast<float4*>(dst + swz_off(r, j)) = valid ? to_tf32(o) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      } else if (EPI == DE_DIST) {
+        tmem_ld_wait();
+        // squared feature distance of unit vectors, 2 - 2 <a, b> (models/common.py:64-66), rows = seeds, columns = points
+        float* stg = sStg + q * 1024;
+        const int srow = lane >> 3, sj = lane & 7;
+        const int col0 = cb * 128 + c * 32;
+        float* obase = a.out + blockIdx.z * a.out_pair_stride + (size_t)(row0 + q * 32) * a.ld + col0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_float4(fmaf(-2.0f, __uint_as_float(v[4 * j]), 2.0f), fmaf(-2.0f, __uint_as_float(v[4 * j + 1]), 2.0f),
+                          fmaf(-2.0f, __uint_as_float(v[4 * j + 2]), 2.0f), fmaf(-2.0f, __uint_as_float(v[4 * j + 3]), 2.0f));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rw = i * 4 + srow;
+          if (row0 + q * 32 + rw < a.L) {
+            const float4 o = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
+            float* dst = obase + (size_t)rw * a.ld + sj * 4;
+            const int cc = col0 + sj * 4;
+            if (cc + 3 < a.ncols && (a.ld & 3) == 0) *reinterpret_cast<float4*>(dst) = o;
+            else {
+              if (cc < a.ncols) dst[0] = o.x;
+              if (cc + 1 < a.ncols) dst[1] = o.y;
+              if (cc + 2 < a.ncols) dst[2] = o.z;
+              if (cc + 3 < a.ncols) dst[3] = o.w;
+            }
+          }
+        }
+        __syncwarp();
       } else if (EPI == DE_RES) {
         tmem_ld_wait();
         // coalesced row-major I/O through a per-warp XOR-swizzled 32 x 32 staging tile
@@ -264,7 +322,7 @@ __global__ void __launch_bounds__(192) img_gemm_kernel(const ImgGemmArgs a) {
 }
 
 template <int NB, int EPI>
-inline cudaError_t launch_img_gemm(const ImgGemmArgs& a, int col_blocks, cudaStream_t st) {
+inline cudaError_t launch_img_gemm(const ImgGemmArgs& a, int col_blocks, cudaStream_t st, int pairs = 1) {
   using Cfg = IgCfg<NB, EPI>;
   static bool configured = false;
   auto kern = img_gemm_kernel<NB, EPI>;
@@ -273,7 +331,7 @@ inline cudaError_t launch_img_gemm(const ImgGemmArgs& a, int col_blocks, cudaStr
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<dim3(a.tiles, col_blocks), 192, Cfg::SMEM, st>>>(a);
+  kern<<<dim3(a.tiles, col_blocks, pairs), 192, Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 

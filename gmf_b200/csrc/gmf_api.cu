@@ -202,6 +202,7 @@ struct gmf_ctx {
   int chunk_pairs = 64;
   int pcn_qkv = 1;          // PointCN + QKV projection chained in one kernel
   int sc_fuse_fc = 1;       // fc_message.0/.3 fused into the SC attention kernel's tail
+  int knn_impl = 1;         // 1 = seed kNN distances on the tensor pipe (error-compensated tf32, K = 384), 0 = FP32 register-blocked SGEMM
   int ffn_impl = 3;         // 3 = fused GEGLU FFN kernel + fused fc_message.6 tail, 2 = fused FFN, 1 = two linear kernels
   int fus_impl = 3;         // 3 = fusion attention with fused to_out + residual, 2 = separate to_out kernel
   int sc_impl = 14;         // 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12 = 1 thread per row
@@ -237,6 +238,7 @@ struct Work {
   __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts, *aq, *bd;
   __nv_bfloat16 *kf_all, *vtf_all;   // [layers] context K / V^T tiles of every encoder layer (projected up front on a side stream)
   size_t kv_stride;
+  float *knn_a, *knn_b;   // split-tf32 operand images of the seed kNN distance GEMM (seed rows / all points)
   int *perm;          // points of each pair in descending-x order (windowed NMS)
   float *normed, *conf, *key, *seed_w, *seed_trans, *pre_refine, *dist, *seedM;
   int *seeds, *knn, *counts, *best;
@@ -277,6 +279,7 @@ size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k, int laye
   w.seed_w = b.take<float>((size_t)B * S * k); w.seed_trans = b.take<float>((size_t)B * S * 16);
   w.pre_refine = b.take<float>((size_t)B * 16);
   w.dist = b.take<float>((size_t)B * S * N);
+  w.knn_a = b.take<float>((size_t)B * cdiv(S, 128) * 12 * 4096); w.knn_b = b.take<float>((size_t)B * nt * 12 * 4096);
   w.seedM = b.take<float>((size_t)B * S * 1600);
   w.seeds = b.take<int>((size_t)B * S); w.knn = b.take<int>((size_t)B * S * k); w.counts = b.take<int>((size_t)B * S);
   w.best = b.take<int>(B); w.pair_mask = b.take<unsigned>(B);
@@ -550,8 +553,22 @@ int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const 
   if (k < 1 || k > 40) return fail(GMF_ERR_INVALID, "k must be in [1, 40]");
   {
     ProfScope ps(CAT_KNN, st);
-    seed_dist_kernel<<<dim3(cdiv(N, 128), cdiv(S, 128), B), 256, 0, st>>>(normed, seeds, N, S, w.dist);
-    LAUNCHED();
+    if (ctx->knn_impl >= 1) {   // tensor pipe, error-compensated tf32 (K = 384): dgr_head.cuh knn_operand_kernel + img_gemm_kernel<128, DE_DIST>
+      const int st_ = cdiv(S, 128), nt_ = cdiv(N, 128);
+      knn_operand_kernel<<<dim3(st_ * 16, B), 256, 0, st>>>(normed, seeds, N, S, st_, w.knn_a);
+      LAUNCHED();
+      knn_operand_kernel<<<dim3(nt_ * 16, B), 256, 0, st>>>(normed, nullptr, N, N, nt_, w.knn_b);
+      LAUNCHED();
+      ImgGemmArgs a{};
+      a.a_img = w.knn_a; a.w_packed = w.knn_b; a.K = 384; a.L = S; a.tiles = st_; a.out = w.dist; a.ld = N; a.ncols = N;
+      a.a_pair_stride = (size_t)st_ * 12 * 4096; a.w_pair_stride = (size_t)nt_ * 12 * 4096; a.out_pair_stride = (size_t)S * N;
+      cudaError_t e = launch_img_gemm<128, DE_DIST>(a, nt_, st, B);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (e != cudaSuccess) return fail_cuda(e, "seed kNN distance GEMM launch");
+    } else {
+      seed_dist_kernel<<<dim3(cdiv(N, 128), cdiv(S, 128), B), 256, 0, st>>>(normed, seeds, N, S, w.dist);
+      LAUNCHED();
+    }
     TRY(launch_select(w.dist, B, N, S, k, knn, st));
   }
   ProfScope ps(CAT_SPECTRAL, st);
@@ -712,6 +729,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   if (const char* e = getenv("GMF_SC_IMPL")) c->sc_impl = atoi(e);
   if (const char* e = getenv("GMF_FUS_IMPL")) c->fus_impl = atoi(e);
   if (const char* e = getenv("GMF_FFN_IMPL")) c->ffn_impl = atoi(e);
+  if (const char* e = getenv("GMF_KNN_IMPL")) c->knn_impl = atoi(e);
   if (const char* e = getenv("GMF_SC_FUSE_FC")) c->sc_fuse_fc = atoi(e);
   if (const char* e = getenv("GMF_PCN_QKV")) c->pcn_qkv = atoi(e);
   if (const char* e = getenv("GMF_OVERLAP")) c->overlap = atoi(e);
