@@ -14,6 +14,7 @@ _lib: Optional[C.CDLL] = None
 EXPORTS = [
     "gmf_last_error", "gmf_version", "gmf_create", "gmf_destroy", "gmf_weight_count", "gmf_weight_spec",
     "gmf_load_weights", "gmf_workspace_bytes", "gmf_pointdsc_forward", "gmf_pointdsc_forward_host",
+    "gmf_pointdsc_forward_host_async", "gmf_stream_synchronize",
     "gmf_fusion_layer", "gmf_sc_attention", "gmf_encoder_layer", "gmf_classify", "gmf_pick_seeds",
     "gmf_seed_hypotheses", "gmf_score_hypotheses", "gmf_rigid_transform_3d", "gmf_launch_count",
     "gmf_debug_linear", "gmf_debug_attention", "gmf_profile_enable", "gmf_profile_read",
@@ -58,6 +59,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     lib.gmf_pointdsc_forward.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.gmf_pointdsc_forward_host.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
+    lib.gmf_pointdsc_forward_host_async.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
+    lib.gmf_stream_synchronize.argtypes = [vp, vp]
     lib.gmf_fusion_layer.argtypes = [vp, i, vp, vp, i, i, i, vp, vp, sz, vp]
     lib.gmf_sc_attention.argtypes = [vp, i, vp, vp, vp, i, i, vp, vp, sz, vp]
     lib.gmf_encoder_layer.argtypes = [vp, i, vp, vp, vp, vp, i, i, i, vp, vp, sz, vp]

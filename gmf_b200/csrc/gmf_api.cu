@@ -223,6 +223,9 @@ struct gmf_ctx {
   cudaStream_t copy_stream = nullptr;   // uploads of the next chunk overlap the current chunk's kernels
   cudaEvent_t copy_ev[64] = {};
   cudaEvent_t start_ev = nullptr;
+  cudaEvent_t in_done[2] = {};          // forward that read input staging set 0 / 1 has finished (double-buffered across host calls)
+  int in_set = 0;
+  int in_shape[3] = {0, 0, 0};          // (B, N, T) of the previous host call: a different shape moves the staging layout
   Prof prof;
 };
 
@@ -753,6 +756,7 @@ void gmf_destroy(gmf_ctx* ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     for (auto e : ctx->copy_ev) if (e) cudaEventDestroy(e);
     cudaEventDestroy(ctx->start_ev);
+    for (auto e : ctx->in_done) if (e) cudaEventDestroy(e);
   }
   for (auto e : ctx->prof.ev) cudaEventDestroy(e);
   if (g_prof == &ctx->prof) g_prof = nullptr;
@@ -1019,9 +1023,9 @@ std::vector<int> plan_host_chunks(int B, int N, int cap, int sms) {
 
 extern "C" {
 
-int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
-                              const float* q_tok, int B, int N, int T, int testing, float* final_trans, float* final_labels,
-                              float* confidence, void* stream) {
+static int forward_host_impl(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
+                             const float* q_tok, int B, int N, int T, int testing, float* final_trans, float* final_labels,
+                             float* confidence, void* stream, bool sync) {
   TRY(require_loaded(ctx));
   if (B < 1 || N < 2 || T < 1) return fail(GMF_ERR_INVALID, "need B >= 1, N >= 2, T >= 1");
   CU(cudaSetDevice(ctx->device));
@@ -1031,15 +1035,21 @@ int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* 
   Bump b{nullptr};
   auto layout = [&](Bump& bb, float*& d_corr, float*& d_src, float*& d_tgt, float*& d_p, float*& d_q, float*& d_tr, float*& d_lab,
                     float*& d_conf, int*& d_seeds, uint8_t*& d_ws) {
-    d_corr = bb.take<float>((size_t)B * N * 6); d_src = bb.take<float>((size_t)B * N * 3); d_tgt = bb.take<float>((size_t)B * N * 3);
-    d_p = bb.take<float>((size_t)B * T * 128); d_q = bb.take<float>((size_t)B * T * 128);
+    // two input staging sets: the uploads of call k+1 may start while call k still computes from the other set
+    for (int set = 0; set < 2; ++set) {
+      float* c_ = bb.take<float>((size_t)B * N * 6); float* s_ = bb.take<float>((size_t)B * N * 3); float* t_ = bb.take<float>((size_t)B * N * 3);
+      float* p_ = bb.take<float>((size_t)B * T * 128); float* q_ = bb.take<float>((size_t)B * T * 128);
+      if (set == ctx->in_set) { d_corr = c_; d_src = s_; d_tgt = t_; d_p = p_; d_q = q_; }
+    }
     d_tr = bb.take<float>((size_t)B * 16); d_lab = bb.take<float>((size_t)B * N); d_conf = bb.take<float>((size_t)B * N);
     d_seeds = bb.take<int>((size_t)B * S); d_ws = bb.take<uint8_t>(ws);
   };
   float *d_corr, *d_src, *d_tgt, *d_p, *d_q, *d_tr, *d_lab, *d_conf; int* d_seeds; uint8_t* d_ws;
   layout(b, d_corr, d_src, d_tgt, d_p, d_q, d_tr, d_lab, d_conf, d_seeds, d_ws);
   const size_t need = b.off + 2048;
+  bool realloc_stage = false;
   if (need > ctx->stage_bytes) {
+    realloc_stage = true;
     CU(cudaDeviceSynchronize());
     if (ctx->stage) cudaFree(ctx->stage);
     ctx->stage = nullptr; ctx->stage_bytes = 0;
@@ -1054,13 +1064,27 @@ int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* 
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->copy_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming));
+    for (auto& e : ctx->in_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->in_done[0], st)); CU(cudaEventRecord(ctx->in_done[1], st));
   }
   cudaStream_t cs = ctx->copy_stream;
-  CU(cudaEventRecord(ctx->start_ev, st));                      // the staging buffers may still be read by earlier work on `st`
-  CU(cudaStreamWaitEvent(cs, ctx->start_ev, 0));
+  if (realloc_stage) {                                         // fresh buffers: nothing in flight refers to them
+    CU(cudaEventRecord(ctx->in_done[0], st)); CU(cudaEventRecord(ctx->in_done[1], st));
+  }
+  CU(cudaStreamWaitEvent(cs, ctx->in_done[ctx->in_set], 0));   // the forward that last read this input set has finished
+  if (ctx->in_shape[0] != B || ctx->in_shape[1] != N || ctx->in_shape[2] != T) {
+    CU(cudaStreamWaitEvent(cs, ctx->in_done[ctx->in_set ^ 1], 0));   // the layout moved: nothing earlier may still be reading
+    ctx->in_shape[0] = B; ctx->in_shape[1] = N; ctx->in_shape[2] = T;
+  }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  const std::vector<int> cuts = plan_host_chunks(B, N, std::min(48, ctx->chunk_pairs), sms);     // chunk boundaries
+  // chunk boundaries.  The asynchronous entry point is meant for back-to-back submission: the whole upload of call k+1 already overlaps
+  // the kernels of call k, so its batch is not split (every chunk pays the fixed cost of the small seed / pose kernels again).
+  std::vector<int> cuts = sync ? plan_host_chunks(B, N, std::min(48, ctx->chunk_pairs), sms) : std::vector<int>{0};
+  if (!sync) {
+    for (int b0 = ctx->chunk_pairs; b0 < B; b0 += ctx->chunk_pairs) cuts.push_back(b0);
+    cuts.push_back(B);
+  }
   const int nchunk = (int)cuts.size() - 1;
   if (nchunk > (int)(sizeof(ctx->copy_ev) / sizeof(ctx->copy_ev[0]))) return fail(GMF_ERR_INVALID, "batch too large for the host entry point (max 64 chunks)");
   for (int c = 0; c < nchunk; ++c) {
@@ -1082,7 +1106,28 @@ int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* 
   CU(cudaMemcpyAsync(final_trans, d_tr, (size_t)B * 16 * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(final_labels, d_lab, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   if (confidence) CU(cudaMemcpyAsync(confidence, d_conf, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(cudaEventRecord(ctx->in_done[ctx->in_set], st));
+  ctx->in_set ^= 1;
+  if (sync) CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
+                              const float* q_tok, int B, int N, int T, int testing, float* final_trans, float* final_labels,
+                              float* confidence, void* stream) {
+  return forward_host_impl(ctx, corr_pos, src, tgt, p_tok, q_tok, B, N, T, testing, final_trans, final_labels, confidence, stream, true);
+}
+
+int gmf_pointdsc_forward_host_async(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
+                                    const float* q_tok, int B, int N, int T, int testing, float* final_trans, float* final_labels,
+                                    float* confidence, void* stream) {
+  return forward_host_impl(ctx, corr_pos, src, tgt, p_tok, q_tok, B, N, T, testing, final_trans, final_labels, confidence, stream, false);
+}
+
+int gmf_stream_synchronize(gmf_ctx* ctx, void* stream) {
+  if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
 

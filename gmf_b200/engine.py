@@ -105,6 +105,18 @@ class Engine:
                                                       1 if testing else 0, _ptr(out_trans), _ptr(out_labels), _ptr(out_conf),
                                                       self._stream()))
 
+    def forward_host_async(self, corr_pos, src, tgt, p_tok, q_tok, out_trans, out_labels, out_conf=None, testing=True):
+        """Like forward_host but returns once the work is enqueued; call `synchronize()` before reading the outputs.  Consecutive
+        calls overlap: the uploads of call k+1 run while call k computes (double-buffered staging inside the library)."""
+        B, N, _ = corr_pos.shape
+        T = p_tok.shape[1]
+        _lib.check(self.lib.gmf_pointdsc_forward_host_async(self.h, _ptr(corr_pos), _ptr(src), _ptr(tgt), _ptr(p_tok), _ptr(q_tok), B, N, T,
+                                                            1 if testing else 0, _ptr(out_trans), _ptr(out_labels), _ptr(out_conf),
+                                                            self._stream()))
+
+    def synchronize(self):
+        _lib.check(self.lib.gmf_stream_synchronize(self.h, self._stream()))
+
     # ---- stages ---------------------------------------------------------------------------------
     def fusion_layer(self, layer: int, queries, context):
         queries, context = _chk(queries), _chk(context)

@@ -83,6 +83,15 @@ int gmf_pointdsc_forward_host(gmf_ctx* ctx, const float* corr_pos, const float* 
                               const float* q_tok, int B, int N, int T, int testing, float* final_trans,
                               float* final_labels, float* confidence, void* stream);
 
+/* Same, without the final synchronise: the call returns once everything is enqueued (uploads on a context-owned copy stream,
+ * kernels and the D2H copies on `stream`).  Input staging is double-buffered, so the uploads of call k+1 overlap the kernels of
+ * call k; the host input buffers must stay valid and the outputs must not be read until gmf_stream_synchronize(ctx, stream)
+ * (or any later synchronising call on that stream) returns.  Use one stream per context for the host entry points. */
+int gmf_pointdsc_forward_host_async(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok,
+                                    const float* q_tok, int B, int N, int T, int testing, float* final_trans,
+                                    float* final_labels, float* confidence, void* stream);
+int gmf_stream_synchronize(gmf_ctx* ctx, void* stream);
+
 /* ---- per-stage entry points (teacher-forced parity) ---------------------------------------- */
 /* FusionLayer.forward (models/fusion_layer.py:172-201), depth 0.  layer < 0: encoder.fusion_layer_1 (pe=False);
  * layer >= 0: NonLocal_layer_{layer}.fusion_layer_2 (pe=True).  queries [B,Lq,128], context [B,Lk,128] -> out [B,Lq,128]. */

@@ -416,3 +416,34 @@ def test_c_abi_error_paths():
         eng.classify(torch.zeros(1, 8, 128).cuda())
     with pytest.raises(GmfError):
         Engine(num_layers=1, k=64)
+
+
+def test_host_entry_async_pipelined_calls_match_sync_calls():
+    """gmf_pointdsc_forward_host_async: consecutive calls with different inputs (double-buffered staging, uploads overlapping the
+    previous call's kernels) give the same results as synchronous calls; a shape change in between is handled."""
+    from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
+    from gmf_b200.weights import hot_path_spec
+    cfg = dict(O.DEFAULT_CFG, num_layers=2)
+    eng = make_engine(cfg, synth_state_dict(hot_path_spec(2), seed=0, plain_init=True))
+
+    def inputs(B, N, T, seed):
+        pr = synth_pairs(B, N, seed=seed, inlier_ratio=0.3, noise=0.002)
+        return [t.contiguous().pin_memory() for t in (pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], synth_tokens(B, T, seed), synth_tokens(B, T, seed + 1))]
+
+    def outs(B, N):
+        return [torch.empty(B, 4, 4).pin_memory(), torch.empty(B, N).pin_memory(), torch.empty(B, N).pin_memory()]
+
+    cases = [(12, 700, 300, 1), (12, 700, 300, 2), (5, 512, 96, 3), (12, 700, 300, 4)]
+    ins = [inputs(*c) for c in cases]
+    ref = []
+    for c, x in zip(cases, ins):
+        o = outs(c[0], c[1])
+        eng.forward_host(*x, *o, testing=True)
+        ref.append([t.clone() for t in o])
+    got = [outs(c[0], c[1]) for c in cases]
+    for x, o in zip(ins, got):
+        eng.forward_host_async(*x, *o, testing=True)
+    eng.synchronize()
+    for r, g in zip(ref, got):
+        for a_, b_ in zip(r, g):
+            assert torch.equal(a_, b_)
