@@ -80,9 +80,10 @@ __global__ void __launch_bounds__(256) rows_to_img_kernel(const float* __restric
 // Operands of the seed kNN distance GEMM (models/common.py:53-75 restricted to the seed rows) for the tensor pipe at fp32 accuracy:
 // x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  <a, b> ~ a_hi b_hi + a_hi b_lo + a_lo b_hi  (the dropped lo*lo term is 2^-22
 // relative), written as ONE K = 384 product:  A row = [a_hi | a_hi | a_lo],  B row = [b_hi | b_lo | b_hi].
-// rows: idx == NULL -> row r of x (B side), else row idx[r] (A side, the seeds).  One warp per row; image layout as above, 12 chunks.
-__global__ void __launch_bounds__(256) knn_operand_kernel(const float* __restrict__ x, const int* __restrict__ idx, int L, int nrows, int tiles,
-                                                          float* __restrict__ img) {
+// rows: idx == NULL -> row r of x, else row idx[r] (the seeds); a_side selects the A-row / B-row chunk order.  One warp per row; image
+// layout as above, 12 chunks.
+__global__ void __launch_bounds__(256) knn_operand_kernel(const float* __restrict__ x, const int* __restrict__ idx, int a_side, int L, int nrows,
+                                                          int tiles, float* __restrict__ img) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp, pair = blockIdx.y;
   if (r >= tiles * 128) return;
@@ -98,11 +99,11 @@ __global__ void __launch_bounds__(256) knn_operand_kernel(const float* __restric
   const uint32_t off = swz_off(rr, lane & 7);
   const int ch = lane >> 3;
   *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)ch * 4096) + off) = hi;
-  *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)(4 + ch) * 4096) + off) = idx ? hi : lo;
-  *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)(8 + ch) * 4096) + off) = idx ? lo : hi;
+  *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)(4 + ch) * 4096) + off) = a_side ? hi : lo;
+  *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)(8 + ch) * 4096) + off) = a_side ? lo : hi;
 }
 
-enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4 };
+enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4, DE_COMPAT = 5 };
 
 struct ImgGemmArgs {
   const float* a_img;      // [tiles][K/32][128 x 32] tf32 chunks (rows_to_img_kernel / DE_GEGLU epilogue)
@@ -119,6 +120,7 @@ struct ImgGemmArgs {
   // batched use (blockIdx.z = pair): element strides of a_img / w_packed / out between pairs; DE_DIST: valid output columns
   size_t a_pair_stride, w_pair_stride, out_pair_stride;
   int ncols;
+  float scale;             // DE_COMPAT: 1 / sigma^2
 };
 
 template <int NB, int EPI>
@@ -127,7 +129,7 @@ struct IgCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = NB * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = (EPI == DE_RES || EPI == DE_DIST) ? 4 * 4096 : 0;
+  static constexpr int STG_BYTES = (EPI == DE_RES || EPI == DE_DIST || EPI == DE_COMPAT) ? 4 * 4096 : 0;
   static constexpr int SMEM = 1024 + NSTG * STAGE + 256 + STG_BYTES;
 };
 
@@ -221,18 +223,29 @@ __global__ void __launch_bounds__(192) img_gemm_kernel(const ImgGemmArgs a) {
                                  (__uint_as_float(v[4 * j + 3]) + b1.w) * gelu_erf(__uint_as_float(gt[4 * j + 3]) + b2.w));
           *reinterpret_cast<float4*>(dst + swz_off(r, j)) = valid ? to_tf32(o) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      } else if (EPI == DE_DIST) {
+      } else if (EPI == DE_DIST || EPI == DE_COMPAT) {
         tmem_ld_wait();
-        // squared feature distance of unit vectors, 2 - 2 <a, b> (models/common.py:64-66), rows = seeds, columns = points
+        // DE_DIST: squared feature distance of unit vectors, 2 - 2 <a, b> (models/common.py:64-66), rows = seeds, columns = points
+        // DE_COMPAT: feature compatibility clamp(1 - (1 - <a, b>) / sigma^2, 0, 1) with a zero diagonal (models/PointDSC.py:231-234)
         float* stg = sStg + q * 1024;
         const int srow = lane >> 3, sj = lane & 7;
         const int col0 = cb * 128 + c * 32;
         float* obase = a.out + blockIdx.z * a.out_pair_stride + (size_t)(row0 + q * 32) * a.ld + col0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_float4(fmaf(-2.0f, __uint_as_float(v[4 * j]), 2.0f), fmaf(-2.0f, __uint_as_float(v[4 * j + 1]), 2.0f),
-                          fmaf(-2.0f, __uint_as_float(v[4 * j + 2]), 2.0f), fmaf(-2.0f, __uint_as_float(v[4 * j + 3]), 2.0f));
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          if (EPI == DE_DIST) {
+            o = make_float4(fmaf(-2.0f, __uint_as_float(v[4 * j]), 2.0f), fmaf(-2.0f, __uint_as_float(v[4 * j + 1]), 2.0f),
+                            fmaf(-2.0f, __uint_as_float(v[4 * j + 2]), 2.0f), fmaf(-2.0f, __uint_as_float(v[4 * j + 3]), 2.0f));
+          } else {
+            const int grow = row0 + r, gc = col0 + 4 * j;      // this thread's row, first of its four columns
+            float e[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) e[t] = (grow == gc + t) ? 0.f : __saturatef(1.0f - (1.0f - __uint_as_float(v[4 * j + t])) * a.scale);
+            o = make_float4(e[0], e[1], e[2], e[3]);
+          }
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+        }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

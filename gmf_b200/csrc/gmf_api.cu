@@ -558,9 +558,9 @@ int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const 
     ProfScope ps(CAT_KNN, st);
     if (ctx->knn_impl >= 1) {   // tensor pipe, error-compensated tf32 (K = 384): dgr_head.cuh knn_operand_kernel + img_gemm_kernel<128, DE_DIST>
       const int st_ = cdiv(S, 128), nt_ = cdiv(N, 128);
-      knn_operand_kernel<<<dim3(st_ * 16, B), 256, 0, st>>>(normed, seeds, N, S, st_, w.knn_a);
+      knn_operand_kernel<<<dim3(st_ * 16, B), 256, 0, st>>>(normed, seeds, 1, N, S, st_, w.knn_a);
       LAUNCHED();
-      knn_operand_kernel<<<dim3(nt_ * 16, B), 256, 0, st>>>(normed, nullptr, N, N, nt_, w.knn_b);
+      knn_operand_kernel<<<dim3(nt_ * 16, B), 256, 0, st>>>(normed, nullptr, 0, N, N, nt_, w.knn_b);
       LAUNCHED();
       ImgGemmArgs a{};
       a.a_img = w.knn_a; a.w_packed = w.knn_b; a.K = 384; a.L = S; a.tiles = st_; a.out = w.dist; a.ld = N; a.ncols = N;
@@ -1281,3 +1281,4 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
 
 #include "dgr_head_api.inl"
 #include "matcher_api.inl"
+#include "compat_api.inl"

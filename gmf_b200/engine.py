@@ -114,6 +114,16 @@ class Engine:
                                                             1 if testing else 0, _ptr(out_trans), _ptr(out_labels), _ptr(out_conf),
                                                             self._stream()))
 
+    def feature_compat(self, feat):
+        """Training-mode `M` (PointDSC.py:231-234): feat [B,N,128] un-normalised encoder features -> [B,N,N]."""
+        feat = _chk(feat)
+        B, N, _ = feat.shape
+        M = torch.empty(B, N, N, device=feat.device)
+        nb = int(self.lib.gmf_feature_compat_workspace_bytes(B, N))
+        ws = torch.empty(nb, dtype=torch.uint8, device=feat.device)
+        _lib.check(self.lib.gmf_feature_compat(self.h, _ptr(feat), B, N, _ptr(M), _ptr(ws), nb, self._stream()))
+        return M
+
     def synchronize(self):
         _lib.check(self.lib.gmf_stream_synchronize(self.h, self._stream()))
 

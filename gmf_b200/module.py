@@ -175,8 +175,5 @@ class PointDSC(nn.Module):
             if testing:
                 return {"final_trans": trans, "final_labels": labels, "M": None}
             # training-mode outputs (PointDSC.py:231-234, 260): M from normalised features, logits as labels
-            f = torch.nn.functional.normalize(feat, p=2, dim=-1)
-            M = torch.clamp(1 - (1 - f @ f.transpose(1, 2)) / self.sigma ** 2, min=0, max=1)
-            idx = torch.arange(M.shape[1], device=M.device)
-            M[:, idx, idx] = 0
+            M = _ENGINES[self._engine_id].feature_compat(feat)
             return {"final_trans": trans, "final_labels": conf, "M": M}

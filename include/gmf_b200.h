@@ -141,6 +141,12 @@ int gmf_dgr_head_load_weights(gmf_dgr_head* h, const float* host_flat, int64_t n
 /* latents [M,256] (all active bottleneck voxels of the batch as one sequence), image_feat [T,128] -> out [M,256]; device pointers */
 int gmf_dgr_head_forward(gmf_dgr_head* h, const float* latents, const float* image_feat, int M, int T, float* out, void* stream);
 
+/* Training-mode output `M` of PointDSC.forward (models/PointDSC.py:231-234): feat [B,N,128] (un-normalised encoder features, the
+ * optional `feat` output of gmf_pointdsc_forward) -> M [B,N,N] = clamp(1 - (1 - Fn Fn^T) / sigma^2, 0, 1) with a zero diagonal,
+ * Fn = F.normalize(feat), sigma = the loaded `sigma` parameter.  Tensor-pipe GEMM at fp32 accuracy (error-compensated tf32). */
+size_t gmf_feature_compat_workspace_bytes(int B, int N);
+int gmf_feature_compat(gmf_ctx* ctx, const float* feat, int B, int N, float* M, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- correspondence construction (the step right before the path) ------------- */
 /* Nearest-neighbour matcher in descriptor space + network input assembly, NumPy in the reference's datasets
  * (GMF_PointDSC/datasets/ThreeDMatch.py:384-391, 401-402, 411-414; datasets/KITTI.py:94-102):

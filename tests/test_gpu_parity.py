@@ -315,6 +315,27 @@ def test_module_drop_in_with_backbone():
     data.pop("testing")
     res = m(data)                                           # training-mode outputs: logits + M
     assert res["M"].shape == (1, 384, 384) and (res["final_labels"].cpu() - fx["confidence"]).abs().max() < 1e-2
+    # M = clamp(1 - (1 - Fn Fn^T) / sigma^2, 0, 1), zero diagonal (PointDSC.py:231-234), from the reference's own features
+    fn = F.normalize(fx["feat"].double(), dim=-1)
+    Mref = torch.clamp(1 - (1 - fn @ fn.transpose(1, 2)) / float(sd["sigma"]) ** 2, min=0, max=1)
+    Mref[:, torch.arange(384), torch.arange(384)] = 0
+    assert (res["M"].cpu().double() - Mref).abs().max() < 2e-2          # bf16-attention feature noise through 1/sigma^2
+
+
+def test_feature_compat_matches_fp64_formula():
+    """gmf_feature_compat (training-mode M) on given features: tensor-pipe GEMM at fp32 accuracy, ragged N, B > 1, zero diagonal."""
+    from gmf_b200.synth import synth_state_dict
+    from gmf_b200.weights import hot_path_spec
+    sd = synth_state_dict(hot_path_spec(1), seed=3)
+    eng = make_engine(dict(O.DEFAULT_CFG, num_layers=1), sd)
+    g = torch.Generator().manual_seed(5)
+    for B, N in [(2, 1000), (1, 130), (3, 257)]:
+        feat = torch.randn(B, N, 128, generator=g) * 3.0
+        M = eng.feature_compat(feat.cuda()).cpu().double()
+        fn = F.normalize(feat.double(), dim=-1)
+        ref = torch.clamp(1 - (1 - fn @ fn.transpose(1, 2)) / float(sd["sigma"]) ** 2, min=0, max=1)
+        ref[:, torch.arange(N), torch.arange(N)] = 0
+        assert M.shape == (B, N, N) and (M - ref).abs().max() < 5e-6, float((M - ref).abs().max())
 
 
 def test_full_size_properties_n5000():
