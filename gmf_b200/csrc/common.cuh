@@ -145,6 +145,7 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int fmt) {
 }
 // advance a descriptor's start address by a byte offset (multiple of 16; no carry out of the 14-bit field in our layouts)
 __device__ __forceinline__ uint64_t umma_desc_adv(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
+constexpr int kFmtF16 = 0;    // kind::f16 operand formats: 0 = F16, 1 = BF16
 constexpr int kFmtBF16 = 1;
 constexpr int kFmtTF32 = 2;
 
@@ -342,6 +343,11 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
 __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 // round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits)

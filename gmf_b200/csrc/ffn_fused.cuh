@@ -10,7 +10,15 @@
 // W1 ring 3 x 32 KB, W2 ring 2 x 32 KB.  Warps: 0-15 workers (LayerNorm prologue, GEGLU, output epilogue), 16 MMA1 issuer, 17 MMA2
 // issuer, 18 W1 producer, 19 W2 producer.  Issue loops are fully unrolled (all descriptors = uniform base + constant).
 #pragma once
+#include <cuda_fp16.h>
 #include "linear_tc.cuh"
+
+// GMF_FFN_F16 = 1 (default): the first GEMM runs in kind::f16 with fp16 operands (LN(x) and W1 rounded to half precision: the same 11-bit
+// significand as TF32, |LN(x)| and |W1| are far inside the fp16 range) - W1 is the bulk of the weight stream (64 of 96 KB per pass), and the
+// pass cadence was set by the 3 x 32 KB W1 ring holding only 1.5 passes; in fp16 a pass is ONE 32 KB chunk and the ring holds three.
+#ifndef GMF_FFN_F16
+#define GMF_FFN_F16 1
+#endif
 
 namespace gmf {
 
@@ -29,7 +37,8 @@ struct FfnArgs {
   int L, tiles;
   const float* ln_g;
   const float* ln_b;
-  const float* w1_packed;  // 8 passes x 2 k-chunks x [128 rows (64 value | 64 gate) x 64 k] swizzled tf32
+  const float* w1_packed;  // tf32 build: 8 passes x 2 k-chunks x [128 rows (64 value | 64 gate) x 64 k] swizzled tf32;
+                           // fp16 build: 8 passes x [128 rows x 128 k] swizzled fp16 (2 atoms of 64 k)
   const float* b1;         // [1024]: value 0..511, gate 512..1023
   const float* w2_packed;  // 8 chunks x [128 out rows x 64 hidden] swizzled tf32
   const float* b2;         // [128]
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint8_t* src = (const uint8_t*)a.w1_packed;
 #pragma unroll 1
-    for (int s = 0; s < 2 * Cfg::PASSES; ++s) {
+    for (int s = 0; s < (GMF_FFN_F16 ? 1 : 2) * Cfg::PASSES; ++s) {
       const int slot = s % Cfg::N1;
       if (s >= Cfg::N1) mbar_wait(&empty1[slot], ((s / Cfg::N1) - 1) & 1);
       mbar_expect_tx_p(&full1[slot], Cfg::W_BYTES, leader);
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
     // ------------------------------- MMA1 issuer: ACC1[p&1] = LN(x) . W1_p^T -------------------------------
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t idesc = umma_idesc(128, 128, kFmtTF32);
+    const uint32_t idesc = umma_idesc(128, 128, GMF_FFN_F16 ? kFmtF16 : kFmtTF32);
     const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
     const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW1));
     mbar_wait(a_ready, 0);
@@ -133,6 +142,25 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       TR(1, 4 * p);
       if (p >= 2) mbar_wait(&acc1_free[p & 1], ((p >> 1) - 1) & 1);
       TR(1, 4 * p + 1);
+#if GMF_FFN_F16
+      {
+        const int slot = p % Cfg::N1;
+        mbar_wait(&full1[slot], (p / Cfg::N1) & 1);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int at = 0; at < 2; ++at)                       // 64 k per swizzle atom, 16 k per MMA
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_bf16(tm + (p & 1) * 128, umma_desc_adv(a_desc0, at * 16384 + ks * 32), umma_desc_adv(w_desc0, slot * Cfg::W_BYTES + at * 16384 + ks * 32),
+                          idesc, (at | ks) ? 1u : 0u);
+          tc_commit(&empty1[slot]);
+          tc_commit(&acc1_full[p & 1]);
+        }
+        __syncwarp();
+        TR(1, 4 * p + 2);
+      }
+#else
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
         const int s = 2 * p + kc, slot = s % Cfg::N1;
@@ -151,6 +179,7 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
         __syncwarp();
         TR(1, 4 * p + 2 + kc);
       }
+#endif
     }
   } else if (warp == 17) {
     // ------------------------------- MMA2 issuer: OUT += H[p&1] . W2_p^T (A operand from tensor memory) -------------------------------
@@ -225,7 +254,17 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       for (int i = 0; i < RPW; ++i) {
         const float r_ = rsqrtf(rs[i] * (1.0f / 128.0f) + 1e-5f);
         const float4 v = make_float4(fmaf(rv[i].x * r_, g4.x, b4.x), fmaf(rv[i].y * r_, g4.y, b4.y), fmaf(rv[i].z * r_, g4.z, b4.z), fmaf(rv[i].w * r_, g4.w, b4.w));
+#if GMF_FFN_F16
+        {
+          const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+          // channels 4 lane .. 4 lane + 3 of row r: atom lane >> 4 (64 channels = 128 B per row), 16-byte piece (lane & 15) >> 1, half of it lane & 1
+          *reinterpret_cast<uint2*>(sA + (lane >> 4) * 16384 + swz_off(rbase + i, (lane & 15) >> 1) + (lane & 1) * 8) = pk;
+        }
+#else
         *reinterpret_cast<float4*>(sA + (lane >> 3) * 16384 + swz_off(rbase + i, lane & 7)) = to_tf32(v);
+#endif
       }
       fence_proxy_async();
       mbar_arrive(a_ready);
@@ -258,10 +297,13 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 b1 = b1v[i], b2 = b1g[i];
-        v[4 * i] = __float_as_uint(to_tf32((__uint_as_float(v[4 * i]) + b1.x) * gelu_erf(__uint_as_float(g[4 * i]) + b2.x)));
-        v[4 * i + 1] = __float_as_uint(to_tf32((__uint_as_float(v[4 * i + 1]) + b1.y) * gelu_erf(__uint_as_float(g[4 * i + 1]) + b2.y)));
-        v[4 * i + 2] = __float_as_uint(to_tf32((__uint_as_float(v[4 * i + 2]) + b1.z) * gelu_erf(__uint_as_float(g[4 * i + 2]) + b2.z)));
-        v[4 * i + 3] = __float_as_uint(to_tf32((__uint_as_float(v[4 * i + 3]) + b1.w) * gelu_erf(__uint_as_float(g[4 * i + 3]) + b2.w)));
+        float o0, o1, o2, o3;
+        unpack2(geglu2(pack2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), pack2(b1.x, b1.y),
+                       pack2(__uint_as_float(g[4 * i]), __uint_as_float(g[4 * i + 1])), pack2(b2.x, b2.y)), o0, o1);
+        unpack2(geglu2(pack2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), pack2(b1.z, b1.w),
+                       pack2(__uint_as_float(g[4 * i + 2]), __uint_as_float(g[4 * i + 3])), pack2(b2.z, b2.w)), o2, o3);
+        v[4 * i] = __float_as_uint(to_tf32(o0)); v[4 * i + 1] = __float_as_uint(to_tf32(o1));
+        v[4 * i + 2] = __float_as_uint(to_tf32(o2)); v[4 * i + 3] = __float_as_uint(to_tf32(o3));
       }
       if (warp == 0) TR(3, 4 * p + 2);
       if (p >= 2) { mbar_wait(&h_free[b], ((p >> 1) - 1) & 1); tc_fence_after(); }   // MMA2 of pass p - 2 has read H[b]
@@ -291,18 +333,13 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
     }
     // ------------------------------- workers: out = OUT + b2 + x (coalesced through a per-warp staging tile) -------------------------------
     if (warp == 0) TR(0, 2);
-    mbar_wait(out_full, 0);
-    tc_fence_after();
-    if (warp == 0) TR(0, 3);
-    float* stg = sStg + warp * 1024;                           // the A image is dead: every MMA1 retired long ago
+    float* stg = sStg + warp * 1024;                           // the A image is dead: every MMA1 retired before the last GEGLU pass
     const int srow = lane >> 3, sj = lane & 7;
     {
       const int c = cq;                                        // one 32-column chunk per warp
-      uint32_t v[32];
-      tmem_ld32(trow + Cfg::COL_OUT + c * 32, v);
-      tmem_ld_wait();
       const int col0 = c * 32;
       const size_t gbase = ((size_t)pair * a.L + row0 + q * 32) * 128 + col0;
+      // the residual rows are fetched into the staging tile while the last MMA2s are still running
       float4 rr[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -316,6 +353,12 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
         *reinterpret_cast<float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2)) = rr[i];
       }
       __syncwarp();
+      mbar_wait(out_full, 0);
+      tc_fence_after();
+      if (warp == 0) TR(0, 3);
+      uint32_t v[32];
+      tmem_ld32(trow + Cfg::COL_OUT + c * 32, v);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 bb = *reinterpret_cast<const float4*>(a.b2 + col0 + 4 * j);
@@ -339,13 +382,15 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       }
     }
     if (a.out_img) {
-      // warp (q, cq) owns rows 32q.. of swizzle atom cq: its 4 KB staging tile sits exactly where that block lives in the image
+      // warp (q, cq) owns rows 32q.. of swizzle atom cq: its 4 KB staging tile sits exactly where that block lives in the image, so
+      // every warp ships its own block as soon as it is complete (no CTA-wide barrier, 16 x 4 KB bulk stores in flight)
       fence_proxy_async();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (tid == 0) {
-        bulk_s2g(a.out_img + (size_t)(pair * a.tiles + tile) * (128 * 128), sStg, 65536);
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(a.out_img + (size_t)(pair * a.tiles + tile) * (128 * 128) + warp * 1024, stg, 4096);
         bulk_commit_wait_read();
       }
+      __syncwarp();
     }
   }
   if (warp == 0) TR(0, 4);

@@ -174,6 +174,24 @@ std::vector<float> pack_linear(const std::vector<float>& W, int nout, int k, int
   return out;
 }
 
+// fp16 variant for kind::f16 B operands: per block of `nb` rows the whole K extent as k/64 swizzle atoms of nb x 128 B (64 halfs per row).
+// Returned as a float vector (two halfs per element) so that it travels in the same weight blob.
+std::vector<float> pack_linear_f16(const std::vector<float>& W, int nout, int k, int nb, const std::vector<int>* rowmap = nullptr) {
+  std::vector<float> out((size_t)nout * k / 2, 0.f);
+  for (int blk = 0; blk < nout / nb; ++blk) {
+    uint8_t* img = (uint8_t*)out.data() + (size_t)blk * nb * k * 2;
+    for (int n = 0; n < nb; ++n) {
+      const int srow = rowmap ? (*rowmap)[blk * nb + n] : blk * nb + n;
+      for (int kk = 0; kk < k; ++kk) {
+        const int atom = kk >> 6, piece = (kk & 63) >> 3, within = kk & 7;
+        __half h = __float2half_rn(W[(size_t)srow * k + kk]);
+        memcpy(img + (size_t)atom * nb * 128 + swz_off(n, piece) + within * 2, &h, 2);
+      }
+    }
+  }
+  return out;
+}
+
 struct FusionW {
   bool pe = false;
   const float *cpe_q_w = nullptr, *cpe_q_b = nullptr, *cpe_c_w = nullptr, *cpe_c_b = nullptr;
@@ -810,7 +828,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     std::vector<int> rowmap8(1024);     // fused FFN: pass p = [value rows 64p.., gate rows 512+64p..]
     for (int p = 0; p < 8; ++p)
       for (int n = 0; n < 128; ++n) rowmap8[p * 128 + n] = n < 64 ? p * 64 + n : 512 + p * 64 + (n - 64);
-    o.w1f = blob.push(pack_linear(W1, 1024, 128, 64, 128, &rowmap8));
+    o.w1f = blob.push(GMF_FFN_F16 ? pack_linear_f16(W1, 1024, 128, 128, &rowmap8) : pack_linear(W1, 1024, 128, 64, 128, &rowmap8));
     o.b1 = blob.push(next("net.0.bias"), 1024);
     const std::vector<float> W2 = vec(next("net.2.weight"), 128 * 512);
     o.w2 = blob.push(pack_linear(W2, 128, 512, 32, 128));

@@ -83,6 +83,35 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-fabsf(hx), e, hx + fabsf(hx));                                         // x/2 (1 + sign(x) erf) = hx + |hx| (1 - e)
 }
 
+// GEGLU on two hidden units at once with packed fp32x2 arithmetic: (v + bv) * gelu_erf(g + bg) for both lanes of each 64-bit operand.
+// Same formula as gelu_erf; the polynomial, the products and the bias adds issue as one FFMA2 / FMUL2 / FADD2 per pair, the two
+// reciprocals and exponentials stay scalar MUFU ops: ~12 issue slots per element instead of ~25 (the fused FFN kernel is bound by
+// exactly this arithmetic: 65 536 hidden activations per 128-token tile).
+__device__ __forceinline__ uint64_t geglu2(uint64_t v2, uint64_t bv2, uint64_t g2, uint64_t bg2) {
+  const uint64_t x2 = fadd2(g2, bg2);
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  const uint64_t ax2 = pack2(fabsf(x0), fabsf(x1));
+  const uint64_t d2 = ffma2(pack2(0.33267263f, 0.33267263f), ax2, pack2(1.0f, 1.0f));
+  float d0, d1, t0, t1;
+  unpack2(d2, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t2 = pack2(t0, t1);
+  uint64_t p2 = ffma2(pack2(0.7478556f, 0.7478556f), t2, pack2(-0.0958798f, -0.0958798f));
+  p2 = ffma2(p2, t2, pack2(0.3480242f, 0.3480242f));
+  float a0, a1;
+  unpack2(fmul2(fmul2(x2, pack2(-0.72134752f, -0.72134752f)), x2), a0, a1);
+  const uint64_t e2 = fmul2(fmul2(p2, t2), pack2(ex2_approx(a0), ex2_approx(a1)));     // 1 - erf(|x| / sqrt2)
+  const uint64_t hx2 = fmul2(x2, pack2(0.5f, 0.5f));
+  float h0, h1;
+  unpack2(hx2, h0, h1);
+  const uint64_t nah2 = pack2(-fabsf(h0), -fabsf(h1));
+  const uint64_t s2 = ffma2(nah2, pack2(-1.0f, -1.0f), hx2);                            // hx + |hx|
+  const uint64_t gelu = ffma2(nah2, e2, s2);
+  return fmul2(fadd2(v2, bv2), gelu);
+}
+
 template <int K, int NOUT, int PRO, int EPI>
 __global__ void __launch_bounds__(288, LinCfg<K, NOUT, PRO>::MIN_CTAS) linear_tc_kernel(const LinArgs a) {
   using Cfg = LinCfg<K, NOUT, PRO>;
