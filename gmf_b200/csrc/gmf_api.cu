@@ -535,7 +535,7 @@ int run_classify(const gmf_ctx* ctx, const float* feat, long long rows, float* n
     configured = true;
   }
   ProfScope ps(CAT_CLASSIFY, st);
-  classify_normalize_kernel<<<(unsigned)((rows + 63) / 64), 256, kClsSmem, st>>>(feat, rows, ctx->cls, normed, conf);
+  classify_normalize_kernel<<<(unsigned)std::min<long long>((rows + 63) / 64, 148 * 3 * 2), 256, kClsSmem, st>>>(feat, rows, ctx->cls, normed, conf);
   LAUNCHED();
   return 0;
 }

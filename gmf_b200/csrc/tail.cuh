@@ -187,9 +187,12 @@ __global__ void __launch_bounds__(256) classify_normalize_kernel(const float* __
   float* h2 = h1 + 64 * 33;         // [64][33]
   float* inv = h2 + 64 * 33;        // [64]
   const int tid = threadIdx.x;
+  // weights are staged (transposed) once per block; the block then walks over 64-row tiles (grid-stride), so the 20 KB of weight
+  // reads and the bank-conflicted transposing stores are paid once per block instead of once per 64 rows
   for (int i = tid; i < 32 * 128; i += 256) w1t[(i & 127) * 32 + (i >> 7)] = cw.w1[i];
   for (int i = tid; i < 32 * 32; i += 256) w2t[(i & 31) * 32 + (i >> 5)] = cw.w2[i];
-  const long long row0 = (long long)blockIdx.x * 64;
+  for (long long row0 = (long long)blockIdx.x * 64; row0 < rows; row0 += (long long)gridDim.x * 64) {
+  __syncthreads();                                           // the previous tile's readers are done with tile / h1 / h2 / inv
   for (int i = tid; i < 64 * 32; i += 256) {
     const int r = i >> 5, c4 = (i & 31) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(256) classify_normalize_kernel(const float* __
       const float4 v = *reinterpret_cast<const float4*>(tile + rr * 132 + c4);
       *reinterpret_cast<float4*>(normed + (row0 + rr) * 128 + c4) = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
     }
+  }
   }
 }
 constexpr int kClsSmem = (64 * 132 + 128 * 32 + 32 * 32 + 2 * 64 * 33 + 64) * 4;

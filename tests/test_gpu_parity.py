@@ -439,6 +439,32 @@ def test_c_abi_error_paths():
         Engine(num_layers=1, k=64)
 
 
+def test_c_abi_error_paths_of_the_newer_entry_points():
+    """Return codes (never exceptions / crashes) for bad arguments of the DGR head, the matcher and the feature-compat entry points."""
+    import ctypes as C
+    from gmf_b200 import _lib
+    from gmf_b200.dgr_head import DgrHeadEngine
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.gmf_dgr_head_create(C.byref(h), 0, 128, 128, 64, 0) == -1 and b"gmf_fusion_layer" in lib.gmf_last_error()
+    assert lib.gmf_dgr_head_create(C.byref(h), 99, 256, 128, 128, 1) == -1
+    eng = DgrHeadEngine(0, pe=True)
+    x = torch.zeros(4, 256, device="cuda")
+    with pytest.raises(_lib.GmfError, match="weights not loaded"):
+        eng.forward(x, torch.zeros(8, 128, device="cuda"))
+    assert lib.gmf_dgr_head_load_weights(eng.h, x.cpu().numpy().ctypes.data_as(C.c_void_p), 7) == -1
+    e = make_engine(dict(O.DEFAULT_CFG, num_layers=1))
+    d = torch.zeros(1, 8, 32, device="cuda")
+    k = torch.zeros(1, 8, 3, device="cuda")
+    out = torch.zeros(1024, device="cuda")
+    args = [e.h, d.data_ptr(), d.data_ptr(), k.data_ptr(), k.data_ptr(), 1, 8, 8, 32, 0] + [out.data_ptr()] * 6
+    assert lib.gmf_build_correspondences(*args, None, 0, None) == -3                       # no workspace
+    assert lib.gmf_build_correspondences(*(args[:8] + [0, 0] + args[10:]), out.data_ptr(), 1 << 20, None) == -1   # D = 0
+    assert lib.gmf_match_workspace_bytes(0, 8, 8) == 0
+    with pytest.raises(_lib.GmfError, match="weights not loaded"):
+        e.feature_compat(torch.zeros(1, 16, 128, device="cuda"))
+
+
 def test_host_entry_async_pipelined_calls_match_sync_calls():
     """gmf_pointdsc_forward_host_async: consecutive calls with different inputs (double-buffered staging, uploads overlapping the
     previous call's kernels) give the same results as synchronous calls; a shape change in between is handled."""

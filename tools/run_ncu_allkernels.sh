@@ -10,7 +10,9 @@ rows = [r for r in csv.reader(open('gpurun_out/allkernels.csv')) if len(r) > 8]
 hdr = rows[0]; ki = hdr.index('Kernel Name'); mi = hdr.index('Metric Name'); vi = hdr.index('Metric Value'); ii = hdr.index('ID')
 per = collections.OrderedDict()
 for r in rows[1:]:
-    per.setdefault(r[ii], {'k': r[ki].split('(')[0][:48]})[r[mi]] = float(r[vi].replace(',', ''))
+    try: val = float(r[vi].replace(',', ''))
+    except ValueError: val = 0.0
+    per.setdefault(r[ii], {'k': r[ki].split('(')[0][:48]})[r[mi]] = val
 agg = collections.OrderedDict()
 for d in per.values():
     a = agg.setdefault(d['k'], collections.Counter()); a['n'] += 1
