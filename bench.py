@@ -306,7 +306,7 @@ def main():
         ws_gb = eng.workspace(a.pairs, a.corr, a.tokens)[1] / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, a.min_warmup),
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16 attention operands + tf32 linear layers, fp32 accumulate/softmax/classifier", "data": "synthetic",
+                "dtype": "bf16 attention operands + tf32/fp16 linear layers, fp32 accumulate/softmax/classifier", "data": "synthetic",
                 "config": {"workload": workload_name(a), "parallelism": f"pair-sharded replicas x{world}, no collective on the data path",
                            "cache": f"per-step inputs ({sum(t.numel() * 4 for t in host) / 1e6:.0f} MB) + workspace ({ws_gb:.1f} GB) exceed the 126 MB L2",
                            "max_translation_error_vs_gt_mm": te_mm},
