@@ -15,6 +15,9 @@ namespace gmf {
 constexpr int kNnTile = 128, kNnKb = 32, kNnLd = kNnTile + 4;
 
 // grid (row tiles, column chunks, pairs).  A [pairs][Na][D], B [pairs][Nb][D]; best [pairs][Na] must be preset to all-ones.
+// FAST: D <= 32 and D % 4 == 0 (FCGF descriptors): the A tile is loaded once, the next B tile travels through registers (four float4
+// per thread, conflict-free transposing stores) while the current one is multiplied.
+template <bool FAST>
 __global__ void __launch_bounds__(256) nn_argmin_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int Na, int Nb, int D,
                                                         int tiles_per_chunk, unsigned long long* __restrict__ best) {
   __shared__ __align__(16) float As[kNnKb][kNnLd];
@@ -43,18 +46,47 @@ __global__ void __launch_bounds__(256) nn_argmin_kernel(const float* __restrict_
     }
   };
 
+  // FAST path staging: element e = tid + 256 i -> row e & 127, k-quad e >> 7
+  auto fetch = [&](const float* P, int n, int r0, float4 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i, r = e & 127, k4 = e >> 7;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < n && k4 * 4 < D) v[i] = *reinterpret_cast<const float4*>(P + (size_t)(r0 + r) * D + k4 * 4);
+    }
+  };
+  auto stash = [&](float (*S)[kNnLd], const float4 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i, r = e & 127, k4 = e >> 7;
+      S[k4 * 4][r] = v[i].x; S[k4 * 4 + 1][r] = v[i].y; S[k4 * 4 + 2][r] = v[i].z; S[k4 * 4 + 3][r] = v[i].w;
+    }
+  };
+  float4 nxt[4];
+  if (FAST) {
+    float4 av4[4];
+    fetch(Ap, Na, row0, av4);
+    stash(As, av4);
+    if (ct0 < ct1) fetch(Bp, Nb, ct0 * kNnTile, nxt);
+  }
+
   for (int ct = ct0; ct < ct1; ++ct) {
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = 0; kb < (FAST ? 1 : nkb); ++kb) {
       __syncthreads();
-      if (nkb > 1 || ct == ct0) load_tile(As, Ap, Na, row0, kb * kNnKb);
-      load_tile(Bs, Bp, Nb, ct * kNnTile, kb * kNnKb);
+      if (FAST) {
+        stash(Bs, nxt);
+      } else {
+        if (nkb > 1 || ct == ct0) load_tile(As, Ap, Na, row0, kb * kNnKb);
+        load_tile(Bs, Bp, Nb, ct * kNnTile, kb * kNnKb);
+      }
       __syncthreads();
-      const int kcount = min(kNnKb, D - kb * kNnKb);       // D = 33 (FPFH): the second block is one step, not 32
+      if (FAST && ct + 1 < ct1) fetch(Bp, Nb, (ct + 1) * kNnTile, nxt);      // in flight during the FMAs below
+      const int kcount = FAST ? ((D + 3) & ~3) : min(kNnKb, D - kb * kNnKb);   // D = 33 (FPFH): the second block is one step, not 32
 #pragma unroll 8
       for (int k = 0; k < kcount; ++k) {
         const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]), a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);

@@ -26,7 +26,8 @@ int gmf_build_correspondences(gmf_ctx* ctx, const float* src_desc, const float* 
     int chunks = std::max(1, std::min(ctl, cdiv(2 * 148, rt * B)));
     const int per = cdiv(ctl, chunks);
     chunks = cdiv(ctl, per);
-    nn_argmin_kernel<<<dim3(rt, chunks, B), 256, 0, st>>>(A, Bm, Na, Nb, D, per, best);
+    if (D <= 32 && (D & 3) == 0 && (((uintptr_t)A | (uintptr_t)Bm) & 15) == 0) nn_argmin_kernel<true><<<dim3(rt, chunks, B), 256, 0, st>>>(A, Bm, Na, Nb, D, per, best);
+    else nn_argmin_kernel<false><<<dim3(rt, chunks, B), 256, 0, st>>>(A, Bm, Na, Nb, D, per, best);
     LAUNCHED();
     return 0;
   };
