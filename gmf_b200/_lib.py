@@ -85,7 +85,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.gmf_feature_compat_workspace_bytes.argtypes = [i, i]
     lib.gmf_feature_compat.argtypes = [vp, vp, i, i, vp, vp, sz, vp]
     lib.gmf_match_workspace_bytes.restype = C.c_size_t
-    lib.gmf_match_workspace_bytes.argtypes = [i, i, i]
+    lib.gmf_match_workspace_bytes.argtypes = [i, i, i, i]
     lib.gmf_build_correspondences.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     _lib = lib
     return lib

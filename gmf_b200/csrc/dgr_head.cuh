@@ -103,7 +103,27 @@ __global__ void __launch_bounds__(256) knn_operand_kernel(const float* __restric
   *reinterpret_cast<float4*>((uint8_t*)(base + (size_t)(8 + ch) * 4096) + off) = a_side ? lo : hi;
 }
 
-enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4, DE_COMPAT = 5 };
+// Same split for short descriptor rows of any width D (FCGF 32, FPFH 33): kd = ceil(D / 32) chunks per segment, K = 96 kd.
+__global__ void __launch_bounds__(256) desc_operand_kernel(const float* __restrict__ x, int D, int kd, int a_side, int nrows, int tiles,
+                                                           float* __restrict__ img) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp, pair = blockIdx.y;
+  if (r >= tiles * 128) return;
+  const int tile = r >> 7, rr = r & 127;
+  float* base = img + ((size_t)pair * tiles + tile) * ((size_t)3 * kd * 4096);
+  for (int j = 0; j < kd; ++j) {
+    const int c = j * 32 + lane;
+    float v = 0.f;
+    if (r < nrows && c < D) v = x[((size_t)pair * nrows + r) * D + c];
+    const float hi = to_tf32(v), lo = to_tf32(v - hi);
+    const uint32_t off = swz_off(rr, lane >> 2) + (lane & 3) * 4;
+    *reinterpret_cast<float*>((uint8_t*)(base + (size_t)j * 4096) + off) = hi;
+    *reinterpret_cast<float*>((uint8_t*)(base + (size_t)(kd + j) * 4096) + off) = a_side ? hi : lo;
+    *reinterpret_cast<float*>((uint8_t*)(base + (size_t)(2 * kd + j) * 4096) + off) = a_side ? lo : hi;
+  }
+}
+
+enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4, DE_COMPAT = 5, DE_ARGMIN = 6 };
 
 struct ImgGemmArgs {
   const float* a_img;      // [tiles][K/32][128 x 32] tf32 chunks (rows_to_img_kernel / DE_GEGLU epilogue)
@@ -121,6 +141,7 @@ struct ImgGemmArgs {
   size_t a_pair_stride, w_pair_stride, out_pair_stride;
   int ncols;
   float scale;             // DE_COMPAT: 1 / sigma^2
+  unsigned long long* best;   // DE_ARGMIN: [pairs][L] running (distance bits << 32 | column) minima, preset to all-ones
 };
 
 template <int NB, int EPI>
@@ -202,11 +223,28 @@ __global__ void __launch_bounds__(192) img_gemm_kernel(const ImgGemmArgs a) {
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    unsigned long long amin = ~0ull;                     // DE_ARGMIN: this row's best key / largest dot product within this column block
+    float atop = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
       tmem_ld32(trow + c * 32, v);
-      if (EPI == DE_GEGLU) {
+      if (EPI == DE_ARGMIN) {
+        tmem_ld_wait();
+        // descriptor-space nearest neighbour (datasets/ThreeDMatch.py:384-385): distance = sqrt(2 - 2 dot + 1e-6) is monotone in the dot
+        // product and the columns are visited in increasing order, so the exact fp32 expression is evaluated only for a new maximum
+        const int col0 = cb * 128 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float dp = __uint_as_float(v[i]);
+          if (col0 + i < a.ncols && dp > atop) {
+            atop = dp;
+            const float d = __fsqrt_rn(__fadd_rn(__fsub_rn(2.0f, __fmul_rn(2.0f, dp)), 1e-6f));
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(col0 + i);
+            amin = key < amin ? key : amin;
+          }
+        }
+      } else if (EPI == DE_GEGLU) {
         uint32_t gt[32];
         tmem_ld32(trow + 128 + c * 32, gt);
         tmem_ld_wait();
@@ -328,6 +366,7 @@ __global__ void __launch_bounds__(192) img_gemm_kernel(const ImgGemmArgs a) {
         }
       }
     }
+    if (EPI == DE_ARGMIN && valid) atomicMin(&a.best[(size_t)blockIdx.z * a.L + row0 + r], amin);
   }
   tc_fence_before();
   __syncthreads();

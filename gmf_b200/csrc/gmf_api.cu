@@ -220,6 +220,8 @@ struct gmf_ctx {
   int chunk_pairs = 64;
   int pcn_qkv = 1;          // PointCN + QKV projection chained in one kernel
   int sc_fuse_fc = 1;       // fc_message.0/.3 fused into the SC attention kernel's tail
+  int match_impl = 0;       // 0 = FP32 register-blocked matcher; 1 = tensor pipe (error-compensated tf32, argmin in the GEMM epilogue): correct but
+                            // slower at K = 96 (6.3 vs 3.4 ms for 64 pairs x 5000^2): one 128 x 128 block per CTA is all fixed latency
   int knn_impl = 1;         // 1 = seed kNN distances on the tensor pipe (error-compensated tf32, K = 384), 0 = FP32 register-blocked SGEMM
   int ffn_impl = 3;         // 3 = fused GEGLU FFN kernel + fused fc_message.6 tail, 2 = fused FFN, 1 = two linear kernels
   int fus_impl = 3;         // 3 = fusion attention with fused to_out + residual, 2 = separate to_out kernel
@@ -751,6 +753,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   if (const char* e = getenv("GMF_FUS_IMPL")) c->fus_impl = atoi(e);
   if (const char* e = getenv("GMF_FFN_IMPL")) c->ffn_impl = atoi(e);
   if (const char* e = getenv("GMF_KNN_IMPL")) c->knn_impl = atoi(e);
+  if (const char* e = getenv("GMF_MATCH_IMPL")) c->match_impl = atoi(e);
   if (const char* e = getenv("GMF_SC_FUSE_FC")) c->sc_fuse_fc = atoi(e);
   if (const char* e = getenv("GMF_PCN_QKV")) c->pcn_qkv = atoi(e);
   if (const char* e = getenv("GMF_OVERLAP")) c->overlap = atoi(e);

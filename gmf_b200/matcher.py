@@ -33,7 +33,7 @@ def build_correspondences(engine, src_desc: torch.Tensor, tgt_desc: torch.Tensor
     src_sel = torch.empty(B, Ns, 3, device=dev)
     tgt_sel = torch.empty(B, Ns, 3, device=dev)
     corr_pos = torch.empty(B, Ns, 6, device=dev)
-    ws_bytes = int(lib.gmf_match_workspace_bytes(B, Ns, Nt))
+    ws_bytes = int(lib.gmf_match_workspace_bytes(B, Ns, Nt, D))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(lib.gmf_build_correspondences(engine.h, src_desc.data_ptr(), tgt_desc.data_ptr(), src_keypts.data_ptr(), tgt_keypts.data_ptr(),

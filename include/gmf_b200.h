@@ -156,7 +156,7 @@ int gmf_feature_compat(gmf_ctx* ctx, const float* feat, int B, int N, float* M, 
  * src_desc [B,Ns,D], tgt_desc [B,Nt,D] (unit-norm descriptors), src_keypts [B,Ns,3], tgt_keypts [B,Nt,3]  ->
  * source_idx [B,Ns] int32, corr [B,Ns,2] int32, n_corr [B] int32, src_sel / tgt_sel [B,Ns,3], corr_pos [B,Ns,6]; rows at and past
  * n_corr[b] are zero (corr: -1).  The Ns x Nt distance matrix is never materialised.  All pointers device. */
-size_t gmf_match_workspace_bytes(int B, int Ns, int Nt);
+size_t gmf_match_workspace_bytes(int B, int Ns, int Nt, int D);
 int gmf_build_correspondences(gmf_ctx* ctx, const float* src_desc, const float* tgt_desc, const float* src_keypts, const float* tgt_keypts,
                               int B, int Ns, int Nt, int D, int use_mutual, int32_t* source_idx, int32_t* corr, int32_t* n_corr,
                               float* src_sel, float* tgt_sel, float* corr_pos, void* workspace, size_t workspace_bytes, void* stream);

@@ -460,7 +460,7 @@ def test_c_abi_error_paths_of_the_newer_entry_points():
     args = [e.h, d.data_ptr(), d.data_ptr(), k.data_ptr(), k.data_ptr(), 1, 8, 8, 32, 0] + [out.data_ptr()] * 6
     assert lib.gmf_build_correspondences(*args, None, 0, None) == -3                       # no workspace
     assert lib.gmf_build_correspondences(*(args[:8] + [0, 0] + args[10:]), out.data_ptr(), 1 << 20, None) == -1   # D = 0
-    assert lib.gmf_match_workspace_bytes(0, 8, 8) == 0
+    assert lib.gmf_match_workspace_bytes(0, 8, 8, 32) == 0
     with pytest.raises(_lib.GmfError, match="weights not loaded"):
         e.feature_compat(torch.zeros(1, 16, 128, device="cuda"))
 

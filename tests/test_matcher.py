@@ -79,6 +79,19 @@ def test_cuda_matcher_matches_oracle_sizes(ns, nt, d, mutual):
 
 
 @pytest.mark.gpu
+def test_cuda_matcher_tensor_pipe_variant_matches_oracle():
+    """GMF_MATCH_IMPL=1: the same matcher as an error-compensated tf32 GEMM with the argmin in its epilogue (kept as an alternative path)."""
+    os.environ["GMF_MATCH_IMPL"] = "1"
+    try:
+        eng = _engine()
+    finally:
+        del os.environ["GMF_MATCH_IMPL"]
+    for ns, nt, d, mutual in [(700, 650, 32, False), (900, 1000, 33, True), (129, 300, 64, True)]:
+        s, t, sk, tk = synth_descriptors(ns, nt, d, seed=ns)
+        _check(_run(eng, s, t, sk, tk, mutual), oracle_build(s, t, sk, tk, mutual), sk, tk, mutual)
+
+
+@pytest.mark.gpu
 def test_cuda_matcher_exact_ties_take_first_index_and_batches_are_independent():
     """Duplicate target rows give exactly equal distances: np.argmin keeps the first index; batched call == per-pair calls."""
     s, t, sk, tk = synth_descriptors(400, 300, 32, seed=7)
