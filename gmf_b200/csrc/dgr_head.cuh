@@ -146,7 +146,10 @@ struct ImgGemmArgs {
 
 template <int NB, int EPI>
 struct IgCfg {
-  static constexpr int NSTG = 4;
+  // many small output blocks (seed kNN distances, feature compat, matcher): two stages only, so that two CTAs share an SM and one's
+  // epilogue overlaps the other's loads and MMAs; the GEMMs of the DGR head (few CTAs) keep a 4-deep ring
+  static constexpr bool SMALL = (EPI == DE_DIST || EPI == DE_COMPAT || EPI == DE_ARGMIN);
+  static constexpr int NSTG = SMALL ? 2 : 4;
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = NB * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
@@ -157,7 +160,7 @@ struct IgCfg {
 // grid (row tiles, column blocks); 6 warps: 0 = bulk-copy producer, 1 = MMA issuer (+ TMEM owner), 2..5 = epilogue (one TMEM lane
 // quadrant each, one thread per accumulator row)
 template <int NB, int EPI>
-__global__ void __launch_bounds__(192) img_gemm_kernel(const ImgGemmArgs a) {
+__global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_kernel(const ImgGemmArgs a) {
   using Cfg = IgCfg<NB, EPI>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
