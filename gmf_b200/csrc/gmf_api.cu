@@ -1239,6 +1239,16 @@ int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* Bp, const 
   return 0;
 }
 
+int gmf_weighted_procrustes(gmf_ctx* ctx, const float* X, const float* Y, const float* w, int B, int N, float eps, float* R, float* t, void* stream) {
+  if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
+  if (!X || !Y || !w || !R || !t) return fail(GMF_ERR_INVALID, "gmf_weighted_procrustes: NULL argument");
+  if (B < 1 || N < 1) return fail(GMF_ERR_INVALID, "need B >= 1, N >= 1");
+  CU(cudaSetDevice(ctx->device));
+  weighted_procrustes_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(X, Y, w, N, eps, R, t);
+  LAUNCHED();
+  return 0;
+}
+
 int gmf_debug_linear(gmf_ctx* ctx, const float* x, const float* w_host, const float* bias_host, const float* residual, int rows, int k,
                      int nout, int relu, float* out, void* stream) {
   if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");

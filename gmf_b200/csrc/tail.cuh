@@ -855,6 +855,57 @@ __global__ void __launch_bounds__(1024) select_refine_kernel(const float4* __res
 }
 
 // standalone batched weighted Kabsch: C-ABI mirror of models/common.py:10-50 (one warp per problem)
+// ------------------------------------------------------------------------------------------------
+// DGR weighted Procrustes (GMF_DeepGlobalRegistration_fcgf/core/registration.py:91-113): one pose per pair from ALL its correspondences.
+//   w_norm = w / (sum |w| + eps); mu_x = sum w_norm x; mu_y = sum w_norm y; Sxy = (Y - mu_y)^T diag(w_norm) (X - mu_x)
+//   R = U diag(1, 1, sign) V^T  (SVD in double precision in the reference, on the host),  t = mu_y - R mu_x
+// One CTA per pair, two sweeps over the points (means, then the 3 x 3 moment), block reductions; the 3 x 3 algebra in fp64 on one lane.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) weighted_procrustes_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ W,
+                                                                  int N, float eps, float* __restrict__ R_out, float* __restrict__ t_out) {
+  __shared__ float red[8][10];
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* x = X + (size_t)pair * N * 3;
+  const float* y = Y + (size_t)pair * N * 3;
+  const float* w = W + (size_t)pair * N;
+  auto block_sum = [&](float (&v)[9], int n, float* out) {       // all threads get the n sums
+    for (int c = 0; c < n; ++c) v[c] = warp_sum(v[c]);
+    __syncthreads();
+    if (lane == 0) for (int c = 0; c < n; ++c) red[warp][c] = v[c];
+    __syncthreads();
+    for (int c = 0; c < n; ++c) {
+      float s = 0.f;
+      for (int k = 0; k < 8; ++k) s += red[k][c];
+      out[c] = s;
+    }
+  };
+  float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tot[9];
+  for (int i = tid; i < N; i += 256) {
+    const float wi = w[i];
+    acc[0] += fabsf(wi);
+    for (int c = 0; c < 3; ++c) { acc[1 + c] += wi * x[i * 3 + c]; acc[4 + c] += wi * y[i * 3 + c]; }
+  }
+  block_sum(acc, 7, tot);
+  const float inv = 1.0f / (tot[0] + eps);
+  float mx[3], my[3];
+  for (int c = 0; c < 3; ++c) { mx[c] = tot[1 + c] * inv; my[c] = tot[4 + c] * inv; }
+  for (int q = 0; q < 9; ++q) acc[q] = 0.f;
+  for (int i = tid; i < N; i += 256) {
+    const float wn = w[i] * inv;
+    for (int p = 0; p < 3; ++p)
+      for (int q = 0; q < 3; ++q) acc[p * 3 + q] += wn * (x[i * 3 + p] - mx[p]) * (y[i * 3 + q] - my[q]);   // H = Sxy^T, as rigid_transform_3d builds it
+  }
+  block_sum(acc, 9, tot);
+  if (tid == 0) {
+    double H[9], R[9];
+    for (int q = 0; q < 9; ++q) H[q] = (double)tot[q];
+    kabsch_rotation(H, R);
+    for (int q = 0; q < 9; ++q) R_out[(size_t)pair * 9 + q] = (float)R[q];
+    for (int p = 0; p < 3; ++p)
+      t_out[(size_t)pair * 3 + p] = (float)((double)my[p] - (R[p * 3] * mx[0] + R[p * 3 + 1] * mx[1] + R[p * 3 + 2] * mx[2]));
+  }
+}
+
 __global__ void rigid_transform_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ W, int M, int k,
                                        float* __restrict__ out) {
   const int prob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;

@@ -124,6 +124,14 @@ class Engine:
         _lib.check(self.lib.gmf_feature_compat(self.h, _ptr(feat), B, N, _ptr(M), _ptr(ws), nb, self._stream()))
         return M
 
+    def weighted_procrustes(self, X, Y, w, eps=1e-6):
+        """DGR weighted Procrustes (core/registration.py:91-113): X, Y [B,N,3], w [B,N] -> R [B,3,3], t [B,3]."""
+        X, Y, w = _chk(X), _chk(Y), _chk(w)
+        B, N, _ = X.shape
+        R, t = torch.empty(B, 3, 3, device=X.device), torch.empty(B, 3, device=X.device)
+        _lib.check(self.lib.gmf_weighted_procrustes(self.h, _ptr(X), _ptr(Y), _ptr(w), B, N, float(eps), _ptr(R), _ptr(t), self._stream()))
+        return R, t
+
     def synchronize(self):
         _lib.check(self.lib.gmf_stream_synchronize(self.h, self._stream()))
 

@@ -122,6 +122,12 @@ int gmf_score_hypotheses(gmf_ctx* ctx, const float* seed_trans, const float* src
 /* rigid_transform_3d (models/common.py:10-50): A,B [M,k,3], weights [M,k] or NULL -> T [M,4,4]. */
 int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* B, const float* weights, int M, int k, float* T, void* stream);
 
+/* DGR's weighted Procrustes (GMF_DeepGlobalRegistration/GMF_DeepGlobalRegistration_fcgf/core/registration.py:91-113, called per pair
+ * from core/trainer.py:594-614 with a host-side double SVD): X, Y [B,N,3], w [B,N] -> R [B,3,3], t [B,3] with
+ * w_norm = w / (sum|w| + eps), R = U diag(1,1,sign) V^T of Sxy = (Y - mu_y)^T diag(w_norm) (X - mu_x), t = mu_y - R mu_x. */
+int gmf_weighted_procrustes(gmf_ctx* ctx, const float* X, const float* Y, const float* w, int B, int N, float eps, float* R, float* t,
+                            void* stream);
+
 /* ---- DGR bottleneck fusion head --------------------------------------------- */
 /* PerceiverIO(depth=0, dim=128, latent_dim=256, cross_heads=1, cross_dim_head=128, pe) of the DGR inlier network
  * (GMF_DeepGlobalRegistration_fcgf/model/perceiver_io.py:140-221; built at model/resunet_new.py:516-525, called from
