@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-backbone", action="store_true", help="skip the separate timing of the PyTorch image backbone")
     return ap.parse_args()
 
 
@@ -129,6 +130,37 @@ def measured_peaks():
             d = json.load(f)
         return d.get("bf16_tflops_sustained", 1391.3), d.get("hbm_gbs", 6548.2), "measured (MEASURED_PEAKS.json, sustained bf16)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def backbone_timing(dev, pairs, h=480, w=640, iters=3):
+    """The image backbone stays in PyTorch and is OUTSIDE the timed path (BASELINE.json north_star); it is timed here on the same batch
+    (2 images per pair) so that the whole pipeline can be budgeted: reference-equivalent fp32 eager, and channels_last + bf16 autocast."""
+    from gmf_b200.backbone import ImageEncoder
+    enc = ImageEncoder().to(dev).eval()
+    img = torch.rand(pairs, 3, h, w, device=dev)
+
+    def run(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn(); fn()                                       # p_image and q_image
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    ms_fp32 = run(lambda: enc.tokens(img))
+    enc_cl = enc.to(memory_format=torch.channels_last)
+    img_cl = img.contiguous(memory_format=torch.channels_last)
+
+    def bf16():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return enc_cl.tokens(img_cl)
+    ms_bf16 = run(bf16)
+    return {"note": "PyTorch ResNet-34 trunk (conv1..layer2), excluded from `value` / `e2e`; 2 x %d images %dx%d per step" % (pairs, h, w),
+            "fp32_eager_ms_per_step": ms_fp32, "channels_last_bf16_ms_per_step": ms_bf16}
 
 
 def make_inputs(a, rank):
@@ -298,6 +330,13 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"1 pair of the same workload (N={a.corr}, T={a.tokens}, {a.layers} layers), single timed pass, {msp / 1000:.1f} s"}
 
+    backbone = None
+    if rank == 0 and world == 1 and not a.no_backbone:
+        try:
+            backbone = backbone_timing(dev, a.pairs)
+        except RuntimeError as e:                                # e.g. out of memory on a smaller device: report, do not fail the bench
+            backbone = {"error": str(e)[:200]}
+
     # sanity on the last device result: poses must be finite and close to the synthetic ground truth
     tr = out["final_trans"].float().cpu()
     gt = pr["gt_trans"]
@@ -310,7 +349,7 @@ def main():
                 "config": {"workload": workload_name(a), "parallelism": f"pair-sharded replicas x{world}, no collective on the data path",
                            "cache": f"per-step inputs ({sum(t.numel() * 4 for t in host) / 1e6:.0f} MB) + workspace ({ws_gb:.1f} GB) exceed the 126 MB L2",
                            "max_translation_error_vs_gt_mm": te_mm},
-                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernel_profile": prof_table}
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "backbone": backbone, "kernel_profile": prof_table}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
