@@ -48,7 +48,13 @@ def parse():
 
 
 def workload_name(a):
-    return (f"cfg#2 GMF-PointDSC 3DMatch/FCGF shape: {a.corr} correspondences/pair, {a.pairs} pairs/GPU/step, "
+    if a.corr == 5000 and a.pairs == 64:
+        tag = "cfg#2 GMF-PointDSC 3DMatch/FCGF shape"
+    elif a.corr == 10000:
+        tag = "cfg#4 3DLoMatch low-overlap stress shape"
+    else:
+        tag = "GMF-PointDSC (non-headline shape)"
+    return (f"{tag}: {a.corr} correspondences/pair, {a.pairs} pairs/GPU/step, "
             f"{a.tokens} image tokens/fragment (480x640), {a.layers} layers, testing mode, random-init weights")
 
 
