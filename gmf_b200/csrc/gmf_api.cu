@@ -1239,6 +1239,15 @@ int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* Bp, const 
   return 0;
 }
 
+// host-only helper (no device needed): chunk sizes gmf_pointdsc_forward_host would use; returns the number of chunks
+int gmf_debug_plan_host_chunks(int B, int N, int cap, int sms, int* sizes, int max_sizes) {
+  if (B < 1 || N < 1 || sms < 1) return fail(GMF_ERR_INVALID, "gmf_debug_plan_host_chunks: bad argument");
+  const std::vector<int> cuts = plan_host_chunks(B, N, cap, sms);
+  const int n = (int)cuts.size() - 1;
+  for (int i = 0; i < n && i < max_sizes; ++i) sizes[i] = cuts[i + 1] - cuts[i];
+  return n;
+}
+
 int gmf_weighted_procrustes(gmf_ctx* ctx, const float* X, const float* Y, const float* w, int B, int N, float eps, float* R, float* t, void* stream) {
   if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
   if (!X || !Y || !w || !R || !t) return fail(GMF_ERR_INVALID, "gmf_weighted_procrustes: NULL argument");

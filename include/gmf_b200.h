@@ -179,6 +179,9 @@ int gmf_profile_enable(gmf_ctx* ctx, int enable);
 int gmf_profile_read(gmf_ctx* ctx, int category, double* total_ms, int64_t* launches);
 /* number of gmf kernels launched by this process since the last reset (bench.py's gpu_launches) */
 int64_t gmf_launch_count(int reset);
+/* host-only: the chunk sizes gmf_pointdsc_forward_host cuts a batch of B pairs into (first chunk small, then doubling, snapped to whole
+ * waves of attention CTAs on `sms` SMs, at most `cap` pairs each); writes up to max_sizes entries, returns the chunk count. */
+int gmf_debug_plan_host_chunks(int B, int N, int cap, int sms, int* sizes, int max_sizes);
 /* out[rows,nout] = act(x[rows,k] . W[nout,k]^T + bias) (+ residual) through the tcgen05 TF32 linear kernel.
  * W, bias are HOST pointers (packed on the fly); x/residual/out device.  (k,nout) in {(128,128),(128,64),(64,64),(64,128)}. */
 int gmf_debug_linear(gmf_ctx* ctx, const float* x, const float* w_host, const float* bias_host, const float* residual, int rows, int k,

@@ -134,3 +134,17 @@ def test_host_gather_world2_gloo():
     res = dict(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in ps]
     assert res[0] == res[1] == [float(i) for i in range(7)]
+
+
+def test_host_chunk_plan_properties(lib):
+    """plan_host_chunks (host entry point): chunks cover the batch exactly, respect the cap, start small and never shrink into a short tail."""
+    buf = (C.c_int * 256)()
+    for B, N, cap in [(64, 5000, 48), (32, 10000, 48), (256, 5000, 48), (9, 5000, 48), (5, 5000, 2), (1, 300, 48), (17, 1000, 8), (3000, 300, 48)]:
+        n = lib.gmf_debug_plan_host_chunks(B, N, cap, 148, buf, 256)
+        sizes = [buf[i] for i in range(min(n, 256))]
+        assert n >= 1 and sum(sizes) == B and all(1 <= s <= cap for s in sizes), (B, N, cap, sizes)
+        if B > 8 and n > 1:
+            assert sizes[0] <= max(1, B // 9) * 1.25 + 1                # small first chunk: its upload is the only exposed one
+            assert all(sizes[i + 1] <= 2.6 * sizes[i] + 1 for i in range(n - 2)), sizes   # uploads stay ahead of the kernels
+    assert lib.gmf_debug_plan_host_chunks(64, 5000, 48, 148, buf, 256) == 3 and [buf[i] for i in range(3)] == [7, 14, 43]
+    assert lib.gmf_debug_plan_host_chunks(0, 5000, 48, 148, buf, 256) < 0
