@@ -77,6 +77,32 @@ __global__ void __launch_bounds__(256) rows_to_img_kernel(const float* __restric
   }
 }
 
+// Combine the split-key partial attention results (sc_attn_v9_kernel<.., SPLIT>) and emit the A-operand image of the to_out GEMM:
+//   out = sum_s O_s 2^(ref_s - ref*) / sum_s l_s 2^(ref_s - ref*),  ref* = max_s ref_s.   One warp per query row (128 columns).
+__global__ void __launch_bounds__(256) attn_combine_img_kernel(const float* __restrict__ part_o, const float* __restrict__ part_l, int splits, int M,
+                                                               int tiles, float* __restrict__ img) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= tiles * 128) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < M) {
+    float rmax = -INFINITY;
+    for (int s = 0; s < splits; ++s) rmax = fmaxf(rmax, part_l[((size_t)s * M + r) * 2 + 1]);
+    float L = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float sc = exp2f(part_l[((size_t)s * M + r) * 2 + 1] - rmax);
+      L = fmaf(part_l[((size_t)s * M + r) * 2], sc, L);
+      const float4 o = *reinterpret_cast<const float4*>(part_o + ((size_t)s * M + r) * 128 + lane * 4);
+      acc.x = fmaf(o.x, sc, acc.x); acc.y = fmaf(o.y, sc, acc.y); acc.z = fmaf(o.z, sc, acc.z); acc.w = fmaf(o.w, sc, acc.w);
+    }
+    const float inv = 1.0f / L;
+    acc = to_tf32(make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv));
+  }
+  const int tile = r >> 7, rr = r & 127;
+  uint8_t* chunk = (uint8_t*)(img + ((size_t)tile * 4 + (lane >> 3)) * 4096);
+  *reinterpret_cast<float4*>(chunk + swz_off(rr, lane & 7)) = acc;
+}
+
 // Operands of the seed kNN distance GEMM (models/common.py:53-75 restricted to the seed rows) for the tensor pipe at fp32 accuracy:
 // x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  <a, b> ~ a_hi b_hi + a_hi b_lo + a_lo b_hi  (the dropped lo*lo term is 2^-22
 // relative), written as ONE K = 384 product:  A row = [a_hi | a_hi | a_lo],  B row = [b_hi | b_lo | b_hi].

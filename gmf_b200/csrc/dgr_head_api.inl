@@ -23,7 +23,7 @@ std::vector<Spec> dgr_spec(bool pe) {
 }
 
 struct DgrWork {
-  float *x0, *xq_img, *c_img, *o, *o_img, *x1, *ln_img, *g_img, *kpts;
+  float *x0, *xq_img, *c_img, *o, *o_img, *x1, *ln_img, *g_img, *kpts, *part_o, *part_l;
   __nv_bfloat16 *q_t, *k_t, *vt_t, *aq, *bd;
 };
 
@@ -49,6 +49,8 @@ size_t dgr_carve(DgrWork& w, uint8_t* base, int M, int T) {
   w.vt_t = (__nv_bfloat16*)take(kt * 128 * 128 * 2);
   w.aq = (__nv_bfloat16*)take(xt * 128 * 64 * 2);
   w.bd = (__nv_bfloat16*)take(xt * 128 * 64 * 2);
+  w.part_o = (float*)take(kt * (size_t)M * kDgrHead * 4);        // up to one split per context tile
+  w.part_l = (float*)take(kt * (size_t)M * 2 * 4);
   return off + 1024;
 }
 
@@ -210,12 +212,26 @@ int gmf_dgr_head_forward(gmf_dgr_head* h, const float* latents, const float* ima
     ScAttnArgs sa{};
     sa.q_t = w.q_t; sa.k_t = w.k_t; sa.vt_t = w.vt_t; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = w.o;
     sa.N = T; sa.tiles = kt; sa.Nq = M; sa.q_tiles = mt;
-    e = launch_sc_attn_v9<0, 2>(sa, 1, st);
+    // few query tiles: split the keys over enough CTAs to cover the SMs (flash-decoding style); the combine is folded into the
+    // kernel that builds the to_out GEMM's operand image
+    int splits = std::max(1, std::min(kt, 148 / mt));
+    const int per = cdiv(kt, splits);
+    splits = cdiv(kt, per);
+    if (splits > 1) {
+      sa.tiles_per_split = per; sa.part_o = w.part_o; sa.part_l = w.part_l;
+      e = launch_sc_attn_v9_split(sa, splits, st);
+    } else {
+      e = launch_sc_attn_v9<0, 2>(sa, 1, st);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "dgr attention launch");
+    if (splits > 1) {
+      attn_combine_img_kernel<<<mt * 16, 256, 0, st>>>(w.part_o, w.part_l, splits, M, mt, w.o_img);
+    } else {
+      rows_to_img_kernel<kDgrHead, false, false><<<mt * 16, 256, 0, st>>>(w.o, M, mt, nullptr, nullptr, nullptr, nullptr, nullptr, w.o_img);
+    }
+    LAUNCHED();
   }
-  rows_to_img_kernel<kDgrHead, false, false><<<mt * 16, 256, 0, st>>>(w.o, M, mt, nullptr, nullptr, nullptr, nullptr, nullptr, w.o_img);
-  LAUNCHED();
   {  // to_out + bias + residual
     ImgGemmArgs a{};
     a.a_img = w.o_img; a.w_packed = h->wo; a.K = kDgrHead; a.L = M; a.tiles = mt; a.bias = h->bo; a.residual = resid0; a.out = w.x1; a.ld = kDgrLatent;

@@ -111,7 +111,7 @@ __device__ __forceinline__ void sc9_sd_step(const Sc9Mma& m, int j0, uint32_t ph
   sc9_issue_sd<(T + 3) % 6>(m, j + 3, T + 3 < 6 ? ph : ph ^ 1u);
 }
 
-template <int POLY, int TPR>   // TPR softmax threads share a score row (each takes 32 / TPR columns of a tile): 8 TPR softmax warps
+template <int POLY, int TPR, bool SPLIT = false>   // TPR softmax threads share a score row (each takes 32 / TPR columns of a tile): 8 TPR softmax warps
 __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScAttnArgs a) {
   using Cfg = Sc9Cfg;
   constexpr int D = Cfg::D, BT = Cfg::BT, NS = Cfg::NS, NV = Cfg::NV;
@@ -143,9 +143,12 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
   uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int pair = blockIdx.y, qt = blockIdx.x;
-  const int nt = (a.N + BT - 1) / BT;                     // 32-key tiles
-  const int nw = (a.N + 63) / 64;                         // 64-key stages
+  const int qt = blockIdx.x;
+  const int split = SPLIT ? blockIdx.y : 0, pair = SPLIT ? 0 : blockIdx.y;
+  const int kt0 = SPLIT ? split * a.tiles_per_split : 0;  // first 128-key tile of this CTA
+  const int Nk = SPLIT ? min(a.N - kt0 * 128, a.tiles_per_split * 128) : a.N;
+  const int nt = (Nk + BT - 1) / BT;                      // 32-key tiles
+  const int nw = (Nk + 63) / 64;                          // 64-key stages
   const int Nq = a.Nq ? a.Nq : a.N, qtiles = a.Nq ? a.q_tiles : a.tiles;
 
   if (tid == 0) {
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
           if (wk >= NS) mbar_wait(&k_empty[st], ((wk / NS) - 1) & 1);
           uint8_t* dst = sK + st * Cfg::KSTAGE_BYTES;
           mbar_expect_tx_p(&k_full[st], Cfg::KSTAGE_BYTES, leader);
-          const size_t tix = (size_t)pair * a.tiles + (j >> 1);
+          const size_t tix = (size_t)pair * a.tiles + kt0 + (j >> 1);
           const int h = j & 1;
           const uint8_t* ksrc = (const uint8_t*)(a.k_t + tix * (128 * D)) + h * 8192;
           bulk_g2s_p(dst, ksrc, 8192, &k_full[st], leader);
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
           const int sv_ = wv % NV, j = wv;
           if (wv >= NV) mbar_wait(&v_empty[sv_], ((wv / NV) - 1) & 1);
           mbar_expect_tx_p(&v_full[sv_], Cfg::V_BYTES, leader);
-          const size_t tix = (size_t)pair * a.tiles + (j >> 1);
+          const size_t tix = (size_t)pair * a.tiles + kt0 + (j >> 1);
           bulk_g2s_p(sV + sv_ * Cfg::V_BYTES, (const uint8_t*)(a.vt_t + tix * (128 * D)) + (j & 1) * Cfg::V_BYTES, Cfg::V_BYTES, &v_full[sv_], leader);
           ++wv;
         }
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
         const uint32_t tbuf = tlane + (uint32_t)b * 96u;
         mbar_wait(&s_full[b], (j / 3) & 1);
         tc_fence_after();
-        const int nvalid = a.N - j * BT;
+        const int nvalid = Nk - j * BT;
         uint32_t us[HC], ua[HC], ub[HC], pk[HC / 2];
         if constexpr (TPR == 1) { tmem_ld32(tbuf, us); tmem_ld32(tbuf + 32, ua); tmem_ld32(tbuf + 64, ub); }
         else { tmem_ld16(tbuf + h * 16, us); tmem_ld16(tbuf + 32 + h * 16, ua); tmem_ld16(tbuf + 64 + h * 16, ub); }
@@ -363,13 +366,14 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
     asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
 #pragma unroll
     for (int o = 1; o < NPART; ++o) l_sum += sX[512 + ((part + o) % NPART) * 128 + r];
-    const float inv = 1.f / l_sum;
+    const float inv = SPLIT ? 1.f : 1.f / l_sum;
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int gq = qt * 128 + r;
     constexpr int OC = D / NPART;                             // output columns per thread
     if (!fused) {
-      float* op = a.out + ((size_t)pair * Nq + gq) * D + part * OC;
+      float* op = SPLIT ? a.part_o + ((size_t)split * Nq + gq) * D + part * OC : a.out + ((size_t)pair * Nq + gq) * D + part * OC;
+      if (SPLIT && part == 0 && gq < Nq) { a.part_l[((size_t)split * Nq + gq) * 2] = l_sum; a.part_l[((size_t)split * Nq + gq) * 2 + 1] = ref; }
 #pragma unroll
       for (int c = 0; c < OC / 32; ++c) {
         uint32_t u[32];
@@ -438,6 +442,19 @@ inline cudaError_t launch_sc_attn_v9(const ScAttnArgs& a, int pairs, cudaStream_
     configured = true;
   }
   kern<<<dim3(a.Nq ? a.q_tiles : a.tiles, pairs), 256 * TPR + 96, Sc9Cfg::SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+
+// split-key launch for ONE pair: grid (query tiles, splits)
+inline cudaError_t launch_sc_attn_v9_split(const ScAttnArgs& a, int splits, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = sc_attn_v9_kernel<0, 2, true>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Sc9Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<dim3(a.Nq ? a.q_tiles : a.tiles, splits), 256 * 2 + 96, Sc9Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 

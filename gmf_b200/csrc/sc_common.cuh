@@ -23,6 +23,12 @@ struct ScAttnArgs {
   float* m2_out;
   // cross-attention use (DGR head): Nq != 0 gives the query side its own length / tile count (q_t, aq_t, out are indexed with it)
   int Nq, q_tiles;
+  // split-key mode (SPLIT instantiation, one pair): CTA (q tile, split) takes key tiles [split * tiles_per_split, ...) and writes the
+  // UNnormalised partial output part_o [splits][Nq][128] plus (row sum, softmax reference in log2 units) part_l [splits][Nq][2]; the
+  // consumer combines the splits (flash-decoding style)
+  int tiles_per_split;
+  float* part_o;
+  float* part_l;
 };
 
 
