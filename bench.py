@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-backbone", action="store_true", help="skip the separate timing of the PyTorch image backbone")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg#3 strong-scaling leg (256 KITTI-shaped pairs split over the ranks)")
+    ap.add_argument("--cfg3-pairs", type=int, default=256)
     return ap.parse_args()
 
 
@@ -56,6 +58,49 @@ def workload_name(a):
         tag = "GMF-PointDSC (non-headline shape)"
     return (f"{tag}: {a.corr} correspondences/pair, {a.pairs} pairs/GPU/step, "
             f"{a.tokens} image tokens/fragment (480x640), {a.layers} layers, testing mode, random-init weights")
+
+
+def config_dict(a, world):
+    """Identical for both arms (`--impl gmf_b200` / `--impl reference`) so that the driver sees the same config."""
+    mb = a.pairs * (a.corr * 12 + 2 * a.tokens * 128) * 4 / 1e6
+    return {"workload": workload_name(a), "parallelism": f"pair-sharded replicas x{world}, no collective on the data path",
+            "cache": f"per-step inputs ({mb:.0f} MB per GPU) + multi-GB workspace exceed the 126 MB L2; no explicit flush"}
+
+
+def per_kernel_roofline(prof, a, steps, peak_tf, hbm):
+    """Algorithmic work of every kernel category over `steps` steps (SURVEY.md §8d formulas, stated per launch in DESIGN.md §5) divided by
+    its CUDA-event time.  Tensor-bound categories are rated against the measured sustained bf16 peak, the others against the measured
+    HBM copy bandwidth."""
+    n, t, L, B, C = a.corr, a.tokens, a.layers, a.pairs, 128
+    S = int(n * 0.1)
+    k = 40
+    per_step = {   # (bound, algorithmic FLOPs or bytes per pair per step)
+        "attn_sc": ("tensor", L * (4.0 * n * n * C + 2.0 * n * (C * 64 + 64 * 64))),
+        "attn_fusion": ("tensor", (4.0 * t * t * 64 + 2.0 * t * 64 * C) + L * (4.0 * n * t * 64 + 2.0 * n * 64 * C)),
+        "ffn_geglu": ("tensor", (2.0 * t * C * 1024 + 2.0 * t * 512 * C) + L * (2.0 * n * C * 1024 + 2.0 * n * 512 * C + 2.0 * n * 64 * C)),
+        "pcn_qkv": ("hbm", L * (4.0 * C * n + 4.0 * C * n + 3 * 2.0 * C * n)),                    # feat in; feat1 fp32 + Q,K,V^T bf16 out
+        "fusion_q_proj": ("hbm", (4.0 * C * t + 2.0 * 64 * t) + L * (4.0 * C * n + 4.0 * C * n + 2.0 * 64 * n)),   # x in; (x + dwconv) fp32 + Q bf16 out
+        "fusion_kv_proj": ("hbm", (1 + L) * (4.0 * C * t + 2 * 2.0 * 64 * t)),                    # context in; K, V^T bf16 out
+        "prep_layer0": ("hbm", 24.0 * n * 2 + 24.0 * n + 4.0 * C * n + 2 * 2.0 * 64 * n + 32.0 * n),
+        "classify": ("hbm", 4.0 * C * n + 4.0 * C * n + 4.0 * n),
+        "pick_seeds": ("hbm", 16.0 * n + 4.0 * S),
+        "seed_knn": ("hbm", 4.0 * C * n + 4.0 * S + 4.0 * S * k),
+        "spectral_kabsch": ("hbm", S * k * (4.0 * C + 24) + 4.0 * S * k + 64.0 * S),
+        "score_refine": ("hbm", 24.0 * n + 64.0 * S + 4.0 * n + 64 + 20 * 24.0 * n),
+    }
+    out = {}
+    for name, (ms, launches) in prof.items():
+        if name not in per_step or launches == 0:
+            continue
+        bound, work = per_step[name]
+        total = work * B * steps
+        rate = total / (ms / 1e3)
+        if bound == "tensor":
+            out[name] = {"bound": "tensor", "achieved": rate / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": rate / 1e12 / peak_tf}
+        else:
+            out[name] = {"bound": "hbm", "achieved": rate / 1e9, "peak": hbm, "unit": "GB/s", "frac": rate / 1e9 / hbm}
+        out[name].update({"ms_per_step": ms / steps, "launches_per_step": launches / steps})
+    return out
 
 
 def flops_per_pair(n, t, layers):
@@ -184,37 +229,110 @@ def synth_weights(layers):
 
 
 def cpu_reference_pairs_per_s(a, steps, warmup, sample_pairs=1):
-    """The reference algorithm on the host cores (oracle port of the reference's PyTorch CPU path), bs=1 loop."""
+    """The reference's own CPU implementation of the path on the host cores, bs=1 loop (the reference asserts bs == 1 in testing mode):
+    the UNMODIFIED reference module from oracle/_ref (or /root/reference) with the image backbone bypassed (it is outside the timed
+    path) when that copy is present -> kind "reference"; otherwise the oracle port of it -> kind "port"."""
     from oracle import pointdsc_oracle as O
+    from oracle import ref_shim
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synth_weights(a.layers)
     cfg = dict(O.DEFAULT_CFG, num_layers=a.layers)
     a1 = argparse.Namespace(**{**vars(a), "pairs": sample_pairs})
     pr, p_tok, q_tok = make_inputs(a1, 0)
+    if ref_shim.available():
+        model = ref_shim.build_reference_hot_path(sd, cfg)
+        kind, what = "reference", ref_shim.source()
+        run = lambda: ref_shim.forward_tokens(model, pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok)   # noqa: E731
+    else:
+        kind, what = "port", "oracle/pointdsc_oracle.py"
+        run = lambda: O.forward_testing(sd, cfg, pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok)      # noqa: E731
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        O.forward_testing(sd, cfg, pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok)
+        run()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     tot = sum(times)
-    return sample_pairs * len(times) / tot, cores, 1000.0 * tot / len(times)
+    return sample_pairs * len(times) / tot, cores, 1000.0 * tot / len(times), kind, what
 
 
 def run_reference(a, rank, world):
     if rank != 0:
         return
-    v, cores, ms = cpu_reference_pairs_per_s(a, a.steps, a.warmup)
+    v, cores, ms, kind, what = cpu_reference_pairs_per_s(a, a.steps, a.warmup)
     sample = f"1 pair/step of the same workload (N={a.corr}, T={a.tokens}, {a.layers} layers), {a.steps} timed steps after {a.warmup} warm-ups"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "note": "reference algorithm on host CPU cores (oracle port of the reference's "
-                       "PyTorch fp32 path; the Python reference tree does not travel to the GPU box); step = 1 pair"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": config_dict(a, world),
+            "note": f"reference CPU path on the host cores: {what}; image backbone bypassed (outside the timed path); step = 1 pair",
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "source": what},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cfg3_strong_scaling(a, eng, dev, rank, world, timed):
+    """BASELINE.json configs[2]: a FIXED batch of 256 KITTI-shaped pairs (60 m extent, sigma_d = tau = nms = 1.2, 5000 correspondences,
+    4800 image tokens) split contiguously over the ranks (gmf_b200.shard.shard_range); every step uploads the rank's shard from pinned host
+    memory, runs the path and ends with the host gather of poses and labels (gmf_b200.shard.gather_poses + labels D2H) inside the timed
+    region.  Strong scaling: total work fixed.  On N > 1 ranks, rank 0 afterwards runs the whole batch alone (the others wait at the
+    barrier) so that the line carries its own single-GPU denominator measured on the same box in the same run."""
+    import torch.distributed as dist
+    from gmf_b200.engine import Engine
+    from gmf_b200.shard import gather_poses, shard_range
+    from gmf_b200.synth import synth_pairs, synth_tokens
+    B, N, T, thr = a.cfg3_pairs, a.corr, a.tokens, 1.2
+    sd = synth_weights(a.layers)
+    sd["sigma_spat"] = torch.tensor([thr])
+    keng = Engine(num_layers=a.layers, inlier_threshold=thr, nms_radius=thr, device=dev)
+    keng.load_state_dict(sd)
+
+    def shard_inputs(lo, hi):
+        # pair b of the global batch is generated from its own seed, so every rank (and the single-GPU run) sees the same pairs
+        pr = [synth_pairs(1, N, seed=3000 + b, extent=60.0, inlier_ratio=0.30, noise=0.04) for b in range(lo, hi)]
+        cat = lambda key: torch.cat([p[key] for p in pr]).contiguous().pin_memory()   # noqa: E731
+        tok = lambda s0: torch.cat([synth_tokens(1, T, s0 + b) for b in range(lo, hi)]).contiguous().pin_memory()   # noqa: E731
+        return [cat("corr_pos"), cat("src_keypts"), cat("tgt_keypts"), tok(100000), tok(200000)], torch.cat([p["gt_trans"] for p in pr])
+
+    def run_split(r, w, steps):
+        lo, hi = shard_range(B, r, w)
+        host, gt = shard_inputs(lo, hi)
+        nb = hi - lo
+        h_tr, h_lab = torch.empty(nb, 4, 4).pin_memory(), torch.empty(nb, N).pin_memory()
+        res = {}
+
+        def step():
+            keng.forward_host(*host, h_tr, h_lab, None, testing=True)               # H2D + path + D2H, stream-synchronised
+            res["poses"] = gather_poses(h_tr, B, r, w) if w > 1 else h_tr             # final host gather (all ranks end with every pose)
+        for _ in range(2):
+            step()
+        ms = timed(step, steps) if w > 1 else None
+        if w == 1:                                                                  # single-rank run: no collective, time locally
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        te = float((h_tr[:, :3, 3] - gt[:, :3, 3]).norm(dim=-1).max())
+        return ms / steps, te
+
+    steps = max(2, min(a.steps, 5))
+    ms_n, te = run_split(rank, world, steps)
+    out = {"workload": f"cfg#3 KITTI shape: {B} pairs total x {N} correspondences, {T} image tokens, {a.layers} layers, extent 60 m, sigma_d = tau = 1.2; "
+                       "shard upload from pinned host memory + host gather of poses/labels inside the timed region",
+           "scaling": "strong", "pairs_total": B, "pairs_per_gpu": -(-B // world), "n_gpus": world, "ms_per_batch": ms_n,
+           "value": B / (ms_n / 1e3), "unit": UNIT, "max_translation_error_vs_gt_m": te}
+    if world > 1:
+        if rank == 0:
+            ms_1, _ = run_split(0, 1, steps)
+            out.update({"single_gpu_ms_per_batch": ms_1, "single_gpu_value": B / (ms_1 / 1e3), "speedup_vs_1gpu": ms_1 / ms_n,
+                        "efficiency": ms_1 / ms_n / world})
+        dist.barrier()
+    return out
 
 
 def main():
@@ -310,7 +428,8 @@ def main():
         prof = eng.profile_read()
         eng.profile(False)
         tot_ms = sum(v[0] for v in prof.values())
-        prof_table = {k: {"ms_per_step": v[0] / a.steps, "launches_per_step": v[1] / a.steps, "share": v[0] / tot_ms} for k, v in prof.items()}
+        prof_table = {k: {"ms_per_step": v[0] / a.steps, "launches_per_step": v[1] / a.steps, "share": v[0] / tot_ms} for k, v in prof.items()
+                      if v[1] > 0}
         sc_ms, sc_n = prof["attn_sc"]
         sc_flops = 4.0 * a.corr * a.corr * 128 * a.pairs * a.layers * a.steps           # 4 N^2 C per pair-layer
         ach = sc_flops / (sc_ms / 1000.0) / 1e12
@@ -326,15 +445,16 @@ def main():
                 "peak_source": how, "avg_launch_ms": sc_ms / max(sc_n, 1), "launches": sc_n,
                 "algorithmic_flops_per_launch": sc_flops / max(sc_n, 1),
                 "mufu_colimit": {"floor_ms_per_launch": mufu_floor_ms, "frac": mufu_floor_ms / (sc_ms / max(sc_n, 1))},
+                "per_kernel": per_kernel_roofline(prof, a, a.steps, peak_tf, hbm),
                 "whole_path": {"flops_per_pair": flops_per_pair(a.corr, a.tokens, a.layers),
                                "achieved_tflops": flops_per_pair(a.corr, a.tokens, a.layers) * value / world / 1e12,
                                "frac_of_tensor_peak": flops_per_pair(a.corr, a.tokens, a.layers) * value / world / 1e12 / peak_tf}}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, cores, msp = cpu_reference_pairs_per_s(a, steps=1, warmup=0)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 pair of the same workload (N={a.corr}, T={a.tokens}, {a.layers} layers), single timed pass, {msp / 1000:.1f} s"}
+        v, cores, msp, kind, what = cpu_reference_pairs_per_s(a, steps=2, warmup=1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "source": what,
+               "sample": f"1 pair of the same workload (N={a.corr}, T={a.tokens}, {a.layers} layers) per pass, 2 timed passes after 1 warm-up, {msp / 1000:.1f} s each"}
 
     backbone = None
     if rank == 0 and world == 1 and not a.no_backbone:
@@ -342,6 +462,10 @@ def main():
             backbone = backbone_timing(dev, a.pairs)
         except RuntimeError as e:                                # e.g. out of memory on a smaller device: report, do not fail the bench
             backbone = {"error": str(e)[:200]}
+
+    strong = None
+    if not a.no_cfg3:
+        strong = cfg3_strong_scaling(a, eng, dev, rank, world, timed)
 
     # sanity on the last device result: poses must be finite and close to the synthetic ground truth
     tr = out["final_trans"].float().cpu()
@@ -352,10 +476,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, a.min_warmup),
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16 attention operands + tf32/fp16 linear layers, fp32 accumulate/softmax/classifier", "data": "synthetic",
-                "config": {"workload": workload_name(a), "parallelism": f"pair-sharded replicas x{world}, no collective on the data path",
-                           "cache": f"per-step inputs ({sum(t.numel() * 4 for t in host) / 1e6:.0f} MB) + workspace ({ws_gb:.1f} GB) exceed the 126 MB L2",
-                           "max_translation_error_vs_gt_mm": te_mm},
-                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "backbone": backbone, "kernel_profile": prof_table}
+                "config": config_dict(a, world),
+                "sanity": {"max_translation_error_vs_gt_mm": te_mm, "workspace_gb": ws_gb},
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "strong_scaling": strong,
+                "backbone": backbone, "kernel_profile": prof_table}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

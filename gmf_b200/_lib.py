@@ -25,7 +25,7 @@ EXPORTS = [
 
 
 class GmfConfig(C.Structure):
-    _fields_ = [("num_layers", C.c_int32), ("num_iterations", C.c_int32), ("k", C.c_int32), ("ratio", C.c_float),
+    _fields_ = [("num_layers", C.c_int32), ("num_iterations", C.c_int32), ("k", C.c_int32), ("ratio", C.c_double),
                 ("inlier_threshold", C.c_float), ("nms_radius", C.c_float)]
 
 

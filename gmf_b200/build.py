@@ -19,23 +19,31 @@ def _stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """`out` / `defines` build a development variant (e.g. -DGMF_SC_DBG=2) next to the product library; the product is always
+    gmf_b200/libgmf_b200.so built with no extra defines."""
+    target = out or LIB
+    if not force and out is None and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DGMF_SC_DBG=" + os.environ.get("GMF_SC_DBG", "0"),] + (["-DGMF_FFN_TRACE"] if os.environ.get("GMF_FFN_TRACE") else []) + (["-DGMF_PCN_TRACE"] if os.environ.get("GMF_PCN_TRACE") else []) + [
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"] + [f"-D{d}" for d in defines] + [
+           "-Xcompiler", "-fPIC", "-shared", "-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libgmf_b200.so")
+        raise RuntimeError("nvcc failed building " + target)
     if verbose:
         print(r.stdout + r.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose="-v" in sys.argv))
+    # python -m gmf_b200.build [-v] [--out build/libvariant.so] [-DNAME=VALUE ...]
+    argv = sys.argv[1:]
+    out = argv[argv.index("--out") + 1] if "--out" in argv else None
+    if out:
+        os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
+    print(build(force=True, verbose="-v" in argv, out=out, defines=[x[2:] for x in argv if x.startswith("-D")]))

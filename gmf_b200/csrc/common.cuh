@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 namespace gmf {
 
@@ -369,6 +370,25 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// host: opt-in dynamic shared memory, once per (kernel, device)
+// ------------------------------------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the device's context: a process that drives several GPUs (one Engine per
+// device behind the C ABI) must set it on each of them.  One 64-bit mask per kernel instantiation, bit = device ordinal.
+template <class Kern>
+inline cudaError_t ensure_dyn_smem(Kern kern, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);   // idempotent: a racing thread repeats it harmlessly
+  if (e != cudaSuccess) return e;
+  done.fetch_or(bit, std::memory_order_release);
+  return cudaSuccess;
 }
 
 }  // namespace gmf

@@ -405,13 +405,9 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
 template <int NB, int EPI>
 inline cudaError_t launch_img_gemm(const ImgGemmArgs& a, int col_blocks, cudaStream_t st, int pairs = 1) {
   using Cfg = IgCfg<NB, EPI>;
-  static bool configured = false;
+  static std::atomic<unsigned long long> configured{0};
   auto kern = img_gemm_kernel<NB, EPI>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem(kern, Cfg::SMEM, configured)) return e;
   kern<<<dim3(a.tiles, col_blocks, pairs), 192, Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }

@@ -23,12 +23,12 @@ std::vector<Spec> dgr_spec(bool pe) {
 }
 
 struct DgrWork {
-  float *x0, *xq_img, *c_img, *o, *o_img, *x1, *ln_img, *g_img, *kpts, *part_o, *part_l;
-  __nv_bfloat16 *q_t, *k_t, *vt_t, *aq, *bd;
+  float *x0, *xq_img, *c_img, *o, *o_img, *x1, *ln_img, *g_img, *part_o, *part_l;
+  __nv_bfloat16 *q_t, *k_t, *vt_t;
 };
 
 size_t dgr_carve(DgrWork& w, uint8_t* base, int M, int T) {
-  const size_t mt = cdiv(M, 128), kt = cdiv(T, 128), xt = std::max(mt, kt);
+  const size_t mt = cdiv(M, 128), kt = cdiv(T, 128);
   size_t off = 0;
   auto take = [&](size_t bytes) -> uint8_t* {
     uint8_t* p = base ? base + off : nullptr;
@@ -43,12 +43,9 @@ size_t dgr_carve(DgrWork& w, uint8_t* base, int M, int T) {
   w.x1 = (float*)take((size_t)M * kDgrLatent * 4);
   w.ln_img = (float*)take(mt * 128 * kDgrLatent * 4);
   w.g_img = (float*)take(mt * 128 * kDgrHidden * 4);
-  w.kpts = (float*)take(xt * 128 * 8 * 4);
   w.q_t = (__nv_bfloat16*)take(mt * 128 * 128 * 2);
   w.k_t = (__nv_bfloat16*)take(kt * 128 * 128 * 2);
   w.vt_t = (__nv_bfloat16*)take(kt * 128 * 128 * 2);
-  w.aq = (__nv_bfloat16*)take(xt * 128 * 64 * 2);
-  w.bd = (__nv_bfloat16*)take(xt * 128 * 64 * 2);
   w.part_o = (float*)take(kt * (size_t)M * kDgrHead * 4);        // up to one split per context tile
   w.part_l = (float*)take(kt * (size_t)M * 2 * 4);
   return off + 1024;
@@ -64,7 +61,11 @@ struct gmf_dgr_head {
   const float *lnq_g, *lnq_b, *lnc_g, *lnc_b, *lnf_g, *lnf_b, *wq, *wkv, *wo, *bo, *w1, *b1, *w2, *b2;
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  int feat_tiles = 0;        // neutral distance-feature tiles currently valid in the workspace
+  // neutral distance-feature tiles (compat == 1) for the attention kernel.  They live in their OWN allocation: inside the per-call
+  // workspace their offsets would move with M (the active-voxel count changes every call) while a cache keyed on the tile count
+  // would still call them valid.
+  uint8_t* feat = nullptr;   // [kpts | aq | bd] for feat_tiles tiles
+  int feat_tiles = 0;
 };
 
 extern "C" {
@@ -91,6 +92,7 @@ void gmf_dgr_head_destroy(gmf_dgr_head* h) {
   cudaSetDevice(h->device);
   if (h->blob) cudaFree(h->blob);
   if (h->ws) cudaFree(h->ws);
+  if (h->feat) cudaFree(h->feat);
   delete h;
 }
 
@@ -168,18 +170,27 @@ int gmf_dgr_head_forward(gmf_dgr_head* h, const float* latents, const float* ima
   if (need > h->ws_bytes) {
     CU(cudaDeviceSynchronize());
     if (h->ws) cudaFree(h->ws);
-    h->ws = nullptr; h->ws_bytes = 0; h->feat_tiles = 0;
+    h->ws = nullptr; h->ws_bytes = 0;
     CU(cudaMalloc(&h->ws, need));
     h->ws_bytes = need;
   }
   dgr_carve(w, (uint8_t*)(((uintptr_t)h->ws + 1023) & ~(uintptr_t)1023), M, T);
-  if (h->feat_tiles != xt) {
-    // neutral spatial-consistency operand: all-zero coordinates give DA = 0, Y = -1 in the attention kernel, i.e. compat == 1
-    CU(cudaMemsetAsync(w.kpts, 0, (size_t)xt * 128 * 8 * 4, st));
-    dist_feature_scaled_kernel<<<dim3(xt, 1), 128, 0, st>>>(w.kpts, xt * 128, 1.0f, w.aq, w.bd);
+  if (h->feat_tiles < xt) {
+    // neutral spatial-consistency operand: all-zero coordinates give DA = 0, Y = -1 in the attention kernel, i.e. compat == 1.
+    // Every row is the same, so a buffer generated for xt tiles serves any smaller (M, T) as well.
+    CU(cudaDeviceSynchronize());
+    if (h->feat) cudaFree(h->feat);
+    h->feat = nullptr; h->feat_tiles = 0;
+    const size_t kp_bytes = (size_t)xt * 128 * 8 * 4, f_bytes = (size_t)xt * 128 * 64 * 2;
+    CU(cudaMalloc(&h->feat, kp_bytes + 2 * f_bytes));
+    CU(cudaMemsetAsync(h->feat, 0, kp_bytes, st));
+    dist_feature_scaled_kernel<<<dim3(xt, 1), 128, 0, st>>>((const float*)h->feat, xt * 128, 1.0f, (__nv_bfloat16*)(h->feat + kp_bytes),
+                                                           (__nv_bfloat16*)(h->feat + kp_bytes + f_bytes));
     LAUNCHED();
     h->feat_tiles = xt;
   }
+  const __nv_bfloat16* n_aq = (const __nv_bfloat16*)(h->feat + (size_t)h->feat_tiles * 128 * 8 * 4);
+  const __nv_bfloat16* n_bd = n_aq + (size_t)h->feat_tiles * 128 * 64;
   const float* resid0 = latents;
   if (h->pe) {
     rows_to_img_kernel<kDgrLatent, true, true><<<mt * 16, 256, 0, st>>>(latents, M, mt, h->cpe_q_w, h->cpe_q_b, h->lnq_g, h->lnq_b, w.x0, w.xq_img);
@@ -210,7 +221,7 @@ int gmf_dgr_head_forward(gmf_dgr_head* h, const float* latents, const float* ima
   }
   {  // softmax(q k^T / sqrt(128)) v
     ScAttnArgs sa{};
-    sa.q_t = w.q_t; sa.k_t = w.k_t; sa.vt_t = w.vt_t; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = w.o;
+    sa.q_t = w.q_t; sa.k_t = w.k_t; sa.vt_t = w.vt_t; sa.aq_t = n_aq; sa.bd_t = n_bd; sa.out = w.o;
     sa.N = T; sa.tiles = kt; sa.Nq = M; sa.q_tiles = mt;
     // few query tiles: split the keys over enough CTAs to cover the SMs (flash-decoding style); the combine is folded into the
     // kernel that builds the to_out GEMM's operand image

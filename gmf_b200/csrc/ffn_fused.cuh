@@ -400,12 +400,8 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
 }
 
 inline cudaError_t launch_ffn_fused(const FfnArgs& a, int pairs, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = ensure_dyn_smem(ffn_fused_kernel, FfnCfg::SMEM, configured)) return e;
   ffn_fused_kernel<<<dim3(a.tiles, pairs), 640, FfnCfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }

@@ -368,12 +368,8 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
 }
 
 inline cudaError_t launch_fus_attn_v2(const AttnArgs& a, int pairs, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fus_attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa2Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = ensure_dyn_smem(fus_attn_v2_kernel, Fa2Cfg::SMEM, configured)) return e;
   fus_attn_v2_kernel<<<dim3((a.q_tiles + 1) / 2, pairs), 672, Fa2Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }

@@ -50,8 +50,9 @@ struct ProfScope {
   }
   ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
 };
-enum { CAT_PCN = 0, CAT_QKV, CAT_FC12, CAT_QFUS, CAT_KVFUS, CAT_OUT64, CAT_FFN1, CAT_FFN2, CAT_ATTN_FUS, CAT_ATTN_SC, CAT_PREP,
-       CAT_CLASSIFY, CAT_SEEDS, CAT_KNN, CAT_SPECTRAL, CAT_SCORE, CAT_COUNT };
+enum { CAT_QKV = 0, CAT_QFUS, CAT_KVFUS, CAT_FFN, CAT_ATTN_FUS, CAT_ATTN_SC, CAT_PREP, CAT_CLASSIFY, CAT_SEEDS, CAT_KNN, CAT_SPECTRAL,
+       CAT_SCORE, CAT_OTHER, CAT_COUNT };
+static_assert(CAT_COUNT == GMF_PROFILE_CATEGORIES, "profile categories out of sync with include/gmf_b200.h");
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -196,11 +197,11 @@ struct FusionW {
   bool pe = false;
   const float *cpe_q_w = nullptr, *cpe_q_b = nullptr, *cpe_c_w = nullptr, *cpe_c_b = nullptr;
   const float *lnq_g, *lnq_b, *lnc_g, *lnc_b, *lnf_g, *lnf_b;
-  const float *wq, *wkv, *wo, *bo, *w1, *b1, *w2, *b2;
+  const float *wq, *wkv, *wo, *bo, *b1, *b2;
   const float *w1f, *w2f;   // fused-FFN packing (8 passes of 64 hidden columns)
 };
 struct LayerW {
-  const float *pcn_w, *pcn_b, *qkv_w, *qkv_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
+  const float *pcn_b, *qkv_w, *qkv_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
   const float* pq_w;        // PointCN + QKV weight chunks for the chained kernel (pcn_qkv.cuh)
   FusionW f2;
 };
@@ -218,28 +219,18 @@ struct gmf_ctx {
   std::vector<LayerW> layers;
   ClsWeights cls{};
   int chunk_pairs = 64;
-  int pcn_qkv = 1;          // PointCN + QKV projection chained in one kernel
-  int sc_fuse_fc = 1;       // fc_message.0/.3 fused into the SC attention kernel's tail
   int match_impl = 0;       // 0 = FP32 register-blocked matcher; 1 = tensor pipe (error-compensated tf32, argmin in the GEMM epilogue): correct but
                             // slower at K = 96 (6.3 vs 3.4 ms for 64 pairs x 5000^2): one 128 x 128 block per CTA is all fixed latency
-  int knn_impl = 1;         // 1 = seed kNN distances on the tensor pipe (error-compensated tf32, K = 384), 0 = FP32 register-blocked SGEMM
-  int ffn_impl = 3;         // 3 = fused GEGLU FFN kernel + fused fc_message.6 tail, 2 = fused FFN, 1 = two linear kernels
-  int fus_impl = 3;         // 3 = fusion attention with fused to_out + residual, 2 = separate to_out kernel
-  int sc_impl = 14;         // 14/15/16 = 2 threads per score row with 0/1/2 of 4 exponentials on the FMA pipe, 11/12 = 1 thread per row
+  int sc_impl = 0;          // development switch of the SC attention kernel variants (GMF_SC_IMPL); 0 = shipped configuration
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
-  // overlap: (1) inside a lane the context K/V and query projections run on side streams next to the SC attention; (2) a chunk of
-  // pairs is split into two lanes that run the whole path concurrently, so one lane's partial waves and small tail kernels
-  // (sort, spectral matching, refinement) are filled by the other lane's attention CTAs.
-  int overlap = 1;                      // 0 = single stream, 1 = side streams, 2 = side streams + two lanes
+  // side streams: the context K/V projections of all layers and each layer's Fusion-2 query projection run next to the SC attention
   struct Lane {
-    cudaStream_t main = nullptr;          // lane 0 runs on the caller's stream, lane 1 on this one
     cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_img = nullptr, ev_f1 = nullptr, ev_q = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_img = nullptr, ev_f1 = nullptr, ev_q = nullptr;
     std::vector<cudaEvent_t> ev_kv;
-  } lanes[2];
-  cudaEvent_t ev_fork = nullptr;
+  } lane;
   cudaStream_t copy_stream = nullptr;   // uploads of the next chunk overlap the current chunk's kernels
   cudaEvent_t copy_ev[64] = {};
   cudaEvent_t start_ev = nullptr;
@@ -257,7 +248,7 @@ namespace {
 struct Work {
   float *kpts; float4 *src4, *tgt4;
   float *feat_img;   // tf32 tile image of the layer output (handed from the FFN kernel to the next layer's PointCN/QKV kernel)
-  float *imgfeat, *featA, *feat1, *x0, *x1, *x2, *of, *g_t, *msg, *m1, *m2;
+  float *imgfeat, *featA, *feat1, *x0, *x1, *m2;
   __nv_bfloat16 *qf, *kf, *vtf, *qs, *ks, *vts, *aq, *bd;
   __nv_bfloat16 *kf_all, *vtf_all;   // [layers] context K / V^T tiles of every encoder layer (projected up front on a side stream)
   size_t kv_stride;
@@ -287,10 +278,8 @@ size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k, int laye
   w.imgfeat = b.take<float>((size_t)B * std::max(T, 1) * 128);
   w.featA = b.take<float>((size_t)B * N * 128); w.feat1 = b.take<float>((size_t)B * N * 128);
   w.feat_img = b.take<float>((size_t)B * nt * 128 * 128);
-  w.x0 = b.take<float>(B * Lm * 128); w.x1 = b.take<float>(B * Lm * 128); w.x2 = b.take<float>(B * Lm * 128);
-  w.of = b.take<float>(B * Lm * 64);
-  w.g_t = b.take<float>(B * tm * 128 * 512);
-  w.msg = b.take<float>((size_t)B * N * 128); w.m1 = b.take<float>((size_t)B * N * 64); w.m2 = b.take<float>((size_t)B * N * 64);
+  w.x0 = b.take<float>(B * Lm * 128); w.x1 = b.take<float>(B * Lm * 128);
+  w.m2 = b.take<float>((size_t)B * N * 64);
   w.qf = b.take<__nv_bfloat16>(B * tm * 128 * 64);
   w.kf = b.take<__nv_bfloat16>(B * tm * 128 * 64); w.vtf = b.take<__nv_bfloat16>(B * tm * 128 * 64);
   w.kv_stride = (size_t)B * tt * 128 * 64;
@@ -309,7 +298,7 @@ size_t carve(Work& w, uint8_t* base, int B, int N, int T, int S, int k, int laye
   return b.off + 1024;
 }
 
-inline int num_seeds(const gmf_ctx* c, int N) { return (int)((double)N * (double)c->cfg.ratio); }
+inline int num_seeds(const gmf_ctx* c, int N) { return (int)((double)N * c->cfg.ratio); }   // int(num_corr * self.ratio) in double
 inline int eff_k(const gmf_ctx* c, int N) { return std::min(c->cfg.k, N - 1); }
 
 int check_ws(const gmf_ctx* ctx, Work& w, void* ws, size_t bytes, int B, int N, int T) {
@@ -326,7 +315,7 @@ int check_ws(const gmf_ctx* ctx, Work& w, void* ws, size_t bytes, int B, int N, 
 // launch schedule
 // ------------------------------------------------------------------------------------------------
 template <int K, int NOUT, int PRO, int EPI>
-int run_linear(const LinArgs& a, int pairs, cudaStream_t st, int category = CAT_FC12) {
+int run_linear(const LinArgs& a, int pairs, cudaStream_t st, int category = CAT_OTHER) {
   ProfScope ps(category, st);
   cudaError_t e = launch_linear<K, NOUT, PRO, EPI>(a, pairs, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -382,20 +371,15 @@ int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* 
                     float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3, float* out_img) {
   {
     AttnArgs a{};
-    a.q_t = w.qf; a.k_t = kf; a.vt_t = vtf; a.out = w.of;
+    a.q_t = w.qf; a.k_t = kf; a.vt_t = vtf; a.out = nullptr;
     a.Lq = Lq; a.Lk = Lk; a.q_tiles = cdiv(Lq, 128); a.k_tiles = cdiv(Lk, 128);
-    if (ctx->fus_impl >= 3) { a.wo_packed = f.wo; a.bo = f.bo; a.resid = resid0; a.xout = w.x1; }   // to_out + bias + residual fused
+    a.wo_packed = f.wo; a.bo = f.bo; a.resid = resid0; a.xout = w.x1;                                // to_out + bias + residual fused
     ProfScope ps(CAT_ATTN_FUS, st);
     cudaError_t e = launch_fus_attn_v2(a, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "fusion attention launch");
   }
-  if (ctx->fus_impl < 3) {  // to_out + bias + residual
-    LinArgs a = lin(w.of, Lq, f.wo, f.bo);
-    a.residual = resid0; a.out = w.x1;
-    TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st, CAT_OUT64)));
-  }
-  if (ctx->ffn_impl >= 2) {   // LN -> Linear(128,1024) -> GEGLU -> Linear(512,128) + bias + residual, hidden activation on chip
+  {   // LN -> Linear(128,1024) -> GEGLU -> Linear(512,128) + bias + residual, hidden activation on chip
     FfnArgs a{};
     a.x = w.x1; a.L = Lq; a.tiles = cdiv(Lq, 128); a.ln_g = f.lnf_g; a.ln_b = f.lnf_b;
     a.w1_packed = f.w1f; a.b1 = f.b1; a.w2_packed = f.w2f; a.b2 = f.b2; a.out = out;
@@ -405,7 +389,7 @@ int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* 
     const bool do_trace = (++n_ffn == 20);
     if (do_trace) { cudaMalloc(&a.trace, 256 * 8); cudaMemsetAsync(a.trace, 0, 256 * 8, st); }
 #endif
-    ProfScope ps(CAT_FFN1, st);
+    ProfScope ps(CAT_FFN, st);
     cudaError_t e = launch_ffn_fused(a, B, st);
 #ifdef GMF_FFN_TRACE
     if (do_trace) {
@@ -417,17 +401,6 @@ int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* 
 #endif
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "ffn_fused launch");
-    return 0;
-  }
-  {  // LN -> Linear(128,1024) -> GEGLU => tiled activation image
-    LinArgs a = lin(w.x1, Lq, f.w1, f.b1);
-    a.ln_g = f.lnf_g; a.ln_b = f.lnf_b; a.out = w.g_t;
-    TRY((run_linear<128, 1024, PRO_LN, EPI_GEGLU_TILED>(a, B, st, CAT_FFN1)));
-  }
-  {  // Linear(512,128) + bias + residual
-    LinArgs a = lin(w.g_t, Lq, f.w2, f.b2);
-    a.residual = w.x1; a.out = out;
-    TRY((run_linear<512, 128, PRO_TILED, EPI_BIAS_RES>(a, B, st, CAT_FFN2)));
   }
   return 0;
 }
@@ -443,13 +416,8 @@ int run_prep(const gmf_ctx* ctx, Work& w, const float* src, const float* tgt, in
 }
 
 cudaError_t launch_sc_any(const gmf_ctx* ctx, const ScAttnArgs& sa, int B, cudaStream_t st) {
-  switch (ctx->sc_impl) {   // GMF_SC_IMPL: threads per score row / exponentials per 4 evaluated on the FMA pipe (profiles/r01_sc_attention.md)
-    case 11: return launch_sc_attn_v9<0, 1>(sa, B, st);
-    case 12: return launch_sc_attn_v9<1, 1>(sa, B, st);
-    case 15: return launch_sc_attn_v9<1, 2>(sa, B, st);
-    case 16: return launch_sc_attn_v9<2, 2>(sa, B, st);
-    default: return launch_sc_attn_v9<0, 2>(sa, B, st);
-  }
+  (void)ctx;
+  return launch_sc_attn_v9<0, 2>(sa, B, st);
 }
 
 // Q/K/V projections + SC-guided attention (PointDSC.py:56-64); feat1 = PointCN output
@@ -476,8 +444,7 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
                       float* feat_out, cudaStream_t st, const gmf_ctx::Lane* lane = nullptr, bool in_img = false, bool out_img = false) {
   const bool overlapped = lane != nullptr;
   const LayerW& lw = ctx->layers[li];
-  const bool chain = ctx->pcn_qkv != 0;                        // PointCN + QKV projection as one chained-GEMM kernel
-  if (chain) {
+  {   // PointCN (conv + folded BN + ReLU) chained with the Q/K/V projections
     PcnQkvArgs a{};
     a.x = feat_in; a.x_img = in_img ? w.feat_img : nullptr; a.L = N; a.tiles = cdiv(N, 128); a.w_packed = lw.pq_w; a.pcn_bias = lw.pcn_b; a.qkv_bias = lw.qkv_b;
     a.feat1 = w.feat1; a.tq = w.qs; a.tk = w.ks; a.tv = w.vts;
@@ -485,12 +452,7 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     cudaError_t e = launch_pcn_qkv(a, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "pcn_qkv launch");
-  } else {
-    LinArgs a = lin(feat_in, N, lw.pcn_w, lw.pcn_b);
-    a.out = w.feat1;
-    TRY((run_linear<128, 128, PRO_NONE, EPI_BIAS_RELU>(a, B, st, CAT_PCN)));
   }
-  const bool fuse_fc = ctx->sc_fuse_fc != 0;   // fc_message.0/.3 run as the tail of the gen-9 attention kernel
   const float* resid0 = nullptr;
   if (overlapped) {
     // the Fusion-2 query projection only needs feat1: it runs on a side stream next to the SC attention (whose last, partial wave
@@ -500,42 +462,21 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     TRY(run_fusion_q(lw.f2, w, w.feat1, B, N, &resid0, lane->aux[1]));
     CU(cudaEventRecord(lane->ev_q, lane->aux[1]));
   }
-  TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, w.msg, st, fuse_fc ? w.m2 : nullptr, chain));
-  if (!fuse_fc) {
-    LinArgs a = lin(w.msg, N, lw.fc1_w, lw.fc1_b);
-    a.out = w.m1;
-    TRY((run_linear<128, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
-  }
-  if (!fuse_fc) {
-    LinArgs a = lin(w.m1, N, lw.fc2_w, lw.fc2_b);
-    a.out = w.m2;
-    TRY((run_linear<64, 64, PRO_NONE, EPI_BIAS_RELU>(a, B, st)));
-  }
+  // SC attention with fc_message.0/.3 as the kernel's tail: writes m2
+  TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, nullptr, st, w.m2, true));
+  // fc_message.6(m2) + fusion_layer_2 output (PointDSC.py:73) are folded into the fused FFN kernel's tail
   if (overlapped) {
     CU(cudaStreamWaitEvent(st, lane->ev_q, 0));
     CU(cudaStreamWaitEvent(st, lane->ev_kv[li], 0));
     return run_fusion_core(ctx, lw.f2, w, resid0, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
                            lw.fc3_w, lw.fc3_b, out_img ? w.feat_img : nullptr);
   }
-  if (ctx->ffn_impl >= 3) {   // fc_message.6(m2) + fusion_layer_2 output (PointDSC.py:73) folded into the fused FFN kernel's tail
-    TRY(run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, feat_out, st, w.m2, lw.fc3_w, lw.fc3_b));
-    return 0;
-  }
-  TRY(run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, w.x2, st));
-  {
-    LinArgs a = lin(w.m2, N, lw.fc3_w, lw.fc3_b);
-    a.residual = w.x2; a.out = feat_out;
-    TRY((run_linear<64, 128, PRO_NONE, EPI_BIAS_RES>(a, B, st, CAT_OUT64)));
-  }
-  return 0;
+  return run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, feat_out, st, w.m2, lw.fc3_w, lw.fc3_b);
 }
 
 int run_classify(const gmf_ctx* ctx, const float* feat, long long rows, float* normed, float* conf, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    CU(cudaFuncSetAttribute(classify_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClsSmem));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  CU(ensure_dyn_smem(classify_normalize_kernel, kClsSmem, configured));
   ProfScope ps(CAT_CLASSIFY, st);
   classify_normalize_kernel<<<(unsigned)std::min<long long>((rows + 63) / 64, 148 * 3 * 2), 256, kClsSmem, st>>>(feat, rows, ctx->cls, normed, conf);
   LAUNCHED();
@@ -547,11 +488,8 @@ int run_pick_seeds(const gmf_ctx* ctx, Work& w, const float* conf, int B, int N,
   while (np2 < N) np2 <<= 1;
   if (np2 > 16384) return fail(GMF_ERR_INVALID, "pick_seeds supports N <= 16384");
   ProfScope ps(CAT_SEEDS, st);
-  static bool configured = false;
-  if (!configured) {
-    CU(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  CU(ensure_dyn_smem(topk_sort_kernel, 16384 * 8, configured));
   const bool windowed = use_nms && N >= 1024;              // x-sorted sweep: far tiles are skipped (tail.cuh, nms_key_kernel)
   if (windowed) {
     topk_sort_kernel<<<B, 1024, (size_t)np2 * 8, st>>>(reinterpret_cast<const float*>(w.src4), 4, N, np2, N, w.perm);
@@ -576,7 +514,7 @@ int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const 
   if (k < 1 || k > 40) return fail(GMF_ERR_INVALID, "k must be in [1, 40]");
   {
     ProfScope ps(CAT_KNN, st);
-    if (ctx->knn_impl >= 1) {   // tensor pipe, error-compensated tf32 (K = 384): dgr_head.cuh knn_operand_kernel + img_gemm_kernel<128, DE_DIST>
+    {   // tensor pipe, error-compensated tf32 (K = 384): dgr_head.cuh knn_operand_kernel + img_gemm_kernel<128, DE_DIST>
       const int st_ = cdiv(S, 128), nt_ = cdiv(N, 128);
       knn_operand_kernel<<<dim3(st_ * 16, B), 256, 0, st>>>(normed, seeds, 1, N, S, st_, w.knn_a);
       LAUNCHED();
@@ -588,9 +526,6 @@ int run_seed_hypotheses(const gmf_ctx* ctx, Work& w, const float* normed, const 
       cudaError_t e = launch_img_gemm<128, DE_DIST>(a, nt_, st, B);
       g_launches.fetch_add(1, std::memory_order_relaxed);
       if (e != cudaSuccess) return fail_cuda(e, "seed kNN distance GEMM launch");
-    } else {
-      seed_dist_kernel<<<dim3(cdiv(N, 128), cdiv(S, 128), B), 256, 0, st>>>(normed, seeds, N, S, w.dist);
-      LAUNCHED();
     }
     TRY(launch_select(w.dist, B, N, S, k, knn, st));
   }
@@ -633,7 +568,7 @@ int forward_chunk(gmf_ctx* ctx, gmf_ctx::Lane* lane, Work& w, const float* corr,
   TRY(run_fusion(ctx, ctx->f1, w, q_tok, p_tok, B, T, T, w.imgfeat, st));
   const int L = ctx->cfg.num_layers;
   // per-launch profiling (gmf_profile_enable) times every kernel alone: it uses the single-stream schedule
-  const bool overlapped = lane && !ctx->prof.on && ctx->sc_fuse_fc && ctx->ffn_impl >= 3 && ctx->fus_impl >= 3;
+  const bool overlapped = lane && !ctx->prof.on;
   if (overlapped) {
     // every layer's context K / V^T depends only on the Fusion-1 output: project them all on a side stream, behind the encoder
     CU(cudaEventRecord(lane->ev_img, st));
@@ -644,7 +579,7 @@ int forward_chunk(gmf_ctx* ctx, gmf_ctx::Lane* lane, Work& w, const float* corr,
     }
   }
   // between layers the features travel as the tf32 tile image the next PointCN/QKV kernel consumes (last layer: row-major)
-  const bool img = overlapped && ctx->pcn_qkv;
+  const bool img = overlapped;
   for (int li = 0; li < L; ++li)
     TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped ? lane : nullptr, img && li > 0, img && li + 1 < L));
   if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
@@ -750,13 +685,7 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   c->cfg = *cfg;
   if (const char* e = getenv("GMF_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, atoi(e));
   if (const char* e = getenv("GMF_SC_IMPL")) c->sc_impl = atoi(e);
-  if (const char* e = getenv("GMF_FUS_IMPL")) c->fus_impl = atoi(e);
-  if (const char* e = getenv("GMF_FFN_IMPL")) c->ffn_impl = atoi(e);
-  if (const char* e = getenv("GMF_KNN_IMPL")) c->knn_impl = atoi(e);
   if (const char* e = getenv("GMF_MATCH_IMPL")) c->match_impl = atoi(e);
-  if (const char* e = getenv("GMF_SC_FUSE_FC")) c->sc_fuse_fc = atoi(e);
-  if (const char* e = getenv("GMF_PCN_QKV")) c->pcn_qkv = atoi(e);
-  if (const char* e = getenv("GMF_OVERLAP")) c->overlap = atoi(e);
   *out = c;
   return 0;
 }
@@ -766,13 +695,12 @@ void gmf_destroy(gmf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->blob) cudaFree(ctx->blob);
   if (ctx->stage) cudaFree(ctx->stage);
-  for (auto& ln : ctx->lanes) {
-    if (!ln.aux[0]) continue;
-    cudaStreamDestroy(ln.main); cudaStreamDestroy(ln.aux[0]); cudaStreamDestroy(ln.aux[1]);
-    cudaEventDestroy(ln.ev_img); cudaEventDestroy(ln.ev_f1); cudaEventDestroy(ln.ev_q); cudaEventDestroy(ln.ev_done);
+  if (ctx->lane.aux[0]) {
+    gmf_ctx::Lane& ln = ctx->lane;
+    cudaStreamDestroy(ln.aux[0]); cudaStreamDestroy(ln.aux[1]);
+    cudaEventDestroy(ln.ev_img); cudaEventDestroy(ln.ev_f1); cudaEventDestroy(ln.ev_q);
     for (auto e : ln.ev_kv) cudaEventDestroy(e);
   }
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);
     for (auto e : ctx->copy_ev) if (e) cudaEventDestroy(e);
@@ -804,7 +732,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
   auto vec = [](const float* p, size_t n) { return std::vector<float>(p, p + n); };
 
   Blob blob;
-  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wkv, wo, bo, w1, b1, w2, b2, w1f, w2f; };
+  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wkv, wo, bo, b1, b2, w1f, w2f; };
   auto pack_fusion = [&](bool pe) {
     FusionOff o{};
     o.pe = pe;
@@ -822,19 +750,13 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     o.wo = blob.push(pack_linear(vec(next("to_out.weight"), 128 * 64), 128, 64, 64, 128));
     o.bo = blob.push(next("to_out.bias"), 128);
     o.lfg = blob.push(next("1.norm.weight"), 128); o.lfb = blob.push(next("1.norm.bias"), 128);
-    std::vector<int> rowmap(1024);      // TMEM column order: pass p = [value rows 128p.., gate rows 512+128p..]
-    for (int p = 0; p < 4; ++p)
-      for (int nbi = 0; nbi < 2; ++nbi)
-        for (int n = 0; n < 128; ++n) rowmap[(p * 2 + nbi) * 128 + n] = (nbi ? 512 : 0) + p * 128 + n;
     const std::vector<float> W1 = vec(next("net.0.weight"), 1024 * 128);
-    o.w1 = blob.push(pack_linear(W1, 1024, 128, 64, 128, &rowmap));
     std::vector<int> rowmap8(1024);     // fused FFN: pass p = [value rows 64p.., gate rows 512+64p..]
     for (int p = 0; p < 8; ++p)
       for (int n = 0; n < 128; ++n) rowmap8[p * 128 + n] = n < 64 ? p * 64 + n : 512 + p * 64 + (n - 64);
     o.w1f = blob.push(GMF_FFN_F16 ? pack_linear_f16(W1, 1024, 128, 128, &rowmap8) : pack_linear(W1, 1024, 128, 64, 128, &rowmap8));
     o.b1 = blob.push(next("net.0.bias"), 1024);
     const std::vector<float> W2 = vec(next("net.2.weight"), 128 * 512);
-    o.w2 = blob.push(pack_linear(W2, 128, 512, 32, 128));
     o.w2f = blob.push(pack_linear(W2, 128, 512, 64, 128));
     o.b2 = blob.push(next("net.2.bias"), 128);
     return o;
@@ -853,7 +775,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
   const float sigma_spat = *next("sigma_spat");
   const size_t l0w = blob.push(next("layer0.weight"), 768), l0b = blob.push(next("layer0.bias"), 128);
   const FusionOff f1 = pack_fusion(false);
-  struct LayerOff { size_t pw, pb, qw, qb, f1w, f1b, f2w, f2b, f3w, f3b, pqw; FusionOff f2; };
+  struct LayerOff { size_t pb, qw, qb, f1w, f1b, f2w, f2b, f3w, f3b, pqw; FusionOff f2; };
   std::vector<LayerOff> lo(L);
   for (int i = 0; i < L; ++i) {
     LayerOff& o = lo[i];
@@ -862,7 +784,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
       std::vector<float> W = vec(next("0.weight"), 128 * 128), b = vec(next("0.bias"), 128);
       const float *g = next("1.weight"), *be = next("1.bias"), *mu = next("1.running_mean"), *va = next("1.running_var");
       fold_bn(W, b, 128, 128, g, be, mu, va);
-      o.pw = blob.push(pack_linear(W, 128, 128, 32, 128)); o.pb = blob.push(b);
+      o.pb = blob.push(b);
       pcn64 = pack_linear(W, 128, 128, 64, 128);
     }
     {
@@ -913,7 +835,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     f.pe = o.pe;
     if (o.pe) { f.cpe_q_w = d + o.cqw; f.cpe_q_b = d + o.cqb; f.cpe_c_w = d + o.ccw; f.cpe_c_b = d + o.ccb; }
     f.lnq_g = d + o.lqg; f.lnq_b = d + o.lqb; f.lnc_g = d + o.lcg; f.lnc_b = d + o.lcb; f.lnf_g = d + o.lfg; f.lnf_b = d + o.lfb;
-    f.wq = d + o.wq; f.wkv = d + o.wkv; f.wo = d + o.wo; f.bo = d + o.bo; f.w1 = d + o.w1; f.b1 = d + o.b1; f.w2 = d + o.w2; f.b2 = d + o.b2;
+    f.wq = d + o.wq; f.wkv = d + o.wkv; f.wo = d + o.wo; f.bo = d + o.bo; f.b1 = d + o.b1; f.b2 = d + o.b2;
     f.w1f = d + o.w1f; f.w2f = d + o.w2f;
     return f;
   };
@@ -924,7 +846,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
   for (int i = 0; i < L; ++i) {
     LayerW& w = ctx->layers[i];
     const LayerOff& o = lo[i];
-    w.pcn_w = d + o.pw; w.pcn_b = d + o.pb; w.qkv_w = d + o.qw; w.qkv_b = d + o.qb; w.pq_w = d + o.pqw;
+    w.pcn_b = d + o.pb; w.qkv_w = d + o.qw; w.qkv_b = d + o.qb; w.pq_w = d + o.pqw;
     w.fc1_w = d + o.f1w; w.fc1_b = d + o.f1b; w.fc2_w = d + o.f2w; w.fc2_b = d + o.f2b; w.fc3_w = d + o.f3w; w.fc3_b = d + o.f3b;
     w.f2 = fuse(o.f2);
   }
@@ -938,9 +860,7 @@ size_t gmf_workspace_bytes(const gmf_ctx* ctx, int B, int N, int T) {
   Work w;
   const int Bc = std::min(B, ctx->chunk_pairs);
   const int S = std::max(num_seeds(ctx, N), 1), k = std::max(eff_k(ctx, N), 1), L = ctx->cfg.num_layers;
-  const size_t whole = carve(w, nullptr, Bc, N, T, S, k, L);
-  const size_t lanes = 2 * ((carve(w, nullptr, (Bc + 1) / 2, N, T, S, k, L) + 1023) & ~(size_t)1023);   // two concurrent half-chunks
-  return std::max(whole, lanes) + 2048;
+  return carve(w, nullptr, Bc, N, T, S, k, L) + 2048;
 }
 
 int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
@@ -956,50 +876,28 @@ int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, 
   const int S = num_seeds(ctx, N);
   const int Bc = std::min(B, ctx->chunk_pairs);
   const int L = ctx->cfg.num_layers;
-  if (ctx->overlap) {
-    for (auto& ln : ctx->lanes) {
-      if (!ln.aux[0]) {
-        CU(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
-        for (auto& a : ln.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-        for (cudaEvent_t* e : {&ln.ev_img, &ln.ev_f1, &ln.ev_q, &ln.ev_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-      }
-      while ((int)ln.ev_kv.size() < L) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.ev_kv.push_back(e); }
+  {
+    gmf_ctx::Lane& ln = ctx->lane;
+    if (!ln.aux[0]) {
+      for (auto& a : ln.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+      for (cudaEvent_t* e : {&ln.ev_img, &ln.ev_f1, &ln.ev_q}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
-    if (!ctx->ev_fork) CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    while ((int)ln.ev_kv.size() < L) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.ev_kv.push_back(e); }
   }
-  const bool two_lanes = ctx->overlap >= 2 && Bc >= 8;         // GMF_OVERLAP=2: measured slightly slower than side streams alone (36.6 vs 36.2 ms)
-  const int Bl = two_lanes ? (Bc + 1) / 2 : Bc;                // pairs per lane
-  Work w[2];
+  Work w;
   {
     if (!workspace) return fail(GMF_ERR_INVALID, "workspace is NULL");
     const int Sw = std::max(S, 1), kw = std::max(eff_k(ctx, N), 1);
-    const size_t lane_bytes = (carve(w[0], nullptr, Bl, N, T, Sw, kw, L) + 1023) & ~(size_t)1023;
-    if (workspace_bytes < lane_bytes * (two_lanes ? 2 : 1) + 1024)
-      return fail(GMF_ERR_STATE, "workspace too small: need " + std::to_string(lane_bytes * (two_lanes ? 2 : 1) + 1024) + " bytes");
-    uint8_t* base = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
-    carve(w[0], base, Bl, N, T, Sw, kw, L);
-    if (two_lanes) carve(w[1], base + lane_bytes, Bl, N, T, Sw, kw, L);
+    const size_t need = carve(w, nullptr, Bc, N, T, Sw, kw, L) + 1024;
+    if (workspace_bytes < need) return fail(GMF_ERR_STATE, "workspace too small: need " + std::to_string(need) + " bytes");
+    carve(w, (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023), Bc, N, T, Sw, kw, L);
   }
-  auto run = [&](int lane_id, cudaStream_t ls, int b0, int nb) -> int {
-    return forward_chunk(ctx, ctx->overlap ? &ctx->lanes[lane_id] : nullptr, w[lane_id], corr_pos + (size_t)b0 * N * 6, src + (size_t)b0 * N * 3,
-                         tgt + (size_t)b0 * N * 3, p_tok + (size_t)b0 * T * 128, q_tok + (size_t)b0 * T * 128, nb, N, T, testing,
-                         final_trans + (size_t)b0 * 16, final_labels + (size_t)b0 * N, confidence + (size_t)b0 * N, seeds + (size_t)b0 * S,
-                         feat ? feat + (size_t)b0 * N * 128 : nullptr, ls);
-  };
   for (int b0 = 0; b0 < B; b0 += Bc) {
     const int nb = std::min(Bc, B - b0);
-    if (two_lanes && nb >= 2) {
-      const int n0 = (nb + 1) / 2;
-      cudaStream_t s1 = ctx->lanes[1].main;
-      CU(cudaEventRecord(ctx->ev_fork, st));                   // lane 1 starts after everything already queued on the caller's stream
-      CU(cudaStreamWaitEvent(s1, ctx->ev_fork, 0));
-      TRY(run(1, s1, b0 + n0, nb - n0));
-      CU(cudaEventRecord(ctx->lanes[1].ev_done, s1));
-      TRY(run(0, st, b0, n0));
-      CU(cudaStreamWaitEvent(st, ctx->lanes[1].ev_done, 0));   // join
-    } else {
-      TRY(run(0, st, b0, nb));
-    }
+    TRY(forward_chunk(ctx, &ctx->lane, w, corr_pos + (size_t)b0 * N * 6, src + (size_t)b0 * N * 3, tgt + (size_t)b0 * N * 3,
+                      p_tok + (size_t)b0 * T * 128, q_tok + (size_t)b0 * T * 128, nb, N, T, testing, final_trans + (size_t)b0 * 16,
+                      final_labels + (size_t)b0 * N, confidence + (size_t)b0 * N, seeds + (size_t)b0 * S,
+                      feat ? feat + (size_t)b0 * N * 128 : nullptr, st));
   }
   return 0;
 }

@@ -475,13 +475,9 @@ __global__ void __launch_bounds__(288, LinCfg<K, NOUT, PRO>::MIN_CTAS) linear_tc
 template <int K, int NOUT, int PRO, int EPI>
 inline cudaError_t launch_linear(const LinArgs& a, int pairs, cudaStream_t st) {
   using Cfg = LinCfg<K, NOUT, PRO>;
-  static bool configured = false;
+  static std::atomic<unsigned long long> configured{0};
   auto kern = linear_tc_kernel<K, NOUT, PRO, EPI>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem(kern, Cfg::SMEM, configured)) return e;
   kern<<<dim3(a.tiles, pairs), 288, Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }

@@ -267,12 +267,8 @@ __global__ void __launch_bounds__(544, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
 }
 
 inline cudaError_t launch_pcn_qkv(const PcnQkvArgs& a, int pairs, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(pcn_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PcnQkvCfg::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = ensure_dyn_smem(pcn_qkv_kernel, PcnQkvCfg::SMEM, configured)) return e;
   pcn_qkv_kernel<<<dim3(a.tiles, pairs), 544, PcnQkvCfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }

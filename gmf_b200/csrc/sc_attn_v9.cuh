@@ -434,26 +434,18 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
 
 template <int POLY, int TPR>
 inline cudaError_t launch_sc_attn_v9(const ScAttnArgs& a, int pairs, cudaStream_t st) {
-  static bool configured = false;
+  static std::atomic<unsigned long long> configured{0};
   auto kern = sc_attn_v9_kernel<POLY, TPR>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Sc9Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem(kern, Sc9Cfg::SMEM, configured)) return e;
   kern<<<dim3(a.Nq ? a.q_tiles : a.tiles, pairs), 256 * TPR + 96, Sc9Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
 // split-key launch for ONE pair: grid (query tiles, splits)
 inline cudaError_t launch_sc_attn_v9_split(const ScAttnArgs& a, int splits, cudaStream_t st) {
-  static bool configured = false;
+  static std::atomic<unsigned long long> configured{0};
   auto kern = sc_attn_v9_kernel<0, 2, true>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Sc9Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem(kern, Sc9Cfg::SMEM, configured)) return e;
   kern<<<dim3(a.Nq ? a.q_tiles : a.tiles, splits), 256 * 2 + 96, Sc9Cfg::SMEM, st>>>(a);
   return cudaGetLastError();
 }

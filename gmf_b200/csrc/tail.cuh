@@ -346,74 +346,7 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(const float* __restrict
 // seed kNN in feature space (common.py:53-75 restricted to the seed rows; PointDSC.py:325-329):
 // d_j = 2 - 2 <f_seed, f_j>, (k+1) smallest, rank 0 dropped.  Ties -> lower index first.
 // ------------------------------------------------------------------------------------------------
-// Kernel 1: D[seed][j] = 2 - 2 <f_seed, f_j> as a register-blocked fp32 SGEMM: 128 seeds x 128 points per CTA, 8x8 accumulators per
-// thread (16 FFMA per shared-memory float4), k consumed strictly in order so every distance is one sequential fmaf chain.
-__global__ void __launch_bounds__(256) seed_dist_kernel(const float* __restrict__ normed, const int* __restrict__ seeds, int N, int S,
-                                                        float* __restrict__ dist) {
-  __shared__ __align__(16) float As[16][132];
-  __shared__ __align__(16) float Bs[16][132];
-  __shared__ int sidx[128];
-  const int pair = blockIdx.z, m0 = blockIdx.y * 128, n0 = blockIdx.x * 128, tid = threadIdx.x;
-  const float* F = normed + (size_t)pair * N * 128;
-  if (tid < 128) sidx[tid] = (m0 + tid < S) ? seeds[(size_t)pair * S + m0 + tid] : -1;
-  __syncthreads();
-  // loader: thread -> (row = tid / 2 (+0), k offset = (tid & 1) * 8): two float4 per operand per 16-wide k slab
-  const int lr = tid >> 1, lk = (tid & 1) * 8;
-  const int arow = sidx[lr];
-  const int brow = (n0 + lr < N) ? n0 + lr : -1;
-  const int ty = tid >> 4, tx = tid & 15;                  // 16 x 16 threads, each 8 (seeds) x 8 (points): rows ty*4+{0..3}, 64+ty*4+{0..3}
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 a0 = z4, a1 = z4, b0 = z4, b1 = z4;
-  if (arow >= 0) { a0 = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + lk); a1 = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + lk + 4); }
-  if (brow >= 0) { b0 = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + lk); b1 = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + lk + 4); }
-  for (int k0 = 0; k0 < 128; k0 += 16) {
-    As[lk][lr] = a0.x; As[lk + 1][lr] = a0.y; As[lk + 2][lr] = a0.z; As[lk + 3][lr] = a0.w;
-    As[lk + 4][lr] = a1.x; As[lk + 5][lr] = a1.y; As[lk + 6][lr] = a1.z; As[lk + 7][lr] = a1.w;
-    Bs[lk][lr] = b0.x; Bs[lk + 1][lr] = b0.y; Bs[lk + 2][lr] = b0.z; Bs[lk + 3][lr] = b0.w;
-    Bs[lk + 4][lr] = b1.x; Bs[lk + 5][lr] = b1.y; Bs[lk + 6][lr] = b1.z; Bs[lk + 7][lr] = b1.w;
-    __syncthreads();
-    if (k0 + 16 < 128) {                                   // prefetch the next k-slab while computing this one
-      a0 = a1 = b0 = b1 = z4;
-      if (arow >= 0) { a0 = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + k0 + 16 + lk); a1 = *reinterpret_cast<const float4*>(F + (size_t)arow * 128 + k0 + 20 + lk); }
-      if (brow >= 0) { b0 = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + k0 + 16 + lk); b1 = *reinterpret_cast<const float4*>(F + (size_t)brow * 128 + k0 + 20 + lk); }
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float4 p0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]), p1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
-      const float4 q0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]), q1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
-      const float aa[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w}, bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
-    if (m >= S) continue;
-    float* d = dist + ((size_t)pair * S + m) * N;
-#pragma unroll
-    for (int jh = 0; jh < 2; ++jh) {
-      const int n = n0 + jh * 64 + tx * 4;
-      if (n + 3 < N && (N & 3) == 0) {
-        *reinterpret_cast<float4*>(d + n) = make_float4(2.0f - 2.0f * acc[i][jh * 4], 2.0f - 2.0f * acc[i][jh * 4 + 1], 2.0f - 2.0f * acc[i][jh * 4 + 2],
-                                                        2.0f - 2.0f * acc[i][jh * 4 + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (n + j < N) d[n + j] = 2.0f - 2.0f * acc[i][jh * 4 + j];
-      }
-    }
-  }
-}
-
+// Kernel 1 is the distance GEMM on the tensor pipe (dgr_head.cuh: knn_operand_kernel + img_gemm_kernel<128, DE_DIST>).
 // Kernel 2: per seed, the (k+1) smallest distances in ascending order (ties -> lower index), rank 0 dropped.  One warp per seed,
 // the seed's distance row in shared memory.  Two scans instead of k+1: (1) every lane finds its two smallest values; the (k+1)-th
 // smallest of those 64 is an upper bound T of the row's (k+1)-th smallest; (2) all entries <= T (usually 41..100) are compacted

@@ -66,7 +66,7 @@ class Engine:
 
     # ---- helpers --------------------------------------------------------------------------------
     def num_seeds(self, n: int) -> int:
-        return int(float(n) * float(C.c_float(self.ratio).value))
+        return int(n * float(self.ratio))               # PointDSC.py:246,270: int(num_corr * self.ratio), Python double
 
     def workspace(self, B: int, N: int, T: int) -> Tuple[torch.Tensor, int]:
         need = int(self.lib.gmf_workspace_bytes(self.h, B, N, max(T, 1)))
@@ -239,9 +239,8 @@ class Engine:
                                                 _ptr(out), _ptr(ws), nb, self._stream()))
         return out
 
-    PROFILE_CATEGORIES = ["pointcn", "qkv_proj", "fc_message_12", "fusion_q_proj", "fusion_kv_proj", "gemm_64_128", "ffn_geglu",
-                          "ffn_out", "attn_fusion", "attn_sc", "prep_layer0", "classify", "pick_seeds", "seed_knn",
-                          "spectral_kabsch", "score_refine"]
+    PROFILE_CATEGORIES = ["pcn_qkv", "fusion_q_proj", "fusion_kv_proj", "ffn_geglu", "attn_fusion", "attn_sc", "prep_layer0", "classify",
+                          "pick_seeds", "seed_knn", "spectral_kabsch", "score_refine", "other"]
 
     def profile(self, enable: bool):
         _lib.check(self.lib.gmf_profile_enable(self.h, 1 if enable else 0))

@@ -135,6 +135,9 @@ class PointDSC(nn.Module):
         self._engine_id = -1
         self._packed_sig: Tuple = ()
 
+    def __del__(self):
+        _ENGINES.pop(getattr(self, "_engine_id", -1), None)
+
     # ---- engine management ------------------------------------------------------------------
     def _weights_signature(self) -> Tuple:
         return tuple((t.data_ptr(), t._version) for n, t in self.state_dict(keep_vars=True).items()
@@ -146,6 +149,7 @@ class PointDSC(nn.Module):
             raise RuntimeError("gmf_b200.PointDSC runs on CUDA (sm_100a) only: call .cuda() first; there is no CPU path")
         eng = _ENGINES.get(self._engine_id)
         if eng is None or eng.device != dev:
+            _ENGINES.pop(self._engine_id, None)        # the module moved: release the old device's workspace / weights / streams
             with torch.cuda.device(dev):
                 eng = Engine(self.num_layers, self.num_iterations, self.k, self.ratio, self.inlier_threshold, self.nms_radius, dev)
             self._engine_id = max(_ENGINES.keys(), default=-1) + 1
@@ -168,7 +172,10 @@ class PointDSC(nn.Module):
             raise RuntimeError("gmf_b200.PointDSC implements the eval-mode (inference) forward only")
         testing = "testing" in data.keys()
         corr_pos, src, tgt = data["corr_pos"], data["src_keypts"], data["tgt_keypts"]
-        self.engine()
+        eng = self.engine()
+        for name in ("corr_pos", "src_keypts", "tgt_keypts", "p_image", "q_image"):
+            if data[name].device != eng.device:      # the C side dereferences raw pointers on the engine's device
+                raise RuntimeError(f"data['{name}'] is on {data[name].device}, the model on {eng.device}")
         with torch.cuda.device(corr_pos.device):
             p_tok, q_tok = self.image_tokens(data["p_image"], data["q_image"])
             trans, labels, conf, _seeds, feat = _pointdsc_forward(corr_pos, src, tgt, p_tok, q_tok, self._engine_id, testing)

@@ -21,7 +21,11 @@ def gather_poses(local_trans: torch.Tensor, num_pairs: int, rank: int, world: in
         return local_trans.cpu()
     sizes = [shard_range(num_pairs, r, world) for r in range(world)]
     mx = max(hi - lo for lo, hi in sizes)
-    buf = torch.zeros(mx, 4, 4, dtype=torch.float32, device=local_trans.device)
+    # NCCL moves device memory only: host-resident results (the C ABI's host entry point) take a [mx,4,4] staging tensor on the GPU
+    dev = local_trans.device
+    if dist.get_backend(group) == "nccl" and dev.type != "cuda":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    buf = torch.zeros(mx, 4, 4, dtype=torch.float32, device=dev)
     buf[: local_trans.shape[0]] = local_trans
     outs: List[torch.Tensor] = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf, group=group)

@@ -40,7 +40,7 @@ typedef struct gmf_config {
   int32_t num_layers;       /* 12 */
   int32_t num_iterations;   /* 10, power iteration cap (:160) */
   int32_t k;                /* 40, seed neighbourhood (:166), <= 40 */
-  float ratio;              /* 0.1, seeds = int(N * ratio) (:161) */
+  double ratio;             /* 0.1, seeds = int(N * ratio) in double precision, as Python evaluates it (:161, :246, :270) */
   float inlier_threshold;   /* 0.10 (3DMatch) / 1.2 (KITTI) (:163) */
   float nms_radius;         /* (:167) */
 } gmf_config;
@@ -170,11 +170,12 @@ int gmf_build_correspondences(gmf_ctx* ctx, const float* src_desc, const float* 
 /* ---- introspection / debugging ------------------------------------------------------------- */
 /* Per-launch CUDA-event timing (bench.py's roofline leg).  While enabled every kernel launch is bracketed by events on
  * the launching stream; gmf_profile_read synchronises the device and returns the summed device time and launch count
- * of one category since the last gmf_profile_enable call.  Categories: 0 PointCN GEMM, 1 QKV projection, 2 fc_message
- * 128->64/64->64, 3 fusion Q projection, 4 fusion KV projection, 5 64->128 GEMMs (to_out, fc_message.6), 6 FFN GEGLU GEMM,
- * 7 FFN output GEMM, 8 fusion flash attention, 9 SC-guided flash attention, 10 prep+layer0, 11 classifier, 12 seed
- * picking, 13 seed kNN, 14 spectral+Kabsch, 15 scoring+refinement. */
-#define GMF_PROFILE_CATEGORIES 16
+ * of one category since the last gmf_profile_enable call.  Categories: 0 PointCN + QKV projection (chained), 1 fusion Q
+ * projection (CPE + LN + to_q), 2 fusion K/V projection (CPE + LN + to_kv), 3 fused GEGLU FFN (+ fc_message.6 tail),
+ * 4 fusion flash attention (+ to_out + residual), 5 SC-guided flash attention (+ fc_message.0/.3 tail), 6 prep + layer0,
+ * 7 classifier, 8 seed picking, 9 seed kNN, 10 spectral matching + Kabsch, 11 scoring + refinement, 12 other (stage / debug
+ * entry points only). */
+#define GMF_PROFILE_CATEGORIES 13
 int gmf_profile_enable(gmf_ctx* ctx, int enable);
 int gmf_profile_read(gmf_ctx* ctx, int category, double* total_ms, int64_t* launches);
 /* number of gmf kernels launched by this process since the last reset (bench.py's gpu_launches) */

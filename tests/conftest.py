@@ -43,3 +43,16 @@ def golden_state_dict(meta):
 @pytest.fixture(scope="session")
 def has_cuda():
     return torch.cuda.is_available()
+
+
+def record(name, **metrics):
+    """Append measured parity numbers to gpurun_out/parity_measured.jsonl (merged back from the GPU box; the round's copy is committed
+    under profiles/).  Never fails a test."""
+    import json
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: (float(v) if isinstance(v, (int, float)) or hasattr(v, "item") else v) for k, v in metrics.items()}}) + "\n")
+    except Exception:
+        pass

@@ -2,8 +2,9 @@
 UNMODIFIED reference `PerceiverIO` (oracle/gen_golden_dgr.py); the CUDA path (C ABI gmf_dgr_head_*) is compared with the oracle.
 
 Tolerance of the CUDA path: the kernels multiply in TF32 (linear layers) and bf16 (attention operands) with fp32 accumulation;
-outputs have |x| up to ~10 (std ~1), and the bound used is 2e-2 abs (BASELINE.json north_star: logits 1e-2 abs refers to the
-PointDSC classifier; this head feeds a BN + ReLU sparse-conv block, resunet_new.py:662-666), with the mean error held below 2e-3."""
+outputs have |x| up to ~10 (std ~1).  The bound is what the kernels measure plus margin: 6e-3 abs (measured max 1.7e-3 .. 3e-3 over
+the cfg#5 shapes, written to gpurun_out/parity_measured.jsonl) and 6e-4 mean — tighter than the 1e-2 abs BASELINE.json states for
+the PointDSC logits, although this head only feeds a BN + ReLU sparse-conv block (resunet_new.py:662-666)."""
 import ctypes as C
 import os
 
@@ -11,13 +12,13 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT
+from conftest import ROOT, record
 from gmf_b200.dgr_head import dgr_head_shapes
 from gmf_b200.synth import synth_state_dict, synth_tokens
 from oracle.dgr_head_oracle import dgr_head_forward, synth_latents
 
 GOLDEN = ["dgr_head_m200_t300", "dgr_head_m130_t257_nope"]
-ABS_TOL, MEAN_TOL = 2e-2, 2e-3
+ABS_TOL, MEAN_TOL = 6e-3, 6e-4
 
 
 def load(name):
@@ -75,8 +76,10 @@ def test_module_has_no_cpu_fallback():
 
 
 # ------------------------------------------------------------------------------------------------ GPU
-def _check(out, ref):
+def _check(out, ref, tag=None):
     err = (out.double().cpu() - ref.double()).abs()
+    if tag:
+        record(tag, max_abs_err=float(err.max()), mean_abs_err=float(err.mean()), out_abs_max=float(ref.abs().max()))
     assert torch.isfinite(out).all()
     assert float(err.max()) <= ABS_TOL, float(err.max())
     assert float(err.mean()) <= MEAN_TOL, float(err.mean())
@@ -107,9 +110,26 @@ def test_cuda_head_matches_oracle_cfg5_shapes(m_rows, t_ctx):
     eng = DgrHeadEngine(0, pe=True)
     eng.load_state_dict(sd)
     out = eng.forward(x.cuda(), ctx.cuda())
-    _check(out, ref)
+    _check(out, ref, f"dgr_head_m{m_rows}_t{t_ctx}")
     out2 = eng.forward(x.cuda(), ctx.cuda())                 # workspace reuse, cached neutral features
     assert torch.equal(out, out2)
+
+
+@pytest.mark.gpu
+def test_cuda_head_one_engine_varying_row_counts():
+    """The reference calls the head once per batch with M = number of active bottleneck voxels, which changes every call while T stays
+    fixed: one engine must serve a shrinking / growing M (workspace offsets move, the neutral distance features must stay valid)."""
+    from gmf_b200.dgr_head import DgrHeadEngine
+    sd = synth_state_dict(dgr_head_shapes(True), seed=9)
+    eng = DgrHeadEngine(0, pe=True)
+    eng.load_state_dict(sd)
+    ctx = synth_tokens(1, 4800, 32)[0]
+    torch.set_num_threads(8)
+    for m_rows, t_ctx in [(2048, 4800), (1500, 4800), (300, 4800), (2500, 4800), (640, 300), (5000, 300), (1500, 4800)]:
+        x = synth_latents(m_rows, 100 + m_rows)
+        ref = dgr_head_forward(sd, x, ctx[:t_ctx], pe=True, dtype=torch.float64)
+        out = eng.forward(x.cuda(), ctx[:t_ctx].contiguous().cuda())
+        _check(out, ref)
 
 
 @pytest.mark.gpu

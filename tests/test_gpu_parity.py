@@ -7,8 +7,9 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import GOLDEN_CASES, golden_cfg, golden_state_dict, load_golden
+from conftest import GOLDEN_CASES, golden_cfg, golden_state_dict, load_golden, record
 from oracle import pointdsc_oracle as O
+from oracle import ref_shim
 
 pytestmark = pytest.mark.gpu
 
@@ -190,8 +191,15 @@ def test_seed_hypotheses_teacher_forced(g384):
     trans, knn, w = eng.seed_hypotheses(nf.cuda(), src.cuda(), tgt.cuda(), fx["seeds"].int().cuda())
     cap = {}
     O.seed_hypotheses(nf, src, tgt, fx["seeds"], cfg["k"], sd["sigma"], sd["sigma_spat"], cfg["num_iterations"], cap)
-    same = (knn.cpu().long() == cap["knn_idx"]).all(-1)[0]
-    assert same.float().mean() > 0.9                       # fp32 dot-product near-ties may swap a neighbour
+    got, want = knn.cpu().long()[0], cap["knn_idx"][0]
+    same = (got == want).all(-1)
+    # every differing row must be a near-tie: position by position the neighbours' exact (fp64) distances to the seed agree to within the
+    # fp32 summation-order noise of a 128-term dot product, i.e. only (near-)equidistant points are swapped / exchanged at the k-th rank
+    d = 2.0 - 2.0 * nf[0][fx["seeds"][0]].double() @ nf[0].double().T                 # [S, N]
+    gap = (d.gather(1, got) - d.gather(1, want)).abs().max(-1)[0]
+    record("seed_knn_teacher_forced", rows=int(same.numel()), rows_differing=int((~same).sum()), max_distance_gap_of_differing_rows=float(gap.max()))
+    assert float(gap.max()) <= 2e-6, float(gap.max())
+    assert same.float().mean() > 0.9
     assert (w.cpu()[0][same] - cap["seed_weight"][0][same]).abs().max() < 1e-5
     assert (trans.cpu()[0][same] - fx["seed_trans"][0][same]).abs().max() < 1e-4
 
@@ -227,6 +235,72 @@ def test_rigid_transform_3d_matches_oracle_and_degenerate_cases():
 
 
 # ------------------------------------------------------------------ end to end
+# north_star: inlier logits within 1e-2 abs.  The KITTI-shaped cases feed un-normalised 60 m coordinates through random-init weights, which
+# gives logits of magnitude ~10 (3DMatch-shaped: ~1.6); the measured deviations are written to gpurun_out/parity_measured.jsonl and
+# discussed in DESIGN.md section 2.
+LOGIT_TOL = {"l2_n384_3dmatch": 1e-2, "l12_n512_3dmatch": 1e-2, "l2_n300_kitti": 1e-2}
+
+
+def _reference_or_oracle(sd, cfg, args):
+    """final pose / labels from the UNMODIFIED reference (oracle/_ref or /root/reference) when it is available, logits + seeds from the
+    oracle port (pinned to the reference at 2e-5 by tests/test_oracle_golden.py)."""
+    port = O.forward_testing(sd, cfg, *args, capture=True)
+    if ref_shim.available():
+        ref = ref_shim.forward_tokens(ref_shim.build_reference_hot_path(sd, cfg), *args)
+        # the port restates the reference: same pose to fp32 summation-order noise
+        assert float(O.rotation_error_deg(port["final_trans"][:, :3, :3], ref["final_trans"][:, :3, :3]).max()) < 1e-3
+        return port, ref, ref_shim.source()
+    return port, port, "oracle port"
+
+
+def _full_size_parity(tag, n, t, layers, extent, thr, inlier_ratio, noise, seed, plain_init, pose_gate=True):
+    from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
+    from gmf_b200.weights import hot_path_spec
+    cfg = dict(O.DEFAULT_CFG, num_layers=layers, inlier_threshold=thr, nms_radius=thr, sigma_d=thr)
+    sd = synth_state_dict(hot_path_spec(layers), seed=0, plain_init=plain_init)
+    sd["sigma_spat"] = torch.tensor([thr])
+    eng = make_engine(cfg, sd)
+    pr = synth_pairs(1, n, seed=seed, extent=extent, inlier_ratio=inlier_ratio, noise=noise)
+    args = [pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], synth_tokens(1, t, 1), synth_tokens(1, t, 2)]
+    torch.set_num_threads(os.cpu_count() or 8)
+    port, ref, what = _reference_or_oracle(sd, cfg, args)
+    out = eng.forward(*[x.cuda() for x in args], testing=True)
+    dl = float((out["confidence"].cpu() - port["confidence"]).abs().max())
+    tr = out["final_trans"].cpu()
+    re = float(O.rotation_error_deg(tr[:, :3, :3], ref["final_trans"][:, :3, :3]).max())
+    te = float((tr[:, :3, 3] - ref["final_trans"][:, :3, 3]).norm(dim=-1).max())
+    lab_diff = float((out["final_labels"].cpu() != ref["final_labels"]).float().mean())
+    record(tag, checker=what, n=n, t=t, layers=layers, extent=extent, max_abs_dlogit=dl, logit_abs_max=float(port["confidence"].abs().max()),
+           rot_err_deg=re, trans_err_mm=te * 1e3, label_mismatch_frac=lab_diff)
+    # teacher-forced seed picking on the checker's logits: identical except exact ties
+    seeds = eng.pick_seeds(pr["src_keypts"].cuda(), port["confidence"].cuda(), use_nms=True).cpu().long()
+    d = torch.cdist(pr["src_keypts"][0], pr["src_keypts"][0])
+    conf0 = port["confidence"][0]
+    is_max = torch.ones(n, dtype=torch.bool)
+    for i0 in range(0, n, 1000):                              # rel[i, j] = conf[j] <= conf[i] or d[i, j] >= R, min over j (PointDSC.py:276-278), in blocks
+        blk = (conf0[None, :] <= conf0[i0:i0 + 1000, None]) | (d[i0:i0 + 1000] >= cfg["nms_radius"])
+        is_max[i0:i0 + 1000] = blk.all(-1)
+    key = conf0 * is_max.float()
+    assert _tie_groups_equal(seeds[0], port["capture"][0]["seeds"].reshape(-1), key)
+    return dl, re, te, lab_diff
+
+
+def test_cfg3_kitti_shape_full_size_matches_reference():
+    """BASELINE.json configs[2]: KITTI shape (60 m extent, sigma_d = tau = nms = 1.2, configs/test_Kitti_config.json), N = 5000, 4800 image
+    tokens, 12 layers — against the reference itself (oracle/_ref) / the oracle port on the same inputs and weights."""
+    dl, re, te, lab = _full_size_parity("cfg3_kitti_n5000_t4800_l12", 5000, 4800, 12, 60.0, 1.2, 0.30, 0.04, 301, True)
+    assert re < 0.01 and te < 1e-3 and lab < 0.002
+    assert dl < 1e-2, dl
+
+
+def test_cfg4_lomatch_n10000_matches_reference():
+    """BASELINE.json configs[3]: 10000 correspondences, 5 % inliers, 4800 image tokens, 12 layers — same bar (the checker needs ~4 s and
+    three 400 MB N x N matrices on the host; the CUDA path never materialises them)."""
+    dl, re, te, lab = _full_size_parity("cfg4_lomatch_n10000_t4800_l12", 10000, 4800, 12, 3.0, 0.10, 0.05, 0.002, 401, True)
+    assert re < 0.01 and te < 1e-3 and lab < 0.002
+    assert dl < 1e-2, dl
+
+
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_forward_matches_reference_golden(name):
     meta, fx = load_golden(name)
@@ -235,13 +309,12 @@ def test_forward_matches_reference_golden(name):
     out = eng.forward(fx["corr_pos"].cuda(), fx["src"].cuda(), fx["tgt"].cuda(), fx["p_tok"].cuda(), fx["q_tok"].cuda(),
                       testing=True, want_feat=True)
     conf = out["confidence"].cpu()
-    scale = max(1.0, float(fx["confidence"].abs().max()))
-    # 1e-2 abs on O(1) logits (3DMatch-shaped); the KITTI-shaped fixture has O(10) logits from un-normalised 60 m inputs,
-    # so the same bf16/tf32 operand noise is bounded relative to the logit scale there
-    assert (conf - fx["confidence"]).abs().max() < 1e-2 * scale
+    dl = float((conf - fx["confidence"]).abs().max())
     re = float(O.rotation_error_deg(out["final_trans"].cpu()[:, :3, :3], fx["final_trans"][:, :3, :3]).max())
     te = float((out["final_trans"].cpu()[:, :3, 3] - fx["final_trans"][:, :3, 3]).norm(dim=-1).max())
-    assert re < 0.01 and te < 1e-3 * (meta["extent"] / 3.0)
+    record("golden_" + name, max_abs_dlogit=dl, logit_abs_max=float(fx["confidence"].abs().max()), rot_err_deg=re, trans_err_mm=te * 1e3)
+    assert dl < LOGIT_TOL[name], dl
+    assert re < 0.01 and te < 1e-3                          # north_star: 0.01 deg, 1 mm (absolute, also at the 60 m KITTI extent)
     assert torch.equal(out["final_labels"].cpu(), fx["final_labels"])
     assert len(set(out["seeds"][0].tolist()) & set(fx["seeds"][0].tolist())) >= 0.85 * fx["seeds"].shape[1]
 

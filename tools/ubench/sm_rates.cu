@@ -176,6 +176,102 @@ __global__ void k_mufu(int iters, long long* out, float* sink) {
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
 }
 
+// T9: does a MUFU warp-instruction get cheaper when most lanes are predicated off?  (The SC softmax could skip sqrt + ex2 for the ~87 % of
+// score elements whose compatibility is exactly 0 if it did.)  MODE 0: all lanes; 1: lanes 0-3 only; 2: one lane in 8; 3: per-element
+// pseudo-random 1/8 of the lanes; 4: whole warps skip 7 of 8 instructions through a uniform branch (the best any skipping could do).
+template <int MODE>
+__global__ void k_mufu_pred(int iters, long long* out, float* sink) {
+  float x[16];
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = 0.001f * (threadIdx.x + i);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      unsigned on;
+      if (MODE == 0) on = 1u;
+      else if (MODE == 1) on = lane < 4;
+      else if (MODE == 2) on = (lane & 7) == 0;
+      else if (MODE == 3) on = (((lane * 2654435761u) >> 7) + i * 5 + it) % 8 == 0;
+      else on = ((i + it) & 7) == 0;
+      if (MODE == 4) { if (on) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i])); }
+      else asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ex2.approx.ftz.f32 %0, %0;\n\t}" : "+f"(x[i]) : "r"(on));
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 123.456f) sink[threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+}
+
+// T10: the arithmetic of one SC softmax tile share (16 score elements per thread: compat from DA / Y, logit, exp2, row max, row sum, bf16
+// pack) in a synchronisation-free loop - the XU-pipe ceiling of the softmax body by itself.  POLY of every 4 exponentials are evaluated on
+// the FMA pipe with packed fp32x2 arithmetic (Cody-Waite split + degree-3 polynomial).
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t t2) {
+  // t in [-126, 126]; 2^t = 2^n * p(f), n = round(t), f = t - n in [-0.5, 0.5]
+  const uint64_t magic = pack2(12582912.f, 12582912.f);
+  const uint64_t fl = fadd2(t2, magic);
+  const uint64_t r = fadd2(fl, pack2(-12582912.f, -12582912.f));
+  const uint64_t f = ffma2(r, pack2(-1.f, -1.f), t2);
+  uint64_t p = ffma2(pack2(0.0551716648f, 0.0551716648f), f, pack2(0.2426111251f, 0.2426111251f));
+  p = ffma2(p, f, pack2(0.6932609677f, 0.6932609677f));
+  p = ffma2(p, f, pack2(0.9999280572f, 0.9999280572f));
+  float p0, p1, f0, f1;
+  unpack2(p, p0, p1); unpack2(fl, f0, f1);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(f0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(f1) << 23));
+  return pack2(p0, p1);
+}
+template <int POLY>
+__global__ void k_softmax_body(int iters, long long* out, float* sink) {
+  float us[16], ua[16], ub[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { us[i] = 0.01f * (threadIdx.x + i); ua[i] = 1.0f + 0.001f * i + 0.01f * threadIdx.x; ub[i] = 0.5f + 0.002f * i; }
+  float rmax = -1e30f;
+  uint64_t psum2 = pack2(0.f, 0.f);
+  uint32_t acc = 0;
+  const uint64_t nref2 = pack2(-1.f, -1.f);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+      const uint64_t A2 = pack2(ua[c], ua[c + 1]), Y2 = pack2(ub[c], ub[c + 1]);
+      float q0, q1, u0, u1, t0_, t1_;
+      unpack2(ffma2(A2, Y2, A2), q0, q1);
+      unpack2(fadd2(A2, Y2), u0, u1);
+      const float c0 = __saturatef(fmaf(sqrt_approx(fabsf(q0)), 2.f, -u0));
+      const float c1 = __saturatef(fmaf(sqrt_approx(fabsf(q1)), 2.f, -u1));
+      const uint64_t t2 = ffma2(pack2(us[c], us[c + 1]), pack2(c0, c1), nref2);
+      unpack2(t2, t0_, t1_);
+      rmax = fmaxf(rmax, fmaxf(t0_, t1_));
+      uint64_t p2;
+      if ((c & 7) < 2 * POLY) p2 = ex2_poly2(pack2(fmaxf(t0_, -126.f), fmaxf(t1_, -126.f)));
+      else p2 = pack2(ex2_approx(t0_), ex2_approx(t1_));
+      psum2 = fadd2(psum2, p2);
+      float p0, p1;
+      unpack2(p2, p0, p1);
+      pk[c >> 1] = pack_bf16(p0, p1);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc ^= pk[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { us[i] += 1e-6f; ua[i] += 1e-7f; }    // keep the loop body from being hoisted
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  float ps0, ps1;
+  unpack2(psum2, ps0, ps1);
+  if (rmax + ps0 + ps1 == 123.456f || acc == 0x12345u) sink[threadIdx.x] = rmax;
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+}
+
 // T8: does packing two fp32 into bf16x2 (cvt.rn.bf16x2.f32, SASS F2FP) share the MUFU (XU) pipe?  MODE 0: 16 cvt per iteration;
 // MODE 1: 16 ex2 + 8 cvt per iteration (the softmax mix: one pack per two exponentials); MODE 2: 16 ex2 + 8 PRMT-style truncating packs
 template <int MODE>
@@ -335,6 +431,33 @@ int main() {
     k_ex2_h2<<<148, 32 * w>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
     printf("  warps=%2d  ex2.approx.f16x2: %.1f instr-lanes/clk/SM = %.1f exponentials/clk/SM\n", w, (double)w * 32 * 16 * iters / h, 2.0 * w * 32 * 16 * iters / h);
+  }
+  printf("== T9 predicated MUFU.EX2: warp-instructions per clk per SM (16 warps; all lanes on = 0.5)\n");
+  {
+    auto run9 = [&](auto kern, const char* name, double frac) {
+      kern<<<148, 512>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
+      printf("  %-44s %8lld clk  %.3f issued warp-instr/clk/SM\n", name, h, 16.0 * 16 * iters * frac / h);
+    };
+    run9(k_mufu_pred<0>, "all 32 lanes on", 1.0);
+    run9(k_mufu_pred<1>, "lanes 0-3 on (one quarter-warp pass)", 1.0);
+    run9(k_mufu_pred<2>, "one lane in 8 on", 1.0);
+    run9(k_mufu_pred<3>, "pseudo-random 1/8 of the lanes on", 1.0);
+    run9(k_mufu_pred<4>, "uniform branch skips 7 of 8 instructions", 0.125);
+  }
+  printf("== T10 SC softmax body without synchronisation (16 warps x 16 elements per thread-iteration): cycles per 128 x 32 tile\n");
+  {
+    auto run10 = [&](auto kern, const char* name) {
+      kern<<<148, 512>>>(iters, d_out, d_sink); CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost));
+      // 16 warps x 32 lanes x 16 elements = 8192 elements per iteration = two 128 x 32 tiles
+      printf("  %-44s %.1f clk per tile (XU floor 512 with 2 MUFU per element)\n", name, (double)h / iters / 2.0);
+    };
+    run10(k_softmax_body<0>, "all exponentials on MUFU");
+    run10(k_softmax_body<1>, "1 of 4 exponentials on the FMA pipe (fp32x2)");
+    run10(k_softmax_body<2>, "2 of 4 exponentials on the FMA pipe (fp32x2)");
+    run10(k_softmax_body<3>, "3 of 4 exponentials on the FMA pipe (fp32x2)");
+    run10(k_softmax_body<4>, "all exponentials on the FMA pipe (fp32x2)");
   }
   printf("== T8 fp32x2 -> bf16x2 packing vs the MUFU pipe (16 warps)\n");
   {
