@@ -9,6 +9,7 @@
 //   packed weights), so the consumer fetches a whole tile with ONE bulk-async copy.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
@@ -49,6 +50,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking phase test (mbarrier.test_wait never suspends the thread).  Used to start a barrier poll BEFORE a block of arithmetic and
+// to consume the answer after it: a completed-phase wait still costs 70-90 cycles of latency when it sits on the critical path.
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug traps (launch failure reported through the C-ABI) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -75,6 +89,96 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, u
   if (!okb) mbar_wait(bar_b, parity_b);
 }
 
+// ---- the same operations on 32-bit shared-window addresses --------------------------------------------------------------------
+// `smem_u32(ptr)` on a pointer that went through generic arithmetic makes the compiler re-derive the shared window base (S2UR
+// SR_CgaCtaId + ULEA + UMOV + LEA, ~10 instructions and a slow special-register read) in front of EVERY mbarrier instruction; the
+// attention kernels execute ~6 barrier operations per warp and key tile, and ncu's source page charged as many issue slots to that
+// glue as to the softmax arithmetic.  Hot loops therefore take the barrier block's address ONCE (`const uint32_t bar0 = smem_u32(bars)`)
+// and address barrier i as `bar0 + 8 * i`.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  long long t0 = clock64();
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;                   // the common case costs two instructions
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);                              // bounded spin out of line: a protocol bug traps instead of hanging the GPU
+}
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t parity_a, uint32_t bar_b, uint32_t parity_b) {
+  uint32_t oka, okb;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "selp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(oka), "=r"(okb)
+      : "r"(bar_a), "r"(parity_a), "r"(bar_b), "r"(parity_b)
+      : "memory");
+  if (!oka) mbar_wait(bar_a, parity_a);
+  if (!okb) mbar_wait(bar_b, parity_b);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint32_t bar, uint32_t bytes, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_p(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "r"(on)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// An "array of mbarriers" held as a 32-bit shared address: drop-in for `uint64_t*` in kernels written against the pointer helpers
+// (`&bars[i]`, `bars + n`, `bars` itself as the first barrier) that resolves to the address-based overloads above.
+struct BarArr {
+  uint32_t base;
+  struct Elem {
+    uint32_t addr;
+    __device__ __forceinline__ uint32_t operator&() const { return addr; }
+  };
+  __device__ __forceinline__ Elem operator[](int i) const { return Elem{base + 8u * (uint32_t)i}; }
+  __device__ __forceinline__ BarArr operator+(int i) const { return BarArr{base + 8u * (uint32_t)i}; }
+  __device__ __forceinline__ operator uint32_t() const { return base; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
 // ------------------------------------------------------------------------------------------------
@@ -82,6 +186,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
                : "memory");
 }
 // bulk async copy shared -> global (TMA store); the issuing thread commits and waits until the source has been read
@@ -206,6 +316,22 @@ __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem,
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_p(uint32_t bar, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_p(void* dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "r"(on)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_p(uint64_t* bar, uint32_t on) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
@@ -319,6 +445,13 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+// Attention Q / K operands are fp16 (11-bit significand, same tensor rate as bf16 in kind::f16): spatial-consistency logits reach
+// ~100 on KITTI-scale inputs, where bf16's 8-bit significand alone costs 2e-2 on the final inlier logits (tools/probe_precision.py);
+// P (range 2^+-80 with the fixed softmax reference) and V stay bf16.  Values saturate at the fp16 maximum.
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  const __half2 t = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&t);
 }
 __device__ __forceinline__ float ex2_approx(float x) {
 #if defined(GMF_SC_DBG) && GMF_SC_DBG == 2

@@ -377,10 +377,10 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 pk;
-            pk.x = pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]));
-            pk.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-            pk.z = pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-            pk.w = pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            pk.x = pack_f16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]));
+            pk.y = pack_f16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+            pk.z = pack_f16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+            pk.w = pack_f16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
             *reinterpret_cast<uint4*>(img + swz_off(r, cc0 + j)) = pk;
           }
         } else {

@@ -27,9 +27,9 @@ struct Fa2Cfg {
 };
 
 struct Fa2Mma {
-  uint32_t tmem, idesc, leader;
+  uint32_t tmem, idesc, idesc_s, leader;
   uint64_t k_desc0, v_desc0;
-  uint64_t *k_full, *k_empty, *v_full, *v_empty, *s_full, *s_free, *p_ready, *pv_done, *o_full;
+  BarArr k_full, k_empty, v_full, v_empty, s_full, s_free, p_ready, pv_done, o_full;   // mbarriers by 32-bit shared address (common.cuh)
   int nt, t;                                                   // key tiles, this issuer's row tile
 };
 
@@ -44,7 +44,7 @@ __device__ __forceinline__ void fa2_issue_s(const Fa2Mma& m, uint32_t ring_parit
     const uint32_t qcol = m.tmem + Cfg::COL_Q + (uint32_t)m.t * 32u;
     const uint64_t kd = umma_desc_adv(m.k_desc0, T * Cfg::K_BYTES);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) tc_mma_bf16_ts(col, qcol + ks * 8, umma_desc_adv(kd, ks * 32), m.idesc, ks ? 1u : 0u);
+    for (int ks = 0; ks < 4; ++ks) tc_mma_bf16_ts(col, qcol + ks * 8, umma_desc_adv(kd, ks * 32), m.idesc_s, ks ? 1u : 0u);
     tc_commit(&m.s_full[2 * m.t + (T & 1)]);
     tc_commit(&m.k_empty[T]);
   }
@@ -91,20 +91,20 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   float* sStg = (float*)(sWo + Cfg::WO_BYTES);           // [16 warps][32][32]
   float* sX = (float*)((uint8_t*)sStg + Cfg::STG_BYTES); // [2][2][2][128]
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
-  uint64_t* q_full = bars;            // [2]
-  uint64_t* k_full = bars + 2;        // [NR]
-  uint64_t* k_empty = k_full + NR;    // [NR]
-  uint64_t* v_full = k_empty + NR;    // [NR]
-  uint64_t* v_empty = v_full + NR;    // [NR]
-  uint64_t* s_full = v_empty + NR;    // [2][2]
-  uint64_t* s_free = s_full + 4;      // [2][2]
-  uint64_t* p_ready = s_free + 4;     // [2]
-  uint64_t* pv_done = p_ready + 2;    // [2]
-  uint64_t* o_full = pv_done + 2;     // [2]
-  uint64_t* on_ready = o_full + 2;    // [2] normalised, tf32-rounded O written back to TMEM
-  uint64_t* x_full = on_ready + 2;    // [2] O . Wo^T complete
-  uint64_t* wo_full = x_full + 2;     // 1
-  uint32_t* tmem_slot = (uint32_t*)(wo_full + 1);
+  const BarArr q_full{smem_u32(bars)};   // [2]  every barrier below is "this address + constant" (no shared-window re-derivation per operation)
+  const BarArr k_full = q_full + 2;      // [NR]
+  const BarArr k_empty = k_full + NR;    // [NR]
+  const BarArr v_full = k_empty + NR;    // [NR]
+  const BarArr v_empty = v_full + NR;    // [NR]
+  const BarArr s_full = v_empty + NR;    // [2][2]
+  const BarArr s_free = s_full + 4;      // [2][2]
+  const BarArr p_ready = s_free + 4;     // [2]
+  const BarArr pv_done = p_ready + 2;    // [2]
+  const BarArr o_full = pv_done + 2;     // [2]
+  const BarArr on_ready = o_full + 2;    // [2] normalised, tf32-rounded O written back to TMEM
+  const BarArr x_full = on_ready + 2;    // [2] O . Wo^T complete
+  const BarArr wo_full = x_full + 2;     // 1
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 + 4 * NR + 4 + 4 + 2 + 2 + 2 + 2 + 2 + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pair = blockIdx.y;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
       Fa2Mma m;
       m.t = (warp - 17) & 1;
       const bool is_pv = warp < 19;
-      m.tmem = __shfl_sync(0xffffffffu, tmem, 0); m.idesc = umma_idesc(128, BN, kFmtBF16);
+      m.tmem = __shfl_sync(0xffffffffu, tmem, 0); m.idesc = umma_idesc(128, BN, kFmtBF16); m.idesc_s = umma_idesc(128, BN, kFmtF16);   // S = Q K^T on fp16 operands, P V on bf16
       m.leader = elect_one() ? 1u : 0u;
       m.k_desc0 = umma_desc_sw128(smem_u32(sK)); m.v_desc0 = umma_desc_sw128(smem_u32(sV));
       m.k_full = k_full; m.k_empty = k_empty; m.v_full = v_full; m.v_empty = v_empty; m.s_full = s_full; m.s_free = s_free;

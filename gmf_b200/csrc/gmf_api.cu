@@ -432,10 +432,23 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
   sa.q_t = w.qs; sa.k_t = w.ks; sa.vt_t = w.vts; sa.aq_t = w.aq; sa.bd_t = w.bd; sa.out = msg;
   sa.N = N; sa.tiles = cdiv(N, 128);
   if (fused_m2) { sa.fc1_w = lw.fc1_w; sa.fc1_b = lw.fc1_b; sa.fc2_w = lw.fc2_w; sa.fc2_b = lw.fc2_b; sa.m2_out = fused_m2; }
+#ifdef GMF_SC_TRACE
+  static int n_sc = 0;
+  const bool do_trace = (++n_sc == 30) && B >= 2;
+  if (do_trace) { cudaMalloc(&sa.trace, 7 * 64 * 8 * 8); cudaMemsetAsync(sa.trace, 0, 7 * 64 * 8 * 8, st); }
+#endif
   ProfScope ps(CAT_ATTN_SC, st);
   cudaError_t e = launch_sc_any(ctx, sa, B, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail_cuda(e, "sc_attn_v9 launch");
+#ifdef GMF_SC_TRACE
+  if (do_trace) {
+    cudaStreamSynchronize(st);
+    static long long h[7 * 64 * 8];
+    cudaMemcpy(h, sa.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen("gpurun_out/sc_trace.bin", "wb")) { fwrite(h, 1, sizeof(h), f); fclose(f); }
+  }
+#endif
   return 0;
 }
 
@@ -611,7 +624,8 @@ __global__ void pack_tiles_kernel(const float* __restrict__ src, int L, int D, i
   size_t off;
   if (!transpose) off = (size_t)(c >> 6) * 16384 + swz_off(r, (c & 63) >> 3) + (c & 7) * 2;
   else off = (size_t)(r >> 6) * (D * 128) + swz_off(c, (r & 63) >> 3) + (r & 7) * 2;
-  *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16_rn(v);
+  if (transpose) *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16_rn(v);                 // V^T: bf16
+  else *reinterpret_cast<__half*>(base + off) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));     // Q / K: fp16
 }
 
 }  // namespace

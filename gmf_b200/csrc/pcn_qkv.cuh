@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(544, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 pk;
-            pk.x = pack_bf16(o[8 * j], o[8 * j + 1]); pk.y = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
-            pk.z = pack_bf16(o[8 * j + 4], o[8 * j + 5]); pk.w = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
+            pk.x = pack_f16(o[8 * j], o[8 * j + 1]); pk.y = pack_f16(o[8 * j + 2], o[8 * j + 3]);
+            pk.z = pack_f16(o[8 * j + 4], o[8 * j + 5]); pk.w = pack_f16(o[8 * j + 6], o[8 * j + 7]);
             *reinterpret_cast<uint4*>(dst + swz_off(r, cc0 + j)) = pk;
           }
         } else {

@@ -34,20 +34,33 @@ struct Sc9Cfg {
   static constexpr int XCH_BYTES = 2 * 4 * 128 * 4;       // [max | sum][group x row part][row]
   static constexpr int AQ_BYTES = 128 * 64 * 2;
   static constexpr int FC_BYTES = (64 * 128 + 64 * 64) * 4;                                    // fc_message.0 / .3 weights (tf32) for the fused tail
-  static constexpr int SMEM = 1024 + AQ_BYTES + NS * KSTAGE_BYTES + NV * V_BYTES + FC_BYTES + XCH_BYTES + 256;
+  static constexpr int SMEM = 1024 + AQ_BYTES + NS * KSTAGE_BYTES + NV * V_BYTES + FC_BYTES + XCH_BYTES + 512;
   static constexpr int COL_Q = 288, COL_P = 352, COL_O = 384;   // P: 16 columns per softmax group
   static constexpr float WINDOW = 80.f;
+  // mbarriers: barrier i lives at bar0 + 8 i (bar0 = 32-bit shared address of the block, taken once per thread)
+  static constexpr int B_Q = 0, B_KF = 1, B_KE = B_KF + NS, B_VF = B_KE + NS, B_VE = B_VF + NV, B_SF = B_VE + NV, B_SR = B_SF + 6, B_PR = B_SR + 6,
+                       B_PD = B_PR + 2, B_AQ = B_PD + 2, B_O = B_AQ + 1, B_ON = B_O + 1, B_H = B_ON + 1, B_X1 = B_H + 1, B_X2 = B_X1 + 1, B_W = B_X2 + 1,
+                       B_COUNT = B_W + 1;
+  static_assert(B_COUNT * 8 + 16 <= 512, "barrier block overflows its shared-memory slot");
 };
+__device__ __forceinline__ constexpr uint32_t sc9_bar(uint32_t bar0, int idx) { return bar0 + 8u * (uint32_t)idx; }
 
 
 // Loop-invariant operands of the MMA issuer.  The issue loop is unrolled over its period (6 tiles = 3 ring stages x 2 sub-tiles =
 // 2 x 3 score buffers) so that every descriptor is "uniform base + compile-time constant": with run-time ring indices the
 // compiler built each descriptor in vector registers and moved it to the uniform file (R2UR) — ~80 issue cycles per MMA, which
 // made the single issuing warp the bottleneck of the whole kernel (gen-9a profile: softmax warps 51 % idle on s_full).
+#ifdef GMF_SC_TRACE
+#define SC_TR(ptr, role, tile, k) do { if ((ptr) && (tile) < 64 && (threadIdx.x & 31) == 0) (ptr)[((role) * 64 + (tile)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define SC_TR(ptr, role, tile, k) do {} while (0)
+#endif
+
 struct Sc9Mma {
-  uint32_t tmem, idesc_s, idesc_o, leader;
+  long long* trc;
+  uint32_t tmem, idesc_s, idesc_d, idesc_o, leader;
   uint64_t k_desc0, v_desc0, aq_desc;
-  uint64_t *k_full, *k_empty, *v_full, *v_empty, *s_full, *s_free, *p_ready, *pv_done, *o_full;
+  uint32_t bar0;
   int nt;
 };
 
@@ -56,7 +69,8 @@ template <int T>
 __device__ __forceinline__ void sc9_issue_sd(const Sc9Mma& m, int j, uint32_t ring_parity) {
   using Cfg = Sc9Cfg;
   constexpr int ST = T >> 1, SUB = T & 1, B = T % 3;
-  if (SUB == 0) { mbar_wait(&m.k_full[ST], ring_parity); tc_fence_after(); }     // the stage's second sub-tile was acquired with the first
+  if (SUB == 0) { mbar_wait(sc9_bar(m.bar0, Cfg::B_KF + ST), ring_parity); tc_fence_after(); }   // the stage's second sub-tile was acquired with the first
+  SC_TR(m.trc, 4, j, 1);
   if (m.leader) {                                                                                    // one lane; every operand is warp-uniform
     const uint32_t col = m.tmem + B * 96;
     const uint64_t kd = umma_desc_adv(m.k_desc0, ST * Cfg::KSTAGE_BYTES + SUB * 4096);                // rows 32 SUB .. +31 of each atom
@@ -66,16 +80,19 @@ __device__ __forceinline__ void sc9_issue_sd(const Sc9Mma& m, int j, uint32_t ri
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
         tc_mma_bf16_ts(col, m.tmem + Cfg::COL_Q + at * 32 + ks * 8, umma_desc_adv(kd, at * 8192 + ks * 32), m.idesc_s, (at | ks) ? 1u : 0u);
+#if !(defined(GMF_SC_DBG) && GMF_SC_DBG == 3)               // development experiment: DBG 3 drops the distance MMAs (timing only)
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
-      tc_mma_bf16(col + 32, umma_desc_adv(m.aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), m.idesc_s, ks ? 1u : 0u);
+      tc_mma_bf16(col + 32, umma_desc_adv(m.aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), m.idesc_d, ks ? 1u : 0u);
 #pragma unroll
     for (int ks = 2; ks < 4; ++ks)
-      tc_mma_bf16(col + 64, umma_desc_adv(m.aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), m.idesc_s, ks > 2 ? 1u : 0u);
-    tc_commit(&m.s_full[B]);
-    if (SUB || j == m.nt - 1) tc_commit(&m.k_empty[ST]);
+      tc_mma_bf16(col + 64, umma_desc_adv(m.aq_desc, ks * 32), umma_desc_adv(bd, ks * 32), m.idesc_d, ks > 2 ? 1u : 0u);
+#endif
+    tc_commit(sc9_bar(m.bar0, Cfg::B_SF + T));
+    if (SUB || j == m.nt - 1) tc_commit(sc9_bar(m.bar0, Cfg::B_KE + ST));
   }
   __syncwarp();
+  SC_TR(m.trc, 4, j, 2);
 }
 
 // PV issuer (warp 9), tile j = j0 + T: O += P_j V_j with P in its group's own TMEM columns
@@ -86,28 +103,35 @@ __device__ __forceinline__ void sc9_pv_step(const Sc9Mma& m, int j0, uint32_t ph
   const int j = j0 + T;
   if (j >= m.nt) return;
   const uint32_t pp = (uint32_t)(j >> 1) & 1u;                  // p_ready[G] completes once per tile of group G
-  if (SUB == 0) mbar_wait2(&m.p_ready[G], pp, &m.v_full[ST], ph);
-  else mbar_wait(&m.p_ready[G], pp);
+  SC_TR(m.trc, 5, j, 0);
+  if (SUB == 0) mbar_wait2(sc9_bar(m.bar0, Cfg::B_PR + G), pp, sc9_bar(m.bar0, Cfg::B_VF + ST), ph);
+  else mbar_wait(sc9_bar(m.bar0, Cfg::B_PR + G), pp);
   tc_fence_after();
+  SC_TR(m.trc, 5, j, 1);
   if (m.leader) {
     const uint64_t vd = umma_desc_adv(m.v_desc0, ST * Cfg::V_BYTES + SUB * 64);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
       tc_mma_bf16_ts(m.tmem + Cfg::COL_O, m.tmem + Cfg::COL_P + G * 16 + ks * 8, umma_desc_adv(vd, ks * 32), m.idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-    tc_commit(&m.pv_done[G]);                                  // P columns of group G are free again
-    if (SUB || j == m.nt - 1) tc_commit(&m.v_empty[ST]);
-    if (j == m.nt - 1) tc_commit(m.o_full);
+    tc_commit(sc9_bar(m.bar0, Cfg::B_PD + G));                 // P columns of group G are free again
+    if (SUB || j == m.nt - 1) tc_commit(sc9_bar(m.bar0, Cfg::B_VE + ST));
+    if (j == m.nt - 1) tc_commit(sc9_bar(m.bar0, Cfg::B_O));
   }
   __syncwarp();
+  SC_TR(m.trc, 5, j, 2);
 }
 
-// score issuer (warp 10): S/DA/DB of tile j + 3 as soon as the softmax group has pulled tile j out of buffer T%3
+// score issuer (warp WS): S/DA/DB of tile j + 3 as soon as the softmax group has pulled tile j out of buffer T%3.
+// Round-2 measurements (profiles/r02_sc_attention.md): a clock64 timeline shows this warp pacing the kernel at ~714 cycles per tile (150 of
+// barrier latency + ~440 in which its UTCHMMA issue is back-pressured by the tensor pipe), but a second score-issuing warp (even / odd tiles)
+// only moves the bottleneck: the softmax warps then share the XU pipe and the issue port at the same ~720 cycles per tile and the extra warp
+// costs 2 %.  What helps is fewer issued instructions: barrier addresses as "bar0 + constant" (no per-operation shared-window re-derivation).
 template <int T>
 __device__ __forceinline__ void sc9_sd_step(const Sc9Mma& m, int j0, uint32_t ph) {
-  constexpr int B = T % 3;
   const int j = j0 + T;
   if (j + 3 >= m.nt) return;
-  mbar_wait(&m.s_free[B], T >= 3 ? 1u : 0u);
+  SC_TR(m.trc, 4, j + 3, 0);
+  mbar_wait(sc9_bar(m.bar0, Sc9Cfg::B_SR + T), ph);             // tile j = j0 + T of this period has left buffer T % 3
   sc9_issue_sd<(T + 3) % 6>(m, j + 3, T + 3 < 6 ? ph : ph ^ 1u);
 }
 
@@ -124,23 +148,9 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
   uint8_t* sFc = sV + NV * Cfg::V_BYTES;                 // fc_message.0 (32 KB) | fc_message.3 (16 KB) weight images
   float* sX = (float*)(sFc + Cfg::FC_BYTES);             // [2][2][128]
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;        // [NS]
-  uint64_t* k_empty = k_full + NS;    // [NS]
-  uint64_t* v_full = k_empty + NS;    // [NV]
-  uint64_t* v_empty = v_full + NV;    // [NV]
-  uint64_t* s_full = v_empty + NV;    // [3]
-  uint64_t* s_free = s_full + 3;      // [3]
-  uint64_t* p_ready = s_free + 3;     // [2]
-  uint64_t* pv_done = p_ready + 2;    // [2]
-  uint64_t* aq_full = pv_done + 2;    // 1
-  uint64_t* o_full = aq_full + 1;     // 1
-  uint64_t* on_ready = o_full + 1;    // fused tail: normalised tf32 O back in TMEM
-  uint64_t* h_ready = on_ready + 1;   //             hidden activation of fc_message in TMEM
-  uint64_t* x1_full = h_ready + 1;
-  uint64_t* x2_full = x1_full + 1;
-  uint64_t* w_full = x2_full + 1;
-  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+  uint32_t* tmem_slot = (uint32_t*)(bars + Cfg::B_COUNT);
+  const uint32_t bar0 = smem_u32(bars);                   // every barrier operation below is "bar0 + constant"
+  auto BAR = [bar0](int idx) { return sc9_bar(bar0, idx); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x;
@@ -149,16 +159,19 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
   const int Nk = SPLIT ? min(a.N - kt0 * 128, a.tiles_per_split * 128) : a.N;
   const int nt = (Nk + BT - 1) / BT;                      // 32-key tiles
   const int nw = (Nk + 63) / 64;                          // 64-key stages
+#ifdef GMF_SC_TRACE
+  long long* trc = (a.trace && blockIdx.x == 7 && blockIdx.y == 1) ? a.trace : nullptr;
+#endif
   const int Nq = a.Nq ? a.Nq : a.N, qtiles = a.Nq ? a.q_tiles : a.tiles;
 
   if (tid == 0) {
-    mbar_init(q_full, NW * 32);
-    for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < NV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128 * TPR); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 128 * TPR); mbar_init(&pv_done[i], 1); }
-    mbar_init(o_full, 1); mbar_init(aq_full, 1);
-    mbar_init(on_ready, NW * 32); mbar_init(h_ready, NW * 32); mbar_init(x1_full, 1); mbar_init(x2_full, 1); mbar_init(w_full, 1);
+    mbar_init(BAR(Cfg::B_Q), NW * 32);
+    for (int i = 0; i < NS; ++i) { mbar_init(BAR(Cfg::B_KF + i), 1); mbar_init(BAR(Cfg::B_KE + i), 1); }
+    for (int i = 0; i < NV; ++i) { mbar_init(BAR(Cfg::B_VF + i), 1); mbar_init(BAR(Cfg::B_VE + i), 1); }
+    for (int i = 0; i < 6; ++i) { mbar_init(BAR(Cfg::B_SF + i), 1); mbar_init(BAR(Cfg::B_SR + i), 128 * TPR); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Cfg::B_PR + i), 128 * TPR); mbar_init(BAR(Cfg::B_PD + i), 1); }
+    mbar_init(BAR(Cfg::B_O), 1); mbar_init(BAR(Cfg::B_AQ), 1);
+    mbar_init(BAR(Cfg::B_ON), NW * 32); mbar_init(BAR(Cfg::B_H), NW * 32); mbar_init(BAR(Cfg::B_X1), 1); mbar_init(BAR(Cfg::B_X2), 1); mbar_init(BAR(Cfg::B_W), 1);
     fence_mbar_init();
   }
   if (warp == WP) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
     else tmem_st16(tlane + Cfg::COL_Q + g * 32 + h * 16, w);
     tmem_st_wait();
     tc_fence_before();
-    mbar_arrive(q_full);
+    mbar_arrive(BAR(Cfg::B_Q));
   }
 
   for (;; ++pass) {
@@ -198,49 +211,57 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
       // ------------------------------------ producer (64-key stages) ------------------------------------
       const uint32_t leader = elect_one() ? 1u : 0u;
       if (pass == 0) {
-        mbar_expect_tx_p(aq_full, Cfg::AQ_BYTES, leader);
-        bulk_g2s_p(sAq, a.aq_t + ((size_t)pair * qtiles + qt) * (128 * 64), Cfg::AQ_BYTES, aq_full, leader);
+        mbar_expect_tx_p(BAR(Cfg::B_AQ), Cfg::AQ_BYTES, leader);
+        bulk_g2s_p(smem_u32(sAq), a.aq_t + ((size_t)pair * qtiles + qt) * (128 * 64), Cfg::AQ_BYTES, BAR(Cfg::B_AQ), leader);
         if (a.fc1_w) {
-          mbar_expect_tx_p(w_full, Cfg::FC_BYTES, leader);
-          bulk_g2s_p(sFc, a.fc1_w, 64 * 128 * 4, w_full, leader);
-          bulk_g2s_p(sFc + 64 * 128 * 4, a.fc2_w, 64 * 64 * 4, w_full, leader);
+          mbar_expect_tx_p(BAR(Cfg::B_W), Cfg::FC_BYTES, leader);
+          bulk_g2s_p(smem_u32(sFc), a.fc1_w, 64 * 128 * 4, BAR(Cfg::B_W), leader);
+          bulk_g2s_p(smem_u32(sFc) + 64 * 128 * 4, a.fc2_w, 64 * 64 * 4, BAR(Cfg::B_W), leader);
         }
       }
       int wk = 0, wv = 0;
       const int wend = nw;
+      const uint32_t sK32 = smem_u32(sK), sV32 = smem_u32(sV);
       while (wk < wend || wv < wend) {
         if (wk < wend && (wv >= wend || wk <= wv + 2)) {
           const int st = wk % NS, j = wk;
-          if (wk >= NS) mbar_wait(&k_empty[st], ((wk / NS) - 1) & 1);
-          uint8_t* dst = sK + st * Cfg::KSTAGE_BYTES;
-          mbar_expect_tx_p(&k_full[st], Cfg::KSTAGE_BYTES, leader);
+          if (wk >= NS) mbar_wait(BAR(Cfg::B_KE + st), ((wk / NS) - 1) & 1);
+          SC_TR(trc, 6, wk, 0);
+          const uint32_t dst = sK32 + st * Cfg::KSTAGE_BYTES, kf = BAR(Cfg::B_KF + st);
+          mbar_expect_tx_p(kf, Cfg::KSTAGE_BYTES, leader);
           const size_t tix = (size_t)pair * a.tiles + kt0 + (j >> 1);
           const int h = j & 1;
           const uint8_t* ksrc = (const uint8_t*)(a.k_t + tix * (128 * D)) + h * 8192;
-          bulk_g2s_p(dst, ksrc, 8192, &k_full[st], leader);
-          bulk_g2s_p(dst + 8192, ksrc + 16384, 8192, &k_full[st], leader);
-          bulk_g2s_p(dst + Cfg::K_BYTES, (const uint8_t*)(a.bd_t + tix * (128 * 64)) + h * Cfg::BD_BYTES, Cfg::BD_BYTES, &k_full[st], leader);
+          bulk_g2s_p(dst, ksrc, 8192, kf, leader);
+          bulk_g2s_p(dst + 8192, ksrc + 16384, 8192, kf, leader);
+          bulk_g2s_p(dst + Cfg::K_BYTES, (const uint8_t*)(a.bd_t + tix * (128 * 64)) + h * Cfg::BD_BYTES, Cfg::BD_BYTES, kf, leader);
           ++wk;
         } else {
           const int sv_ = wv % NV, j = wv;
-          if (wv >= NV) mbar_wait(&v_empty[sv_], ((wv / NV) - 1) & 1);
-          mbar_expect_tx_p(&v_full[sv_], Cfg::V_BYTES, leader);
+          if (wv >= NV) mbar_wait(BAR(Cfg::B_VE + sv_), ((wv / NV) - 1) & 1);
+          SC_TR(trc, 6, wv, 1);
+          mbar_expect_tx_p(BAR(Cfg::B_VF + sv_), Cfg::V_BYTES, leader);
           const size_t tix = (size_t)pair * a.tiles + kt0 + (j >> 1);
-          bulk_g2s_p(sV + sv_ * Cfg::V_BYTES, (const uint8_t*)(a.vt_t + tix * (128 * D)) + (j & 1) * Cfg::V_BYTES, Cfg::V_BYTES, &v_full[sv_], leader);
+          bulk_g2s_p(sV32 + sv_ * Cfg::V_BYTES, (const uint8_t*)(a.vt_t + tix * (128 * D)) + (j & 1) * Cfg::V_BYTES, Cfg::V_BYTES, BAR(Cfg::B_VF + sv_), leader);
           ++wv;
         }
       }
     } else if (warp == WM || warp == WS) {
-      // ------------------------------------ MMA issuers: warp 9 = P V products, warp 10 = scores ------------------------------------
+      // ------------------------------------ MMA issuers: warp WM = P V products, warp WS = scores ------------------------------------
       Sc9Mma m;
-      m.tmem = __shfl_sync(0xffffffffu, tmem, 0); m.idesc_s = umma_idesc(128, BT, kFmtBF16); m.idesc_o = umma_idesc(128, D, kFmtBF16);
+#ifdef GMF_SC_TRACE
+      m.trc = pass == 0 ? trc : nullptr;
+#else
+      m.trc = nullptr;
+#endif
+      m.tmem = __shfl_sync(0xffffffffu, tmem, 0); m.idesc_s = umma_idesc(128, BT, kFmtF16); m.idesc_d = umma_idesc(128, BT, kFmtBF16);
+      m.idesc_o = umma_idesc(128, D, kFmtBF16);                  // S: Q / K fp16; DA / DB: 3-term bf16 features; P V: bf16
       m.leader = elect_one() ? 1u : 0u;
       m.k_desc0 = umma_desc_sw128(smem_u32(sK)); m.v_desc0 = umma_desc_sw128(smem_u32(sV)); m.aq_desc = umma_desc_sw128(smem_u32(sAq));
-      m.k_full = k_full; m.k_empty = k_empty; m.v_full = v_full; m.v_empty = v_empty; m.s_full = s_full; m.s_free = s_free; m.p_ready = p_ready;
-      m.pv_done = pv_done; m.o_full = o_full;
+      m.bar0 = bar0;
       m.nt = nt;
       if (warp == WS) {
-        if (pass == 0) { mbar_wait(q_full, 0); mbar_wait(aq_full, 0); tc_fence_after(); }
+        if (pass == 0) { mbar_wait(BAR(Cfg::B_Q), 0); mbar_wait(BAR(Cfg::B_AQ), 0); tc_fence_after(); }
         sc9_issue_sd<0>(m, 0, 0u);
         if (nt > 1) sc9_issue_sd<1>(m, 1, 0u);
         if (nt > 2) sc9_issue_sd<2>(m, 2, 0u);
@@ -257,23 +278,39 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
           sc9_pv_step<0>(m, j0, ph); sc9_pv_step<1>(m, j0, ph); sc9_pv_step<2>(m, j0, ph);
           sc9_pv_step<3>(m, j0, ph); sc9_pv_step<4>(m, j0, ph); sc9_pv_step<5>(m, j0, ph);
         }
-        mbar_wait(o_full, 0);                                 // every MMA and commit of this pass has retired before the vote
+        mbar_wait(BAR(Cfg::B_O), 0);                          // every MMA and commit of this pass has retired before the vote
       }
     } else {
-      // ------------------------------------ softmax group g: virtual tiles v with (v & 1) == g ------------------------------------
+      // ------------------------------------ softmax group g: tiles j with (j & 1) == g ------------------------------------
+      // Period position T = j % 6, score buffer b = j % 3 and the barrier parities are carried as running counters (no divisions), barrier
+      // addresses are bar0 + 8 (index).  (Unrolling the loop over its period as the issuers do makes every index a constant but multiplies
+      // the ~250-instruction tile body by 6 x {full, ragged}: measured 11 % SLOWER, the 20 warps of the CTA then run out of instruction cache.)
       uint64_t psum2 = pack2(0.f, 0.f);
+      const uint32_t tcol = tlane + h * HC;                  // this thread's first column inside a 32-column accumulator block
+      const uint32_t pcol = tlane + Cfg::COL_P + g * 16 + h * (HC / 2);
+#ifdef GMF_SC_TRACE
+      long long* strc = ((warp & 3) == 0 && pass == 0) ? trc : nullptr;
+      const int srole = warp >> 2;
+#endif
+      int T = g, b = g;                                      // T = j % 6 (s_full / s_free barrier), b = j % 3 (score buffer)
+      uint32_t ph = 0u, pvp = 1u;                            // parity of s_full[T]; parity of the group's previous P V completion
+      const uint32_t bar_pd = BAR(Cfg::B_PD + g), bar_pr = BAR(Cfg::B_PR + g);
+#pragma unroll 1
       for (int j = g; j < nt; j += 2) {
-        const int b = j % 3;
-        const uint32_t tbuf = tlane + (uint32_t)b * 96u;
-        mbar_wait(&s_full[b], (j / 3) & 1);
+        const uint32_t tbuf = tcol + (uint32_t)b * 96u;
+        const uint32_t bar_sf = BAR(Cfg::B_SF) + 8u * (uint32_t)T;
+        SC_TR(strc, srole, j, 0);
+        mbar_wait(bar_sf, ph);
         tc_fence_after();
+        SC_TR(strc, srole, j, 1);
         const int nvalid = Nk - j * BT;
         uint32_t us[HC], ua[HC], ub[HC], pk[HC / 2];
         if constexpr (TPR == 1) { tmem_ld32(tbuf, us); tmem_ld32(tbuf + 32, ua); tmem_ld32(tbuf + 64, ub); }
-        else { tmem_ld16(tbuf + h * 16, us); tmem_ld16(tbuf + 32 + h * 16, ua); tmem_ld16(tbuf + 64 + h * 16, ub); }
+        else { tmem_ld16(tbuf, us); tmem_ld16(tbuf + 32, ua); tmem_ld16(tbuf + 64, ub); }
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_free[b]);                             // the score issuer may refill this buffer with tile j + 3
+        mbar_arrive(bar_sf + 8u * 6u);                       // s_free[T]: the score issuer may refill this buffer with tile j + 3
+        SC_TR(strc, srole, j, 2);
         const uint64_t nref2 = pack2(-ref, -ref);
         auto tile_body = [&](auto ragged_tag) {
           constexpr bool RAGGED = decltype(ragged_tag)::value;
@@ -295,18 +332,28 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
             rmax = fmaxf(rmax, fmaxf(t0, t1));
             const float p0 = (!RAGGED && (c & 3) < POLY) ? ex2_poly(t0) : ex2_approx(t0);
             const float p1 = (!RAGGED && ((c + 1) & 3) < POLY) ? ex2_poly(t1) : ex2_approx(t1);
-            psum2 = fadd2(psum2, pack2(p0, p1));
-            pk[c >> 1] = pack_bf16(p0, p1);
+            // the row sum is taken over the bf16-ROUNDED probabilities the tensor core multiplies with V, so the weights of a row sum to
+            // exactly 1: with peaked rows (KITTI-scale logits ~100) normalising by the unrounded sum leaves a 2^-9 relative error on msg
+            const uint32_t w2 = pack_bf16(p0, p1);
+            psum2 = fadd2(psum2, pack2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u)));
+            pk[c >> 1] = w2;
           }
         };
         if (nvalid >= BT) tile_body(std::false_type{});
         else tile_body(std::true_type{});                    // ragged last tile (CTA-uniform)
-        if (j >= 2) { mbar_wait(&pv_done[g], ((j >> 1) - 1) & 1); tc_fence_after(); }   // P V of this group's previous tile has read the P columns
-        if constexpr (TPR == 1) tmem_st16(tlane + Cfg::COL_P + g * 16, pk);
-        else tmem_st8(tlane + Cfg::COL_P + g * 16 + h * 8, pk);
+        SC_TR(strc, srole, j, 3);
+        if (j >= 2) mbar_wait(bar_pd, pvp);                  // P V of this group's previous tile has read the P columns
+        tc_fence_after();
+        SC_TR(strc, srole, j, 4);
+        if constexpr (TPR == 1) tmem_st16(pcol, pk);
+        else tmem_st8(pcol, pk);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_ready[g]);
+        mbar_arrive(bar_pr);
+        SC_TR(strc, srole, j, 5);
+        T += 2; b += 2; pvp ^= 1u;
+        if (T >= 6) { T -= 6; ph ^= 1u; }
+        if (b >= 3) b -= 3;
       }
       { float ps0, ps1; unpack2(psum2, ps0, ps1); l_sum += ps0 + ps1; }
       sX[part * 128 + r] = rmax;
@@ -325,11 +372,11 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
     }
     l_sum = 0.f; rmax = -INFINITY;
     if (tid == 0) {                                          // every async arrival of the pass has landed (MMA warp waited on o_full): restart the protocol
-      for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-      for (int i = 0; i < NV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-      for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128 * TPR); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 128 * TPR); mbar_init(&pv_done[i], 1); }
-      mbar_init(o_full, 1);
+      for (int i = 0; i < NS; ++i) { mbar_init(BAR(Cfg::B_KF + i), 1); mbar_init(BAR(Cfg::B_KE + i), 1); }
+      for (int i = 0; i < NV; ++i) { mbar_init(BAR(Cfg::B_VF + i), 1); mbar_init(BAR(Cfg::B_VE + i), 1); }
+      for (int i = 0; i < 6; ++i) { mbar_init(BAR(Cfg::B_SF + i), 1); mbar_init(BAR(Cfg::B_SR + i), 128 * TPR); }
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(Cfg::B_PR + i), 128 * TPR); mbar_init(BAR(Cfg::B_PD + i), 1); }
+      mbar_init(BAR(Cfg::B_O), 1);
       fence_mbar_init();
     }
     __syncthreads();                                         // also: sX is rewritten by the next pass
@@ -342,22 +389,22 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc_f = umma_idesc(128, 64, kFmtTF32);
     const uint64_t w1_desc = umma_desc_sw128(smem_u32(sFc)), w2_desc = umma_desc_sw128(smem_u32(sFc + 64 * 128 * 4));
-    mbar_wait2(on_ready, 0, w_full, 0);
+    mbar_wait2(BAR(Cfg::B_ON), 0, BAR(Cfg::B_W), 0);
     tc_fence_after();
     if (leader) {
 #pragma unroll
       for (int i = 0; i < 16; ++i)                             // X1[128 x 64] = msg . W1^T   (msg = normalised O, columns 384..511)
         tc_mma_tf32_ts(tm, tm + Cfg::COL_O + i * 8, umma_desc_adv(w1_desc, (i >> 2) * 8192 + (i & 3) * 32), idesc_f, i ? 1u : 0u);
-      tc_commit(x1_full);
+      tc_commit(BAR(Cfg::B_X1));
     }
     __syncwarp();
-    mbar_wait(h_ready, 0);
+    mbar_wait(BAR(Cfg::B_H), 0);
     tc_fence_after();
     if (leader) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)                              // X2[128 x 64] = H . W2^T      (H in columns 64..127, X2 in 128..191)
         tc_mma_tf32_ts(tm + 128, tm + 64 + i * 8, umma_desc_adv(w2_desc, (i >> 2) * 8192 + (i & 3) * 32), idesc_f, i ? 1u : 0u);
-      tc_commit(x2_full);
+      tc_commit(BAR(Cfg::B_X2));
     }
     __syncwarp();
   }
@@ -367,7 +414,7 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
 #pragma unroll
     for (int o = 1; o < NPART; ++o) l_sum += sX[512 + ((part + o) % NPART) * 128 + r];
     const float inv = SPLIT ? 1.f : 1.f / l_sum;
-    mbar_wait(o_full, 0);
+    mbar_wait(BAR(Cfg::B_O), 0);
     tc_fence_after();
     const int gq = qt * 128 + r;
     constexpr int OC = D / NPART;                             // output columns per thread
@@ -400,10 +447,10 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(on_ready);
+      mbar_arrive(BAR(Cfg::B_ON));
       constexpr int HC1 = 64 / NPART;                         // hidden columns per thread (16 or 32)
       uint32_t x[HC1];
-      mbar_wait(x1_full, 0);
+      mbar_wait(BAR(Cfg::B_X1), 0);
       tc_fence_after();
       if constexpr (HC1 == 16) tmem_ld16(tlane + part * HC1, x); else tmem_ld32(tlane + part * HC1, x);
       tmem_ld_wait();
@@ -412,8 +459,8 @@ __global__ void __launch_bounds__(256 * TPR + 96, 1) sc_attn_v9_kernel(const ScA
       if constexpr (HC1 == 16) tmem_st16(tlane + 64 + part * HC1, x); else tmem_st32(tlane + 64 + part * HC1, x);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(h_ready);
-      mbar_wait(x2_full, 0);
+      mbar_arrive(BAR(Cfg::B_H));
+      mbar_wait(BAR(Cfg::B_X2), 0);
       tc_fence_after();
       if constexpr (HC1 == 16) tmem_ld16(tlane + 128 + part * HC1, x); else tmem_ld32(tlane + 128 + part * HC1, x);
       tmem_ld_wait();

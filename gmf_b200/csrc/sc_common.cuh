@@ -29,6 +29,9 @@ struct ScAttnArgs {
   int tiles_per_split;
   float* part_o;
   float* part_l;
+#ifdef GMF_SC_TRACE
+  long long* trace;           // development build only: clock64 timeline of one CTA, [role 0..6][tile 0..63][stamp 0..7]
+#endif
 };
 
 

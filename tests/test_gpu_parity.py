@@ -34,10 +34,14 @@ def bf16r(x):
     return x.to(torch.bfloat16).to(torch.float64)
 
 
+def f16r(x):
+    return x.to(torch.float16).to(torch.float64)
+
+
 def attn_ref(q, k, v, scale, src=None, tgt=None, sigma=0.1):
-    """fp64 reference on the bf16-rounded operands the kernel consumes (q carries scale*log2e before rounding)."""
+    """fp64 reference on the rounded operands the kernel consumes: Q (carrying scale*log2e) and K in fp16, V in bf16."""
     l2e = 1.4426950408889634
-    s = torch.einsum("bid,bjd->bij", bf16r(q * (scale * l2e)), bf16r(k)) / l2e
+    s = torch.einsum("bid,bjd->bij", f16r(q * (scale * l2e)), f16r(k)) / l2e
     if src is not None:
         c = torch.clamp(1 - (torch.cdist(src.double(), src.double()) - torch.cdist(tgt.double(), tgt.double())) ** 2 / sigma ** 2, min=0)
         s = s * c
