@@ -453,6 +453,20 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   const __half2 t = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
   return *reinterpret_cast<const uint32_t*>(&t);
 }
+// x = hi + lo with both parts fp16 (22 significand bits together): the operand split of the error-compensated kind::f16 GEMMs
+// (x w ~ x_hi w_hi + x_lo w_hi + x_hi w_lo) that replace TF32 where its 11-bit operands are not enough (PointCN / QKV at KITTI scale)
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+  lo = __float2half_rn(fminf(fmaxf(x - __half2float(hi), -65504.f), 65504.f));   // |x| > 1.3e5 saturates instead of producing inf / NaN
+}
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  __half h0, l0, h1, l1;
+  split_f16(x0, h0, l0);
+  split_f16(x1, h1, l1);
+  const __half2 H = __halves2half2(h0, h1), L = __halves2half2(l0, l1);
+  hi = *reinterpret_cast<const uint32_t*>(&H);
+  lo = *reinterpret_cast<const uint32_t*>(&L);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
 #if defined(GMF_SC_DBG) && GMF_SC_DBG == 2
   return fmaf(x, 0.001f, 1.0f);

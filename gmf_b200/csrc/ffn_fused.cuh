@@ -50,7 +50,8 @@ struct FfnArgs {
   const float* m2;         // [B, L, 64] (ReLU(BN(conv(...))) output of fc_message.4) or NULL
   const float* w3_packed;  // [128 out rows x 64] swizzled tf32
   const float* b3;         // [128]
-  // out_img != NULL: instead of the row-major `out`, write the tf32 K-major tile image [B][tiles][128 x 128] that the next layer's
+  // out_img != NULL: instead of the row-major `out`, write the SPLIT fp16 K-major tile image [B][tiles][hi 2 x 16 KB | lo 2 x 16 KB] (x = hi + lo,
+  // common.cuh split_f16; 64 KB like the fp32 tile) that the next layer's
   // chained PointCN/QKV kernel loads with one bulk copy (the per-warp staging tiles already are 32-row blocks of that image)
   float* out_img;
 };
@@ -359,18 +360,46 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       uint32_t v[32];
       tmem_ld32(trow + Cfg::COL_OUT + c * 32, v);
       tmem_ld_wait();
+      const bool live = row0 + r < a.L;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 bb = *reinterpret_cast<const float4*>(a.b2 + col0 + 4 * j);
         if (a.m2) { const float4 b3 = *reinterpret_cast<const float4*>(a.b3 + col0 + 4 * j); bb.x += b3.x; bb.y += b3.y; bb.z += b3.z; bb.w += b3.w; }
         float4* slot = reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2));
         const float4 res = *slot;
-        float4 o = make_float4(__uint_as_float(v[4 * j]) + bb.x + res.x, __uint_as_float(v[4 * j + 1]) + bb.y + res.y,
-                               __uint_as_float(v[4 * j + 2]) + bb.z + res.z, __uint_as_float(v[4 * j + 3]) + bb.w + res.w);
-        if (a.out_img) o = (row0 + r < a.L) ? to_tf32(o) : make_float4(0.f, 0.f, 0.f, 0.f);
-        *slot = o;
+        const float4 o = make_float4(__uint_as_float(v[4 * j]) + bb.x + res.x, __uint_as_float(v[4 * j + 1]) + bb.y + res.y,
+                                     __uint_as_float(v[4 * j + 2]) + bb.z + res.z, __uint_as_float(v[4 * j + 3]) + bb.w + res.w);
+        if (a.out_img) {                                       // kept in registers: the image is assembled below
+          v[4 * j] = __float_as_uint(live ? o.x : 0.f); v[4 * j + 1] = __float_as_uint(live ? o.y : 0.f);
+          v[4 * j + 2] = __float_as_uint(live ? o.z : 0.f); v[4 * j + 3] = __float_as_uint(live ? o.w : 0.f);
+        } else {
+          *slot = o;
+        }
       }
       __syncwarp();
+      if (a.out_img) {
+        // Split fp16 image (x = hi + lo): fp16 swizzle atoms are 64 columns wide, so warps (q, 2m) and (q, 2m + 1) share the 32-row blocks of
+        // atom m.  Their two 4 KB staging tiles become that block of the hi image (even warp's tile) and of the lo image (odd warp's tile);
+        // each warp then ships the block that sits in its own tile.
+        const int m = cq >> 1;
+        const int pair_bar = 1 + m * 4 + q;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // both warps have read their residual rows out of the tiles
+        uint8_t* blk_hi = (uint8_t*)(sStg + ((2 * m) * 4 + q) * 1024);
+        uint8_t* blk_lo = (uint8_t*)(sStg + ((2 * m + 1) * 4 + q) * 1024);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 H, Lw;
+          split_f16x2(__uint_as_float(v[8 * jj]), __uint_as_float(v[8 * jj + 1]), H.x, Lw.x);
+          split_f16x2(__uint_as_float(v[8 * jj + 2]), __uint_as_float(v[8 * jj + 3]), H.y, Lw.y);
+          split_f16x2(__uint_as_float(v[8 * jj + 4]), __uint_as_float(v[8 * jj + 5]), H.z, Lw.z);
+          split_f16x2(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7]), H.w, Lw.w);
+          const uint32_t off = swz_off(lane, (cq & 1) * 4 + jj);
+          *reinterpret_cast<uint4*>(blk_hi + off) = H;
+          *reinterpret_cast<uint4*>(blk_lo + off) = Lw;
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      }
       if (!a.out_img) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -382,12 +411,10 @@ __global__ void __launch_bounds__(640, 1) ffn_fused_kernel(const FfnArgs a) {
       }
     }
     if (a.out_img) {
-      // warp (q, cq) owns rows 32q.. of swizzle atom cq: its 4 KB staging tile sits exactly where that block lives in the image, so
-      // every warp ships its own block as soon as it is complete (no CTA-wide barrier, 16 x 4 KB bulk stores in flight)
-      fence_proxy_async();
-      __syncwarp();
+      // 16 x 4 KB bulk stores in flight, no CTA-wide barrier: tile layout [hi atom 0 | hi atom 1 | lo atom 0 | lo atom 1], 16 KB each
       if (lane == 0) {
-        bulk_s2g(a.out_img + (size_t)(pair * a.tiles + tile) * (128 * 128) + warp * 1024, stg, 4096);
+        uint8_t* img = (uint8_t*)(a.out_img + (size_t)(pair * a.tiles + tile) * (128 * 128));
+        bulk_s2g(img + (cq & 1) * 32768 + (cq >> 1) * 16384 + q * 4096, stg, 4096);
         bulk_commit_wait_read();
       }
       __syncwarp();

@@ -193,6 +193,27 @@ std::vector<float> pack_linear_f16(const std::vector<float>& W, int nout, int k,
   return out;
 }
 
+// Error-compensated fp16 operands (pcn_qkv.cuh): per block of `nb` rows and k-chunk of 64: {hi atom | lo atom}, each nb x 128 B (64 halfs per row),
+// w = hi + lo.  Returned as floats (two halfs per element) so that it travels in the same weight blob; same byte count as fp32.
+std::vector<float> pack_linear_split16(const std::vector<float>& W, int nout, int k, int nb) {
+  std::vector<float> out((size_t)nout * k, 0.f);
+  size_t chunk = 0;
+  for (int blk = 0; blk < nout / nb; ++blk)
+    for (int kc = 0; kc < k / 64; ++kc, ++chunk) {
+      uint8_t* img = (uint8_t*)(out.data() + chunk * (size_t)nb * 64);
+      for (int n = 0; n < nb; ++n)
+        for (int kk = 0; kk < 64; ++kk) {
+          const float w = W[(size_t)(blk * nb + n) * k + kc * 64 + kk];
+          const __half hi = __float2half_rn(std::min(std::max(w, -65504.f), 65504.f));
+          const __half lo = __float2half_rn(w - __half2float(hi));
+          const size_t off = swz_off(n, kk >> 3) + (kk & 7) * 2;
+          memcpy(img + off, &hi, 2);
+          memcpy(img + (size_t)nb * 128 + off, &lo, 2);
+        }
+    }
+  return out;
+}
+
 struct FusionW {
   bool pe = false;
   const float *cpe_q_w = nullptr, *cpe_q_b = nullptr, *cpe_c_w = nullptr, *cpe_c_b = nullptr;
@@ -799,7 +820,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
       const float *g = next("1.weight"), *be = next("1.bias"), *mu = next("1.running_mean"), *va = next("1.running_var");
       fold_bn(W, b, 128, 128, g, be, mu, va);
       o.pb = blob.push(b);
-      pcn64 = pack_linear(W, 128, 128, 64, 128);
+      pcn64 = pack_linear_split16(W, 128, 128, 128);
     }
     {
       std::vector<float> W = vec(next("fc_message.0.weight"), 64 * 128), b = vec(next("fc_message.0.bias"), 64);
@@ -829,7 +850,8 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
       }
       const std::vector<float> qkv64 = pack_linear(W, 384, 128, 64, 128);
       o.qw = blob.push(qkv64); o.qb = blob.push(b);
-      pcn64.insert(pcn64.end(), qkv64.begin(), qkv64.end());
+      const std::vector<float> qkv_split = pack_linear_split16(W, 384, 128, 128);
+      pcn64.insert(pcn64.end(), qkv_split.begin(), qkv_split.end());
       o.pqw = blob.push(pcn64);
     }
     o.f2 = pack_fusion(true);

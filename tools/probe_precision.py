@@ -157,9 +157,10 @@ def main():
     extent, thr, noise = (60.0, 1.2, 0.04) if shape == "kitti" else (3.0, 0.10, 0.002)
     torch.set_num_threads(os.cpu_count() or 8)
     cfg = dict(O.DEFAULT_CFG, num_layers=layers, inlier_threshold=thr, nms_radius=thr, sigma_d=thr)
-    sd = synth_state_dict(hot_path_spec(layers), seed=0, plain_init=True)
+    wseed, dseed, plain = int(os.environ.get("WSEED", 0)), int(os.environ.get("DSEED", 301)), os.environ.get("PLAIN", "1") == "1"
+    sd = synth_state_dict(hot_path_spec(layers), seed=wseed, plain_init=plain)
     sd["sigma_spat"] = torch.tensor([thr])
-    pr = synth_pairs(1, n, seed=301, extent=extent, inlier_ratio=0.30, noise=noise)
+    pr = synth_pairs(1, n, seed=dseed, extent=extent, inlier_ratio=float(os.environ.get("INLIERS", 0.30)), noise=noise)
     args = [pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], synth_tokens(1, t, 1), synth_tokens(1, t, 2)]
     ref = run(sd, cfg, args, [])
     print(shape, "N", n, "T", t, "layers", layers, "logit range", float(ref["confidence"].min()), float(ref["confidence"].max()))

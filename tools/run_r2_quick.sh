@@ -2,7 +2,7 @@
 # quick loop: selected GPU tests + short bench (+ optional SC trace)
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_measured.jsonl
-timeout 900 python -m pytest tests -m gpu -q -x  > gpurun_out/pytest_gpu.log 2>&1; echo "[pytest exit $?]" >> gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q  > gpurun_out/pytest_gpu.log 2>&1; echo "[pytest exit $?]" >> gpurun_out/pytest_gpu.log
 tail -n 6 gpurun_out/pytest_gpu.log
 QUICK="--no-cpu-baseline --no-e2e --no-backbone --no-cfg3"
 timeout 600 python bench.py --steps 5 --warmup 3 $QUICK > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "[bench exit $?]"; tail -n 3 gpurun_out/bench.err
