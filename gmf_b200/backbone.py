@@ -72,3 +72,50 @@ class ImageEncoder(nn.Module):
         f = self.backbone(image)
         b, c, h, w = f.shape
         return f.view(b, c, h * w).permute(0, 2, 1).contiguous()
+
+    # ---- opt-in accelerated trunk: channels_last + bf16 autocast + CUDA graph ---------------------------------
+    # Still PyTorch / cuDNN (the backbone is outside the hot path by BASELINE.json); eval-mode only.  The reference-equivalent fp32 eager trunk
+    # above stays the default: `gmf_b200.PointDSC(..., ).backbone_mode = "bf16_graph"` switches.  The graph is keyed on the input shape and
+    # replays with static input / output buffers; weights are read from the module's parameters at capture time, so `invalidate_fast()`
+    # must be called (the module does it) when they change.
+    def invalidate_fast(self):
+        self._fast = {}
+
+    @torch.no_grad()
+    def tokens_fast(self, image: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
+        if self.training:
+            raise RuntimeError("the accelerated trunk is eval-mode only (BatchNorm running statistics)")
+        if image.device.type != "cuda":
+            raise RuntimeError("the accelerated trunk needs a CUDA device")
+        cache = self.__dict__.setdefault("_fast", {})
+        key = (tuple(image.shape), image.device.index)
+        ent = cache.get(key)
+
+        def run(x):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                f = self.backbone(x)
+            b, c, h, w = f.shape
+            return f.float().permute(0, 2, 3, 1).reshape(b, h * w, c).contiguous()     # NHWC feature map == token-major layout
+
+        if ent is None:
+            if cache.get("_cl") is not True:                   # one-time: channels_last weights (no numerical change)
+                self.backbone.to(memory_format=torch.channels_last)
+                cache["_cl"] = True
+            static_in = torch.empty(image.shape, device=image.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
+            static_in.copy_(image)
+            if not use_graph:
+                return run(static_in)
+            side = torch.cuda.Stream(device=image.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up outside capture (cuDNN autotune, lazy init)
+                for _ in range(2):
+                    run(static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = run(static_in)
+            ent = cache[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = ent
+        static_in.copy_(image)
+        graph.replay()
+        return static_out.clone()

@@ -17,6 +17,7 @@
 #include "tail.cuh"
 #include "dgr_head.cuh"
 #include "matcher.cuh"
+#include "sm_baseline.cuh"
 
 using namespace gmf;
 
@@ -1256,3 +1257,4 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
 #include "dgr_head_api.inl"
 #include "matcher_api.inl"
 #include "compat_api.inl"
+#include "sm_api.inl"

@@ -132,6 +132,18 @@ class Engine:
         _lib.check(self.lib.gmf_weighted_procrustes(self.h, _ptr(X), _ptr(Y), _ptr(w), B, N, float(eps), _ptr(R), _ptr(t), self._stream()))
         return R, t
 
+    def sm_baseline(self, src, tgt, inlier_threshold=0.10, top_ratio=0.1, iters=10):
+        """Classical spectral matching `SM` (baseline_scripts/baseline_3DMatch.py:19-53): src, tgt [B,N,3] ->
+        (trans [B,4,4], labels [B,N], leading_eig [B,N])."""
+        src, tgt = _chk(src), _chk(tgt)
+        B, N, _ = src.shape
+        trans, labels, eig = torch.empty(B, 4, 4, device=src.device), torch.empty(B, N, device=src.device), torch.empty(B, N, device=src.device)
+        nb = int(self.lib.gmf_sm_workspace_bytes(B, N, float(top_ratio)))
+        ws = torch.empty(max(nb, 1), dtype=torch.uint8, device=src.device)
+        _lib.check(self.lib.gmf_sm_baseline(self.h, _ptr(src), _ptr(tgt), B, N, float(inlier_threshold), float(top_ratio), int(iters),
+                                            _ptr(trans), _ptr(labels), _ptr(eig), _ptr(ws), nb, self._stream()))
+        return trans, labels, eig
+
     def synchronize(self):
         _lib.check(self.lib.gmf_stream_synchronize(self.h, self._stream()))
 

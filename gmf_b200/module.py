@@ -161,10 +161,24 @@ class PointDSC(nn.Module):
             self._packed_sig = sig
         return eng
 
+    # "fp32": the reference-equivalent eager trunk (default).  "bf16" / "bf16_graph": opt-in channels_last + bf16 autocast trunk, the latter
+    # replayed from a CUDA graph (backbone.py tokens_fast; 28 -> 20 ms per 2 x 64 images at 480 x 640).  The tokens then carry bf16 rounding
+    # noise (~2e-2 abs on tokens of magnitude ~5), which costs ~3e-3 on the logits (tests/test_gpu_parity.py).
+    backbone_mode = "fp32"
+
     @torch.no_grad()
     def image_tokens(self, p_image, q_image):
         enc = self.encoder.image_encoder
-        return enc.tokens(p_image), enc.tokens(q_image)
+        if self.backbone_mode == "fp32":
+            return enc.tokens(p_image), enc.tokens(q_image)
+        if self.backbone_mode not in ("bf16", "bf16_graph"):
+            raise ValueError(f"unknown backbone_mode {self.backbone_mode!r}")
+        sig = tuple((t.data_ptr(), t._version) for t in enc.state_dict(keep_vars=True).values())
+        if getattr(self, "_bb_sig", None) != sig:              # weights changed: drop captured graphs
+            enc.invalidate_fast()
+            self._bb_sig = sig
+        g = self.backbone_mode == "bf16_graph"
+        return enc.tokens_fast(p_image, g), enc.tokens_fast(q_image, g)
 
     @torch.no_grad()
     def forward(self, data):

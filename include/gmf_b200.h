@@ -128,6 +128,16 @@ int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* B, const f
 int gmf_weighted_procrustes(gmf_ctx* ctx, const float* X, const float* Y, const float* w, int B, int N, float eps, float* R, float* t,
                             void* stream);
 
+/* ---- classical SM baseline ------------------------------------------------ */
+/* `SM` of GMF_PointDSC/baseline_scripts/baseline_3DMatch.py:19-53: M_ij = max(0, 4.5 - (|s_i-s_j| - |t_i-t_j|)^2 / (2 sigma^2)) with
+ * sigma = inlier_threshold / 3 and a zero diagonal, `iters` (reference: 10) power iterations v <- M v / (|M v| + 1e-6) from v = 1, labels =
+ * the top int(N * top_ratio) entries of v, pose = rigid_transform_3d(src, tgt, v * labels).  The N x N matrix is recomputed from the points
+ * inside every fused mat-vec and never stored.  src, tgt [B,N,3] -> trans [B,4,4], labels [B,N] (0/1), leading_eig [B,N] (optional, may be
+ * NULL).  No weights needed.  N <= 16384. */
+size_t gmf_sm_workspace_bytes(int B, int N, double top_ratio);
+int gmf_sm_baseline(gmf_ctx* ctx, const float* src, const float* tgt, int B, int N, float inlier_threshold, double top_ratio, int iters,
+                    float* trans, float* labels, float* leading_eig, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- DGR bottleneck fusion head --------------------------------------------- */
 /* PerceiverIO(depth=0, dim=128, latent_dim=256, cross_heads=1, cross_dim_head=128, pe) of the DGR inlier network
  * (GMF_DeepGlobalRegistration_fcgf/model/perceiver_io.py:140-221; built at model/resunet_new.py:516-525, called from

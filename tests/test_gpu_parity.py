@@ -404,6 +404,39 @@ def test_module_drop_in_with_backbone():
     assert (res["M"].cpu().double() - Mref).abs().max() < 2e-2          # bf16-attention feature noise through 1/sigma^2
 
 
+def test_module_accelerated_backbone_option():
+    """opt-in channels_last + bf16 autocast (+ CUDA graph) image trunk.  Token parity against the fp32 trunk and the
+    resulting logit / pose deviation against the reference-generated fixture; a second call replays the captured graph."""
+    from gmf_b200 import PointDSC
+    from gmf_b200.synth import synth_state_dict
+    meta, fx = load_golden("l2_n384_3dmatch")
+    m = PointDSC(num_layers=2, inlier_threshold=meta["thr"], sigma_d=meta["thr"], nms_radius=meta["thr"])
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = synth_state_dict(shapes, seed=meta["wseed"], plain_init=meta["plain"])
+    sd["sigma_spat"] = torch.tensor([meta["thr"]])
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().cuda()
+    p_img, q_img = fx["p_image"].cuda(), fx["q_image"].cuda()
+    ref_p, ref_q = m.image_tokens(p_img, q_img)
+    assert (ref_p.cpu() - fx["p_tok"]).abs().max() < 2e-2       # cuDNN's default TF32 convolutions vs the CPU fp32 trunk that made the fixture
+    for mode in ("bf16", "bf16_graph"):
+        m.backbone_mode = mode
+        tp, tq = m.image_tokens(p_img, q_img)
+        tp2, _ = m.image_tokens(p_img, q_img)                   # graph replay / cached channels_last weights
+        assert torch.equal(tp, tp2) and tp.shape == ref_p.shape and tp.dtype == torch.float32
+        dt = float((tp - ref_p).abs().max() / ref_p.abs().max())
+        data = {"corr_pos": fx["corr_pos"].cuda(), "src_keypts": fx["src"].cuda(), "tgt_keypts": fx["tgt"].cuda(), "p_image": p_img, "q_image": q_img}
+        logits = m(data)["final_labels"].cpu()                  # training-mode contract: logits
+        dl = float((logits - fx["confidence"]).abs().max())
+        data["testing"] = True
+        res = m(data)
+        re = float(O.rotation_error_deg(res["final_trans"].cpu()[:, :3, :3], fx["final_trans"][:, :3, :3]).max())
+        te = float((res["final_trans"].cpu()[:, :3, 3] - fx["final_trans"][:, :3, 3]).norm(dim=-1).max())
+        record("backbone_" + mode, token_rel_err=dt, max_abs_dlogit=dl, rot_err_deg=re, trans_err_mm=te * 1e3)
+        assert dt < 2e-2 and dl < 1e-2 and re < 0.01 and te < 1e-3
+        assert torch.equal(res["final_labels"].cpu(), fx["final_labels"])
+
+
 def test_feature_compat_matches_fp64_formula():
     """gmf_feature_compat (training-mode M) on given features: tensor-pipe GEMM at fp32 accuracy, ragged N, B > 1, zero diagonal."""
     from gmf_b200.synth import synth_state_dict
