@@ -18,6 +18,7 @@
 #include "dgr_head.cuh"
 #include "matcher.cuh"
 #include "sm_baseline.cuh"
+#include "se3_refine.cuh"
 
 using namespace gmf;
 
@@ -1170,6 +1171,21 @@ int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* Bp, const 
   if (M < 1 || k < 1) return fail(GMF_ERR_INVALID, "need M >= 1, k >= 1");
   CU(cudaSetDevice(ctx->device));
   rigid_transform_kernel<<<cdiv(M, 4), 128, 0, (cudaStream_t)stream>>>(A, Bp, weights, M, k, T);
+  LAUNCHED();
+  return 0;
+}
+
+int gmf_global_registration(gmf_ctx* ctx, const float* X, const float* Y, const float* w, int B, int N, float quantization_size, int max_iter,
+                            int max_break_count, float break_threshold_ratio, float* R, float* t, float* info, void* stream) {
+  if (!ctx) return fail(GMF_ERR_INVALID, "ctx is NULL");
+  if (!X || !Y || !w || !R || !t) return fail(GMF_ERR_INVALID, "gmf_global_registration: NULL argument");
+  if (B < 1 || N < 1 || max_iter < 0 || !(quantization_size > 0.f)) return fail(GMF_ERR_INVALID, "gmf_global_registration: need B >= 1, N >= 1, max_iter >= 0, quantization_size > 0");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float eps = 1.1920928955078125e-07f;                   // np.finfo(np.float32).eps: HighDimSmoothL1Loss.eps, also passed to weighted_procrustes (:160)
+  weighted_procrustes_kernel<<<B, 256, 0, st>>>(X, Y, w, N, eps, R, t);     // initialisation (:159-161); refined in place
+  LAUNCHED();
+  se3_refine_kernel<<<B, 512, 0, st>>>(X, Y, w, N, quantization_size, eps, max_iter, max_break_count, break_threshold_ratio, R, t, R, t, info);
   LAUNCHED();
   return 0;
 }

@@ -132,6 +132,16 @@ class Engine:
         _lib.check(self.lib.gmf_weighted_procrustes(self.h, _ptr(X), _ptr(Y), _ptr(w), B, N, float(eps), _ptr(R), _ptr(t), self._stream()))
         return R, t
 
+    def global_registration(self, X, Y, w, quantization_size=1.0, max_iter=1000, max_break_count=20, break_threshold_ratio=1e-5):
+        """DGR `GlobalRegistration` (core/registration.py:135-194): weighted Procrustes + robust SE(3) Adam refinement, all on the device.
+        X, Y [B,N,3], w [B,N] -> (R [B,3,3], t [B,3], info [B,3] = exit iteration, loss, break count)."""
+        X, Y, w = _chk(X), _chk(Y), _chk(w)
+        B, N, _ = X.shape
+        R, t, info = torch.empty(B, 3, 3, device=X.device), torch.empty(B, 3, device=X.device), torch.empty(B, 3, device=X.device)
+        _lib.check(self.lib.gmf_global_registration(self.h, _ptr(X), _ptr(Y), _ptr(w), B, N, float(quantization_size), int(max_iter),
+                                                    int(max_break_count), float(break_threshold_ratio), _ptr(R), _ptr(t), _ptr(info), self._stream()))
+        return R, t, info
+
     def sm_baseline(self, src, tgt, inlier_threshold=0.10, top_ratio=0.1, iters=10):
         """Classical spectral matching `SM` (baseline_scripts/baseline_3DMatch.py:19-53): src, tgt [B,N,3] ->
         (trans [B,4,4], labels [B,N], leading_eig [B,N])."""

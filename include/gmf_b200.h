@@ -128,6 +128,15 @@ int gmf_rigid_transform_3d(gmf_ctx* ctx, const float* A, const float* B, const f
 int gmf_weighted_procrustes(gmf_ctx* ctx, const float* X, const float* Y, const float* w, int B, int N, float eps, float* R, float* t,
                             void* stream);
 
+/* DGR's pose solver `GlobalRegistration` (core/registration.py:135-194; called from core/deep_global_registration.py:336-341 with the predicted
+ * inlier weights): weighted Procrustes initialisation (:159-161), then up to max_iter (reference: 1000) Adam iterations (lr 0.1, ExponentialLR 0.999)
+ * on the 6-D rotation parameterisation + translation (`Transformation`, :116-132) of the weighted HighDimSmoothL1Loss with quantization_size
+ * (core/loss.py:42-61); early exits: loss < 1e-7, or max_break_count (20) iterations with |dloss| < break_threshold_ratio x loss (:172,:183-186).
+ * One persistent CTA per pair runs the whole loop on the device (the reference does every iteration on the host with autograd).
+ * X, Y [B,N,3], w [B,N] (non-negative) -> R [B,3,3], t [B,3]; info [B,3] = (exit iteration index, final loss, break count), may be NULL. */
+int gmf_global_registration(gmf_ctx* ctx, const float* X, const float* Y, const float* w, int B, int N, float quantization_size, int max_iter,
+                            int max_break_count, float break_threshold_ratio, float* R, float* t, float* info, void* stream);
+
 /* ---- classical SM baseline ------------------------------------------------ */
 /* `SM` of GMF_PointDSC/baseline_scripts/baseline_3DMatch.py:19-53: M_ij = max(0, 4.5 - (|s_i-s_j| - |t_i-t_j|)^2 / (2 sigma^2)) with
  * sigma = inlier_threshold / 3 and a zero diagonal, `iters` (reference: 10) power iterations v <- M v / (|M v| + 1e-6) from v = 1, labels =

@@ -31,6 +31,7 @@ FILES = [
     # DGR bottleneck fusion head (cfg#5) and the pose solvers of §8f N3
     ("GMF_DeepGlobalRegistration/GMF_DeepGlobalRegistration_fcgf/model/perceiver_io.py", "dgr_fcgf/model/perceiver_io.py"),
     ("GMF_DeepGlobalRegistration/GMF_DeepGlobalRegistration_fcgf/core/registration.py", "dgr_fcgf/core/registration.py"),
+    ("GMF_DeepGlobalRegistration/GMF_DeepGlobalRegistration_fcgf/core/loss.py", "dgr_fcgf/core/loss.py"),
     # classical spectral-matching baseline (§8f N4)
     ("GMF_PointDSC/baseline_scripts/baseline_3DMatch.py", "GMF_PointDSC/baseline_scripts/baseline_3DMatch.py"),
 ]
