@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) desc_operand_kernel(const float* __restri
   }
 }
 
-enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4, DE_COMPAT = 5, DE_ARGMIN = 6 };
+enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4, DE_COMPAT = 5, DE_ARGMIN = 6, DE_STORE = 7 };
 
 struct ImgGemmArgs {
   const float* a_img;      // [tiles][K/32][128 x 32] tf32 chunks (rows_to_img_kernel / DE_GEGLU epilogue)
@@ -166,7 +166,7 @@ struct ImgGemmArgs {
   // batched use (blockIdx.z = pair): element strides of a_img / w_packed / out between pairs; DE_DIST: valid output columns
   size_t a_pair_stride, w_pair_stride, out_pair_stride;
   int ncols;
-  float scale;             // DE_COMPAT: 1 / sigma^2
+  float scale;             // DE_COMPAT: 1 / sigma^2; DE_STORE: out = scale * acc (+ bias[col]) (+ residual[row][col]), any L / ncols / ld (training path)
   unsigned long long* best;   // DE_ARGMIN: [pairs][L] running (distance bits << 32 | column) minima, preset to all-ones
 };
 
@@ -179,7 +179,7 @@ struct IgCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = NB * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = (EPI == DE_RES || EPI == DE_DIST || EPI == DE_COMPAT) ? 4 * 4096 : 0;
+  static constexpr int STG_BYTES = (EPI == DE_RES || EPI == DE_DIST || EPI == DE_COMPAT || EPI == DE_STORE) ? 4 * 4096 : 0;
   static constexpr int SMEM = 1024 + NSTG * STAGE + 256 + STG_BYTES;
 };
 
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
                                  (__uint_as_float(v[4 * j + 3]) + b1.w) * gelu_erf(__uint_as_float(gt[4 * j + 3]) + b2.w));
           *reinterpret_cast<float4*>(dst + swz_off(r, j)) = valid ? to_tf32(o) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      } else if (EPI == DE_DIST || EPI == DE_COMPAT) {
+      } else if (EPI == DE_DIST || EPI == DE_COMPAT || EPI == DE_STORE) {
         tmem_ld_wait();
         // DE_DIST: squared feature distance of unit vectors, 2 - 2 <a, b> (models/common.py:64-66), rows = seeds, columns = points
         // DE_COMPAT: feature compatibility clamp(1 - (1 - <a, b>) / sigma^2, 0, 1) with a zero diagonal (models/PointDSC.py:231-234)
@@ -301,7 +301,10 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o;
-          if (EPI == DE_DIST) {
+          if (EPI == DE_STORE) {
+            o = make_float4(__uint_as_float(v[4 * j]) * a.scale, __uint_as_float(v[4 * j + 1]) * a.scale, __uint_as_float(v[4 * j + 2]) * a.scale,
+                            __uint_as_float(v[4 * j + 3]) * a.scale);
+          } else if (EPI == DE_DIST) {
             o = make_float4(fmaf(-2.0f, __uint_as_float(v[4 * j]), 2.0f), fmaf(-2.0f, __uint_as_float(v[4 * j + 1]), 2.0f),
                             fmaf(-2.0f, __uint_as_float(v[4 * j + 2]), 2.0f), fmaf(-2.0f, __uint_as_float(v[4 * j + 3]), 2.0f));
           } else {
@@ -318,9 +321,19 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
         for (int i = 0; i < 8; ++i) {
           const int rw = i * 4 + srow;
           if (row0 + q * 32 + rw < a.L) {
-            const float4 o = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
+            float4 o = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
             float* dst = obase + (size_t)rw * a.ld + sj * 4;
             const int cc = col0 + sj * 4;
+            if (EPI == DE_STORE) {
+              float e[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                if (cc + t < a.ncols) {
+                  if (a.bias) e[t] += a.bias[cc + t];
+                  if (a.residual) e[t] += a.residual[(size_t)(row0 + q * 32 + rw) * a.ld + cc + t];
+                }
+              o = make_float4(e[0], e[1], e[2], e[3]);
+            }
             if (cc + 3 < a.ncols && (a.ld & 3) == 0) *reinterpret_cast<float4*>(dst) = o;
             else {
               if (cc < a.ncols) dst[0] = o.x;

@@ -16,6 +16,7 @@
 #include "pcn_qkv.cuh"
 #include "tail.cuh"
 #include "dgr_head.cuh"
+#include "dgr_train.cuh"
 #include "matcher.cuh"
 #include "sm_baseline.cuh"
 #include "se3_refine.cuh"
@@ -1271,6 +1272,7 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
 }  // extern "C"
 
 #include "dgr_head_api.inl"
+#include "dgr_train_api.inl"
 #include "matcher_api.inl"
 #include "compat_api.inl"
 #include "sm_api.inl"

@@ -108,6 +108,97 @@ class DgrHeadEngine:
             pass
 
 
+class DgrHeadTrainer:
+    """One data-parallel training step of the head (BASELINE.json configs[4]; reference loop: core/trainer.py:226-300 with
+    optim.SGD(lr, momentum, weight_decay), core/trainer.py:75-79).  Parameters, gradients and the momentum buffer are flat fp32 CUDA tensors in
+    state_dict order; forward / backward / SGD run in the CUDA library, the gradient all-reduce is ONE torch.distributed call over the flat
+    4.5 MB buffer (NCCL over NVLink when the process group is nccl; gloo in the CPU-side tests of the host logic).
+
+        tr = DgrHeadTrainer(device, pe=True); tr.load_state_dict(sd)
+        out = tr.forward(latents, image_feat)            # saves activations
+        tr.backward(d_out)                               # fills tr.grads (and d_latents / d_image_feat)
+        tr.step(lr=0.1, momentum=0.8, weight_decay=1e-4) # all-reduce (mean) + SGD
+    """
+
+    def __init__(self, device: int = 0, pe: bool = True):
+        self.engine = DgrHeadEngine(device, pe)
+        self.lib, self.pe, self.device = self.engine.lib, pe, torch.device("cuda", device)
+        self.spec = dgr_head_spec(pe)
+        n = int(self.lib.gmf_dgr_head_param_count(int(pe)))
+        assert n == sum(k for _, k in self.spec)
+        self.params = torch.zeros(n, device=self.device)
+        self.grads = torch.zeros(n, device=self.device)
+        self.momentum_buf = torch.zeros(n, device=self.device)
+        self.steps = 0
+        self._ws = None
+        self._saved = None
+
+    def load_state_dict(self, sd) -> None:
+        self.params.copy_(torch.from_numpy(pack_dgr_state_dict(sd, self.pe)))
+        self.steps = 0
+
+    def state_dict(self, shapes=None):
+        shapes = shapes or dgr_head_shapes(self.pe)
+        out, o = {}, 0
+        for key, numel in self.spec:
+            out[key] = self.params[o:o + numel].detach().cpu().reshape(shapes[key]).clone()
+            o += numel
+        return out
+
+    def grad_dict(self, shapes=None):
+        shapes = shapes or dgr_head_shapes(self.pe)
+        out, o = {}, 0
+        for key, numel in self.spec:
+            out[key] = self.grads[o:o + numel].detach().cpu().reshape(shapes[key]).clone()
+            o += numel
+        return out
+
+    def _workspace(self, M, T):
+        need = int(self.lib.gmf_dgr_head_train_workspace_bytes(M, T))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, latents: torch.Tensor, image_feat: torch.Tensor) -> torch.Tensor:
+        x, ctx = latents.contiguous().float(), image_feat.contiguous().float()
+        assert x.is_cuda and ctx.is_cuda and x.shape[1] == 256 and ctx.shape[1] == 128
+        ws = self._workspace(x.shape[0], ctx.shape[0])
+        out = torch.empty_like(x)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.gmf_dgr_head_train_forward(self.engine.h, self.params.data_ptr(), x.data_ptr(), ctx.data_ptr(), x.shape[0], ctx.shape[0],
+                                                       out.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        self._saved = (x, ctx)
+        return out
+
+    def backward(self, d_out: torch.Tensor, want_input_grads: bool = True):
+        if self._saved is None:
+            raise _lib.GmfError("DgrHeadTrainer.backward needs a preceding forward (activations live in the workspace)")
+        x, ctx = self._saved
+        d_out = d_out.contiguous().float()
+        d_x = torch.empty_like(x) if want_input_grads else None
+        d_ctx = torch.empty_like(ctx) if want_input_grads else None
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.gmf_dgr_head_train_backward(self.engine.h, self.params.data_ptr(), x.data_ptr(), ctx.data_ptr(), d_out.data_ptr(),
+                                                        x.shape[0], ctx.shape[0], d_x.data_ptr() if want_input_grads else None,
+                                                        d_ctx.data_ptr() if want_input_grads else None, self.grads.data_ptr(),
+                                                        self._ws.data_ptr(), self._ws.numel(), st))
+        return d_x, d_ctx
+
+    def step(self, lr: float = 0.1, momentum: float = 0.8, weight_decay: float = 1e-4, group=None) -> None:
+        """all-reduce (sum) of the flat gradient over the process group, then SGD with the mean gradient"""
+        import torch.distributed as dist
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(group)
+            if world > 1:
+                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.gmf_sgd_step(self.params.data_ptr(), self.grads.data_ptr(), self.momentum_buf.data_ptr(), self.params.numel(), lr, momentum,
+                                         weight_decay, 1.0 / world, 1 if self.steps == 0 else 0, st))
+        self.steps += 1
+
+
 # ---- parameter containers with the reference's key layout (perceiver_io.py) ----
 class _Attention(nn.Module):                       # :68-81
     def __init__(self, query_dim, context_dim, heads, dim_head):

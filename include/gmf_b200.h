@@ -172,6 +172,22 @@ int gmf_dgr_head_forward(gmf_dgr_head* h, const float* latents, const float* ima
 size_t gmf_feature_compat_workspace_bytes(int B, int N);
 int gmf_feature_compat(gmf_ctx* ctx, const float* feat, int B, int N, float* M, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- DGR head training step (BASELINE.json configs[4]) ---------------------------------------- */
+/* Reference loop: GMF_DeepGlobalRegistration_fcgf/core/trainer.py:226-300 (forward :236, loss.backward() :271, optimizer.step() :300) around
+ * model/perceiver_io.py:187-221, optimiser optim.SGD(lr, momentum, weight_decay) (core/trainer.py:75-79).  params / grads / momentum_buf: FLAT fp32
+ * device buffers of gmf_dgr_head_param_count(pe) floats in gmf_dgr_head_weight_spec order, owned by the caller (so that the gradient can be
+ * all-reduced in one NCCL call).  train_forward saves its activations in `workspace`; train_backward must follow with the same workspace, M, T,
+ * params and inputs.  grads is overwritten; d_latents [M,256] / d_image_feat [T,128] may be NULL.  Products run in TF32 on the tensor pipe. */
+size_t gmf_dgr_head_train_workspace_bytes(int M, int T);
+int64_t gmf_dgr_head_param_count(int pe);
+int gmf_dgr_head_train_forward(gmf_dgr_head* h, const float* params, const float* latents, const float* image_feat, int M, int T, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int gmf_dgr_head_train_backward(gmf_dgr_head* h, const float* params, const float* latents, const float* image_feat, const float* d_out, int M, int T,
+                                float* d_latents, float* d_image_feat, float* grads, void* workspace, size_t workspace_bytes, void* stream);
+/* torch.optim.SGD (dampening 0, no Nesterov): g = grad_scale * grad + weight_decay * p; buf = first ? g : momentum * buf + g; p -= lr * buf. */
+int gmf_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum, float weight_decay, float grad_scale,
+                 int first, void* stream);
+
 /* ---- correspondence construction (the step right before the path) ------------- */
 /* Nearest-neighbour matcher in descriptor space + network input assembly, NumPy in the reference's datasets
  * (GMF_PointDSC/datasets/ThreeDMatch.py:384-391, 401-402, 411-414; datasets/KITTI.py:94-102):
