@@ -94,7 +94,7 @@ def main():
             f = flops(m, t)
             msv = float(ms.item())
             print(json.dumps({"metric": "DGR bottleneck head training steps/sec per GPU (cfg#5: forward + backward + NCCL gradient all-reduce + SGD)",
-                              "workload": f"M={m} latents x 256, T={t} tokens x 128 per rank, pe=True, 1.12 M parameters",
+                              "workload": f"M={m} latents x 256, T={t} tokens x 128 per rank, pe=True, 0.89 M parameters",
                               "n_gpus": world, "scaling": "weak", "value": 1000.0 / msv, "aggregate_steps_per_s": world * 1000.0 / msv, "ms_per_step": msv,
                               "split_ms": {"forward": parts[0], "backward": parts[1], "allreduce_sgd": parts[2]},
                               "allreduce": {"backend": dist.get_backend() if world > 1 else None, "ranks": world, "bytes": int(tr.grads.numel() * 4)},
