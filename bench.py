@@ -456,14 +456,14 @@ def main():
         sc_flops = 4.0 * a.corr * a.corr * 128 * a.pairs * a.layers * a.steps           # 4 N^2 C per pair-layer
         ach = sc_flops / (sc_ms / 1000.0) / 1e12
         # DRAM bytes of one launch from the committed `ncu --set full` capture of this configuration
-        # (profiles/r01_top3_cfg2_ncu_raw.csv: dram__bytes_read.sum 333.43 MB + dram__bytes_write.sum 69.53 MB at 64 pairs, N=5000;
-        #  algorithmic: Q/K/V^T bf16 + distance features 5.8 MB in, m2 fp32 1.3 MB out per pair = 454 MB)
-        traffic = 402.96e6 if (a.pairs == 64 and a.corr == 5000) else None
+        # (profiles/r02_top4_cfg2_ncu_raw.csv: dram__bytes_read.sum 333.03 MB + dram__bytes_write.sum 70.21 MB at 64 pairs, N=5000;
+        #  algorithmic: Q/K fp16 + V^T bf16 + distance features 5.8 MB in, m2 fp32 1.3 MB out per pair = 454 MB)
+        traffic = 403.24e6 if (a.pairs == 64 and a.corr == 5000) else None
         # co-limit: every score element costs one MUFU.SQRT and one MUFU.EX2 at the measured 16 MUFU/clk/SM (tools/ubench/sm_rates.cu)
         mufu_floor_ms = 2.0 * a.corr * a.corr * a.pairs / (16.0 * 148 * 1.965e9) * 1e3
         roof = {"kernel": "sc_attn_v9_kernel<0,2> (SC-guided non-local flash attention, compat on the fly, gen 9)", "bound": "tensor",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r01_top3_cfg2_ncu_raw.csv)",
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_top4_cfg2_ncu_raw.csv)",
                 "peak_source": how, "avg_launch_ms": sc_ms / max(sc_n, 1), "launches": sc_n,
                 "algorithmic_flops_per_launch": sc_flops / max(sc_n, 1),
                 "mufu_colimit": {"floor_ms_per_launch": mufu_floor_ms, "frac": mufu_floor_ms / (sc_ms / max(sc_n, 1))},
@@ -497,7 +497,7 @@ def main():
         ws_gb = eng.workspace(a.pairs, a.corr, a.tokens)[1] / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, a.min_warmup),
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16 attention operands + tf32/fp16 linear layers, fp32 accumulate/softmax/classifier", "data": "synthetic",
+                "dtype": "fp16 Q/K + bf16 P/V attention operands, split-fp16 / tf32 / fp16 linear layers, fp32 accumulate/softmax/classifier", "data": "synthetic",
                 "config": config_dict(a, world),
                 "sanity": {"max_translation_error_vs_gt_mm": te_mm, "workspace_gb": ws_gb},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "strong_scaling": strong,

@@ -242,9 +242,9 @@ def test_rigid_transform_3d_matches_oracle_and_degenerate_cases():
 # north_star: inlier logits within 1e-2 abs.  The KITTI-shaped cases feed un-normalised 60 m coordinates through random-init weights, which
 # gives logits of magnitude ~10 (3DMatch-shaped: ~1.6); the measured deviations are written to gpurun_out/parity_measured.jsonl and
 # discussed in DESIGN.md section 2.
-# Measured (profiles/r02_parity_measured.jsonl): 3DMatch-shaped fixtures 1.3e-3 / 1.9e-3; cfg#3 (KITTI shape, N = 5000, 12 layers, bench weights)
-# 5.5e-3; cfg#4 1.4e-3 - all inside 1e-2 abs.  The one exception is the 2-layer KITTI fixture generated with PERTURBED norm / bias weights:
-# its logits reach 9.5 and the deviation is 1.6e-2 abs = 1.7e-3 of the logit scale (pose: 2e-5 deg, 0.01 mm; labels identical).  Attribution
+# Measured (profiles/r02_parity_measured.jsonl): 3DMatch-shaped fixtures 1.2e-3 / 1.6e-3; cfg#3 (KITTI shape, N = 5000, 12 layers, bench weights)
+# 6.8e-3; cfg#4 1.4e-3 - all inside 1e-2 abs.  The one exception is the 2-layer KITTI fixture generated with PERTURBED norm / bias weights:
+# its logits reach 9.5 and the deviation is 1.45e-2 abs = 1.5e-3 of the logit scale (pose: 2e-5 deg, 0.01 mm; labels identical).  Attribution
 # (tools/probe_precision.py): the bf16 attention probabilities P multiplying 60 m-scale value features (peaked rows, SC logits ~90).  It is
 # stated here and in DESIGN.md section 2 rather than hidden in a scaled tolerance: that fixture is held to 2e-2 abs.
 LOGIT_TOL = {"l2_n384_3dmatch": 1e-2, "l12_n512_3dmatch": 1e-2, "l2_n300_kitti": 2e-2}
