@@ -450,8 +450,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // ~100 on KITTI-scale inputs, where bf16's 8-bit significand alone costs 2e-2 on the final inlier logits (tools/probe_precision.py);
 // P (range 2^+-80 with the fixed softmax reference) and V stay bf16.  Values saturate at the fp16 maximum.
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  const __half2 t = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-  return *reinterpret_cast<const uint32_t*>(&t);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // one F2FP.SATFINITE.F16.F32.PACK_AB
+  return r;
 }
 // x = hi + lo with both parts fp16 (22 significand bits together): the operand split of the error-compensated kind::f16 GEMMs
 // (x w ~ x_hi w_hi + x_lo w_hi + x_hi w_lo) that replace TF32 where its 11-bit operands are not enough (PointCN / QKV at KITTI scale)
@@ -460,13 +461,16 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(fminf(fmaxf(x - __half2float(hi), -65504.f), 65504.f));   // |x| > 1.3e5 saturates instead of producing inf / NaN
 }
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  __half h0, l0, h1, l1;
-  split_f16(x0, h0, l0);
-  split_f16(x1, h1, l1);
-  const __half2 H = __halves2half2(h0, h1), L = __halves2half2(l0, l1);
-  hi = *reinterpret_cast<const uint32_t*>(&H);
-  lo = *reinterpret_cast<const uint32_t*>(&L);
+  hi = pack_f16(x0, x1);                                                           // saturating packed conversions: 5 instructions per pair
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16(x0 - hf.x, x1 - hf.y);
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS); `valid == false` zero-fills without reading
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
 #if defined(GMF_SC_DBG) && GMF_SC_DBG == 2
   return fmaf(x, 0.001f, 1.0f);
@@ -536,6 +540,18 @@ inline cudaError_t ensure_dyn_smem(Kern kern, int bytes, std::atomic<unsigned lo
   if (e != cudaSuccess) return e;
   done.fetch_or(bit, std::memory_order_release);
   return cudaSuccess;
+}
+
+// SM count of the current device (persistent kernels launch one CTA per SM); cached per device ordinal, 148 on a B200.
+inline int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  cache[dev & 63].store(n, std::memory_order_relaxed);
+  return n;
 }
 
 }  // namespace gmf

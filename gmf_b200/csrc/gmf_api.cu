@@ -411,14 +411,14 @@ int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* 
 #ifdef GMF_FFN_TRACE
     static int n_ffn = 0;
     const bool do_trace = (++n_ffn == 20);
-    if (do_trace) { cudaMalloc(&a.trace, 256 * 8); cudaMemsetAsync(a.trace, 0, 256 * 8, st); }
+    if (do_trace) { cudaMalloc(&a.trace, 512 * 8); cudaMemsetAsync(a.trace, 0, 512 * 8, st); }
 #endif
     ProfScope ps(CAT_FFN, st);
     cudaError_t e = launch_ffn_fused(a, B, st);
 #ifdef GMF_FFN_TRACE
     if (do_trace) {
       cudaStreamSynchronize(st);
-      long long h[256];
+      long long h[512];
       cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost);
       if (FILE* f = fopen("gpurun_out/ffn_trace.bin", "wb")) { fwrite(h, 1, sizeof(h), f); fclose(f); }
     }
@@ -792,10 +792,10 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     std::vector<int> rowmap8(1024);     // fused FFN: pass p = [value rows 64p.., gate rows 512+64p..]
     for (int p = 0; p < 8; ++p)
       for (int n = 0; n < 128; ++n) rowmap8[p * 128 + n] = n < 64 ? p * 64 + n : 512 + p * 64 + (n - 64);
-    o.w1f = blob.push(GMF_FFN_F16 ? pack_linear_f16(W1, 1024, 128, 128, &rowmap8) : pack_linear(W1, 1024, 128, 64, 128, &rowmap8));
+    o.w1f = blob.push(pack_linear_f16(W1, 1024, 128, 128, &rowmap8));
     o.b1 = blob.push(next("net.0.bias"), 1024);
     const std::vector<float> W2 = vec(next("net.2.weight"), 128 * 512);
-    o.w2f = blob.push(pack_linear(W2, 128, 512, 64, 128));
+    o.w2f = blob.push(pack_linear_f16(W2, 128, 512, 128));          // 8 chunks of [128 out rows x 64 hidden] fp16
     o.b2 = blob.push(next("net.2.bias"), 128);
     return o;
   };
@@ -839,7 +839,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
       fold_bn(W, b, 64, 64, g, be, mu, va);
       o.f2w = blob.push(pack_linear(W, 64, 64, 64, 64)); o.f2b = blob.push(b);
     }
-    o.f3w = blob.push(pack_linear(vec(next("fc_message.6.weight"), 128 * 64), 128, 64, 64, 128));
+    o.f3w = blob.push(pack_linear_f16(vec(next("fc_message.6.weight"), 128 * 64), 128, 64, 128));   // ninth W2 chunk of the fused FFN
     o.f3b = blob.push(next("fc_message.6.bias"), 128);
     {
       std::vector<float> W(384 * 128), b(384);

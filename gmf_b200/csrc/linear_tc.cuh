@@ -69,46 +69,42 @@ struct LinCfg {
   static constexpr int MIN_CTAS = (LIGHT && SMEM <= 113 * 1024) ? 2 : 1;
 };
 
-// exact (erf) GELU, F.gelu default in the reference (fusion_layer.py:57), with erf from Abramowitz-Stegun 7.1.25
-// (|err| <= 2.5e-5, i.e. <= 1.3e-5 |x| on gelu, two decades below the TF32 rounding of the product): one RCP + one EX2 + 8 FMA-pipe
-// instructions instead of erff's ~30-instruction branchy polynomial.
+// exact (erf) GELU, F.gelu default in the reference (fusion_layer.py:57):  gelu(x) = x/2 + |x|/2 (1 - erfc(|x| / sqrt2)) with
+//     erfc(|x| / sqrt2) = 2^q(|x|),   q = degree-5 polynomial without constant term (weighted minimax fit of log2 erfc, tools/fit_gelu.py):
+// |gelu error| <= 1.3e-6 over all x (q -> -inf for large |x|: 2^q -> 0, no clamp needed), 20 x below the Abramowitz-Stegun 7.1.25 form used
+// before, with ONE special-function op (EX2) instead of two (RCP + EX2) and 5 instead of 8 FMA-pipe instructions: the GEGLU arithmetic of the
+// fused FFN kernel is shared between the XU pipe and the issue port (profiles/r02_summary.md).
+#define GMF_GELU_C1 (-1.1510913f)
+#define GMF_GELU_C2 (-4.5925468e-01f)
+#define GMF_GELU_C3 (-5.2561242e-02f)
+#define GMF_GELU_C4 (7.3975129e-03f)
+#define GMF_GELU_C5 (-5.2045897e-04f)
+// Evaluated in n = -|x| (odd coefficients change sign) with the factor 1/2 folded into the exponent:  gelu(x) = max(x, 0) + n 2^(q(n) - 1).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.33267263f, ax, 1.0f)));    // 1 / (1 + 0.47047 |x| / sqrt2)
-  float p = fmaf(0.7478556f, t, -0.0958798f);
-  p = fmaf(p, t, 0.3480242f);
-  const float e = p * t * ex2_approx(-0.72134752f * x * x);                          // (1 - erf(|x| / sqrt2))
-  const float hx = 0.5f * x;
-  return fmaf(-fabsf(hx), e, hx + fabsf(hx));                                         // x/2 (1 + sign(x) erf) = hx + |hx| (1 - e)
+  const float n = -fabsf(x);
+  float q = fmaf(-GMF_GELU_C5, n, GMF_GELU_C4);
+  q = fmaf(q, n, -GMF_GELU_C3);
+  q = fmaf(q, n, GMF_GELU_C2);
+  q = fmaf(q, n, -GMF_GELU_C1);
+  return fmaf(n, ex2_approx(fmaf(q, n, -1.0f)), fmaxf(x, 0.0f));                     // ex2 = erfc(|x| / sqrt2) / 2
 }
 
 // GEGLU on two hidden units at once with packed fp32x2 arithmetic: (v + bv) * gelu_erf(g + bg) for both lanes of each 64-bit operand.
-// Same formula as gelu_erf; the polynomial, the products and the bias adds issue as one FFMA2 / FMUL2 / FADD2 per pair, the two
-// reciprocals and exponentials stay scalar MUFU ops: ~12 issue slots per element instead of ~25 (the fused FFN kernel is bound by
-// exactly this arithmetic: 65 536 hidden activations per 128-token tile).
+// Same formula as gelu_erf; the polynomial, the products and the bias adds issue as one FFMA2 / FMUL2 / FADD2 per pair, -|x|, max(x, 0) and the
+// exponentials stay scalar: 9 packed + 6 scalar instructions per pair (the fused FFN kernel is bound by the issue rate of exactly this
+// arithmetic: 65 536 hidden activations per 128-token tile).
 __device__ __forceinline__ uint64_t geglu2(uint64_t v2, uint64_t bv2, uint64_t g2, uint64_t bg2) {
   const uint64_t x2 = fadd2(g2, bg2);
   float x0, x1;
   unpack2(x2, x0, x1);
-  const uint64_t ax2 = pack2(fabsf(x0), fabsf(x1));
-  const uint64_t d2 = ffma2(pack2(0.33267263f, 0.33267263f), ax2, pack2(1.0f, 1.0f));
-  float d0, d1, t0, t1;
-  unpack2(d2, d0, d1);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
-  const uint64_t t2 = pack2(t0, t1);
-  uint64_t p2 = ffma2(pack2(0.7478556f, 0.7478556f), t2, pack2(-0.0958798f, -0.0958798f));
-  p2 = ffma2(p2, t2, pack2(0.3480242f, 0.3480242f));
+  const uint64_t n2 = pack2(-fabsf(x0), -fabsf(x1));
+  uint64_t q2 = ffma2(pack2(-GMF_GELU_C5, -GMF_GELU_C5), n2, pack2(GMF_GELU_C4, GMF_GELU_C4));
+  q2 = ffma2(q2, n2, pack2(-GMF_GELU_C3, -GMF_GELU_C3));
+  q2 = ffma2(q2, n2, pack2(GMF_GELU_C2, GMF_GELU_C2));
+  q2 = ffma2(q2, n2, pack2(-GMF_GELU_C1, -GMF_GELU_C1));
   float a0, a1;
-  unpack2(fmul2(fmul2(x2, pack2(-0.72134752f, -0.72134752f)), x2), a0, a1);
-  const uint64_t e2 = fmul2(fmul2(p2, t2), pack2(ex2_approx(a0), ex2_approx(a1)));     // 1 - erf(|x| / sqrt2)
-  const uint64_t hx2 = fmul2(x2, pack2(0.5f, 0.5f));
-  float h0, h1;
-  unpack2(hx2, h0, h1);
-  const uint64_t nah2 = pack2(-fabsf(h0), -fabsf(h1));
-  const uint64_t s2 = ffma2(nah2, pack2(-1.0f, -1.0f), hx2);                            // hx + |hx|
-  const uint64_t gelu = ffma2(nah2, e2, s2);
+  unpack2(ffma2(q2, n2, pack2(-1.0f, -1.0f)), a0, a1);
+  const uint64_t gelu = ffma2(n2, pack2(ex2_approx(a0), ex2_approx(a1)), pack2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
   return fmul2(fadd2(v2, bv2), gelu);
 }
 
