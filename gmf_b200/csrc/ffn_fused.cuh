@@ -12,7 +12,7 @@
 // With the fused NonLocalBlock tail (m2 != NULL) the LayerNorm warps also park m2 (fp16) in tensor memory and a ninth MMA2 step adds m2 . W3^T.
 // TMEM (512 columns): ACC1 2 x 128 | H 2 x 32 | m2 2 x 32 | OUT 128.  Shared memory: LN(x) tile image 2 x 32 KB (double buffered across tiles), W1 ring
 // 2 x 32 KB, W2 ring 2 x 16 KB, epilogue staging 16 x 4 KB.  Warps: 0-15 workers (GEGLU, output epilogue), 16 MMA1 issuer, 17 MMA2 issuer,
-// 18 weight producer, 20-23 LayerNorm of the tile after the current one (one per SM sub-partition: the kernel is bound by instruction issue, and
+// 18 / 19 W1 / W2 producers, 20-23 LayerNorm of the tile after the current one (one per SM sub-partition: the kernel is bound by instruction issue, and
 // a single LayerNorm warp competing with four GEGLU warps on its sub-partition needed 40 k cycles per tile).  768 threads x 80 registers.
 #pragma once
 #include <cuda_fp16.h>
@@ -54,6 +54,18 @@ struct FfnArgs {
   float* out_img;
 };
 
+// residual rows [32 x 32 floats] of one worker warp -> its swizzled staging tile, 8 x 16-byte asynchronous copies per lane
+__device__ __noinline__ void ffn_stage_residual(float* stg, const float* src, int rows_left, int lane) {
+  const int srow = lane >> 3, sj = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rw = i * 4 + srow;
+    const bool ok = rw < rows_left;
+    cp_async16(stg + rw * 32 + ((sj ^ (rw & 7)) << 2), ok ? src + (size_t)rw * 128 + sj * 4 : src, ok);
+  }
+  cp_async_commit();
+}
+
 __global__ void __launch_bounds__(FfnCfg::THREADS, 1) ffn_fused_kernel(const FfnArgs a) {
   using Cfg = FfnCfg;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -63,20 +75,21 @@ __global__ void __launch_bounds__(FfnCfg::THREADS, 1) ffn_fused_kernel(const Ffn
   uint8_t* sW2 = sW1 + 2 * Cfg::W1_BYTES;                 // [2] stages
   float* sStg = (float*)(sW2 + 2 * Cfg::W2_BYTES);
   uint64_t* bars = (uint64_t*)((uint8_t*)sStg + Cfg::STG_BYTES);
-  uint64_t* a_ready = bars;            // [2] 128  LayerNorm warps -> MMA1
-  uint64_t* a_free = bars + 2;         // [2]      MMA1 of a tile retired -> LayerNorm warp (tile + 2)
-  uint64_t* full1 = bars + 4;          // [2]
-  uint64_t* empty1 = bars + 6;         // [2]
-  uint64_t* full2 = bars + 8;          // [2]
-  uint64_t* empty2 = bars + 10;        // [2]
-  uint64_t* acc1_full = bars + 12;     // [2]
-  uint64_t* acc1_free = bars + 14;     // [2] 512
-  uint64_t* h_ready = bars + 16;       // [2] 512
-  uint64_t* h_free = bars + 18;        // [2]
-  uint64_t* out_full = bars + 20;      //          last MMA2 of a tile retired -> workers
-  uint64_t* out_free = bars + 21;      // 512      workers have read OUT -> MMA2 of the next tile
-  uint64_t* m2_ready = bars + 22;      // [2] 128  LayerNorm warps parked m2 (fp16) in tensor memory -> MMA2
-  uint64_t* m2_free = bars + 24;       // [2]      tail MMA of a tile retired -> LayerNorm warps (tile + 2)
+  const uint32_t bar0 = smem_u32(bars);                    // barriers are addressed as bar0 + 8 i (common.cuh BarArr): no per-op address re-derivation
+  const BarArr a_ready{bar0};                     // [2] 128  LayerNorm warps -> MMA1
+  const BarArr a_free = BarArr{bar0} + 2;  // [2]      MMA1 of a tile retired -> LayerNorm warp (tile + 2)
+  const BarArr full1 = BarArr{bar0} + 4;  // [2]
+  const BarArr empty1 = BarArr{bar0} + 6;  // [2]
+  const BarArr full2 = BarArr{bar0} + 8;  // [2]
+  const BarArr empty2 = BarArr{bar0} + 10;  // [2]
+  const BarArr acc1_full = BarArr{bar0} + 12;  // [2]
+  const BarArr acc1_free = BarArr{bar0} + 14;  // [2] 512
+  const BarArr h_ready = BarArr{bar0} + 16;  // [2] 512
+  const BarArr h_free = BarArr{bar0} + 18;  // [2]
+  const BarArr out_full = BarArr{bar0} + 20;  //          last MMA2 of a tile retired -> workers
+  const BarArr out_free = BarArr{bar0} + 21;  // 512      workers have read OUT -> MMA2 of the next tile
+  const BarArr m2_ready = BarArr{bar0} + 22;  // [2] 128  LayerNorm warps parked m2 (fp16) in tensor memory -> MMA2
+  const BarArr m2_free = BarArr{bar0} + 24;  // [2]      tail MMA of a tile retired -> LayerNorm warps (tile + 2)
   uint32_t* tmem_slot = (uint32_t*)(bars + 26);
   float* sBias = (float*)(bars + 64);                     // [128] b2 (+ b3): output bias of the block
 
@@ -107,32 +120,36 @@ __global__ void __launch_bounds__(FfnCfg::THREADS, 1) ffn_fused_kernel(const Ffn
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 18) {
-    // ------------------------------- weight producer: W1 one pass ahead of W2, both through 2-deep rings, running across tiles -----------
-    // Order per tile: W1(0), then W1(p) before W2(p-1): the wait for a W2 slot (MMA2 two passes back) never delays a W1 stage that is already
-    // free.  Every load only waits for MMAs whose own operands precede it in this order, so the sequence cannot deadlock.
+    // ------------------------------- W1 producer: one 32 KB stage per pass through a 2-deep ring, running across tiles -------------------
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint8_t* w1 = (const uint8_t*)a.w1_packed;
-    const uint8_t* w2 = (const uint8_t*)a.w2_packed;
-    int s1 = 0, s2 = 0;
+    int s1 = 0;
 #pragma unroll 1
     for (int g = blockIdx.x; g < total; g += gridDim.x) {
 #pragma unroll 1
-      for (int p = 0; p <= NP; ++p) {
-        if (p < Cfg::PASSES) {
-          const int slot = s1 & 1;
-          if (s1 >= 2) mbar_wait(&empty1[slot], ((s1 >> 1) - 1) & 1);
-          mbar_expect_tx_p(&full1[slot], Cfg::W1_BYTES, leader);
-          bulk_g2s_p(sW1 + slot * Cfg::W1_BYTES, w1 + (size_t)p * Cfg::W1_BYTES, Cfg::W1_BYTES, &full1[slot], leader);
-          ++s1;
-        }
-        if (p >= 1) {
-          const int c = p - 1, slot = s2 & 1;                  // chunk 8 = fc_message.6 weight of the fused block tail
-          if (s2 >= 2) mbar_wait(&empty2[slot], ((s2 >> 1) - 1) & 1);
-          mbar_expect_tx_p(&full2[slot], Cfg::W2_BYTES, leader);
-          bulk_g2s_p(sW2 + slot * Cfg::W2_BYTES, c < Cfg::PASSES ? w2 + (size_t)c * Cfg::W2_BYTES : (const uint8_t*)a.w3_packed, Cfg::W2_BYTES,
-                     &full2[slot], leader);
-          ++s2;
-        }
+      for (int p = 0; p < Cfg::PASSES; ++p, ++s1) {
+        const int slot = s1 & 1;
+        if (s1 >= 2) mbar_wait(&empty1[slot], ((s1 >> 1) - 1) & 1);
+        mbar_expect_tx_p(&full1[slot], Cfg::W1_BYTES, leader);
+        bulk_g2s_p(sW1 + slot * Cfg::W1_BYTES, w1 + (size_t)p * Cfg::W1_BYTES, Cfg::W1_BYTES, &full1[slot], leader);
+      }
+    }
+  } else if (warp == 19) {
+    // ------------------------------- W2 producer: one 16 KB chunk per MMA2 step (chunk 8 = fc_message.6 weight of the fused block tail) -----
+    // A warp of its own: behind the W1 loads in one instruction stream, a wait for a W2 slot (MMA2 two steps back) delayed the W1 stage of the
+    // next pass and with it MMA1.
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint8_t* w2 = (const uint8_t*)a.w2_packed;
+    int s2 = 0;
+#pragma unroll 1
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+#pragma unroll 1
+      for (int c = 0; c < NP; ++c, ++s2) {
+        const int slot = s2 & 1;
+        if (s2 >= 2) mbar_wait(&empty2[slot], ((s2 >> 1) - 1) & 1);
+        mbar_expect_tx_p(&full2[slot], Cfg::W2_BYTES, leader);
+        bulk_g2s_p(sW2 + slot * Cfg::W2_BYTES, c < Cfg::PASSES ? w2 + (size_t)c * Cfg::W2_BYTES : (const uint8_t*)a.w3_packed, Cfg::W2_BYTES,
+                   &full2[slot], leader);
       }
     }
   } else if (warp == 16) {
@@ -322,143 +339,148 @@ __global__ void __launch_bounds__(FfnCfg::THREADS, 1) ffn_fused_kernel(const Ffn
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     float* stg = sStg + warp * 1024;
     const int srow = lane >> 3, sj = lane & 7;
-    int it = 0;
+    // Software pipeline over the tiles of this CTA: the output epilogue of tile i - 1 runs AFTER the first GEGLU pass of tile i, so that the
+    // last MMA2s of tile i - 1 (and the fused block tail) retire underneath that pass instead of being waited for.
+    const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 #pragma unroll 1
-    for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
+    for (int it = 0; it <= my_tiles; ++it) {
+      const bool has = it < my_tiles;                            // it == my_tiles: only the epilogue of the last tile is left
+      const int g = blockIdx.x + it * gridDim.x;
       const int pair = g / a.tiles, tile = g - pair * a.tiles;
       const int row0 = tile * 128;
       if (warp == 0) TR(0, 0);
       // ---------------- GEGLU between the two GEMMs ----------------
 #pragma unroll 1
-      for (int p = 0; p < Cfg::PASSES; ++p) {
-        const int b = p & 1;                                     // 8 passes per tile: buffers and parities of pass p are the same in every tile
-        const int hc0 = p * 64 + cq * 16;                        // hidden column of v[0]
-        float4 b1v[4], b1g[4];                                   // bias loads in flight while waiting for the accumulator
+      for (int p = 0; p < (has ? Cfg::PASSES : 1); ++p) {
+        if (has) {
+          const int b = p & 1;                                     // 8 passes per tile: buffers and parities of pass p are the same in every tile
+          const int hc0 = p * 64 + cq * 16;                        // hidden column of v[0]
+          float4 b1v[4], b1g[4];                                   // bias loads in flight while waiting for the accumulator
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          b1v[i] = __ldg(reinterpret_cast<const float4*>(a.b1 + hc0) + i);
-          b1g[i] = __ldg(reinterpret_cast<const float4*>(a.b1 + 512 + hc0) + i);
+          for (int i = 0; i < 4; ++i) {
+            b1v[i] = __ldg(reinterpret_cast<const float4*>(a.b1 + hc0) + i);
+            b1g[i] = __ldg(reinterpret_cast<const float4*>(a.b1 + 512 + hc0) + i);
+          }
+          if (p == Cfg::PASSES - 3) {
+            // residual rows of this warp's 32 x 32 output block -> staging tile (asynchronous, zero-filled past L); the image blocks of the
+            // previous tile have long left the tile (their bulk stores were issued more than five passes ago).  Out of line: inlined, its
+            // address arithmetic was hoisted into every pass.
+            if (a.out_img) {
+              if (lane == 0) bulk_wait_read();
+              __syncwarp();
+            }
+            ffn_stage_residual(stg, a.x + ((size_t)pair * a.L + row0 + q * 32) * 128 + cq * 32, a.L - (row0 + q * 32), lane);
+          }
+          if (warp == 0) TR(3, 4 * p);
+          mbar_wait(&acc1_full[b], (p >> 1) & 1);
+          tc_fence_after();
+          if (warp == 0) TR(3, 4 * p + 1);
+          uint32_t v[16], gt[16];
+          tmem_ld16(trow + b * 128 + cq * 16, v);
+          tmem_ld16(trow + b * 128 + 64 + cq * 16, gt);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&acc1_free[b]);                              // MMA1 two passes on may overwrite the accumulator
+          uint32_t hw[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b1 = b1v[i], b2 = b1g[i];
+            float o0, o1, o2, o3;
+            unpack2(geglu2(pack2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), pack2(b1.x, b1.y),
+                           pack2(__uint_as_float(gt[4 * i]), __uint_as_float(gt[4 * i + 1])), pack2(b2.x, b2.y)), o0, o1);
+            unpack2(geglu2(pack2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), pack2(b1.z, b1.w),
+                           pack2(__uint_as_float(gt[4 * i + 2]), __uint_as_float(gt[4 * i + 3])), pack2(b2.z, b2.w)), o2, o3);
+            hw[2 * i] = pack_f16(o0, o1);
+            hw[2 * i + 1] = pack_f16(o2, o3);
+          }
+          if (warp == 0) TR(3, 4 * p + 2);
+          if (it > 0 || p >= 2) { mbar_wait(&h_free[b], ((p >> 1) - 1) & 1); tc_fence_after(); }   // MMA2 two passes back has read H[b]
+          if (warp == 0) TR(3, 4 * p + 3);
+          tmem_st8(trow + Cfg::COL_H + b * 32 + cq * 8, hw);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&h_ready[b]);
+      
         }
-        if (p == Cfg::PASSES - 3) {
-          // residual rows of this warp's 32 x 32 output block -> staging tile (asynchronous, zero-filled past L); the image blocks of the
-          // previous tile have long left the tile (their bulk stores were issued more than five passes ago)
+        if (p == 0 && it > 0) {
+          const int eg = g - gridDim.x, eit = it - 1;
+          const int epair = eg / a.tiles, erow0 = (eg - epair * a.tiles) * 128;
+          // ---------------- out = OUT + b2 (+ b3) + x, assembled through the per-warp staging tile (one 32-column chunk per warp) ----------------
+          if (warp == 0) TR(0, 2);
+          const int col0 = cq * 32;
+          const size_t gbase = ((size_t)epair * a.L + erow0 + q * 32) * 128 + col0;
+          cp_async_wait_all();                                       // residual rows have landed in the staging tile
+          __syncwarp();
+          if (warp == 0) TR(0, 7);
+          mbar_wait(out_full, eit & 1);
+          tc_fence_after();
+          if (warp == 0) TR(0, 3);
+          uint32_t v[32];
+          tmem_ld32(trow + Cfg::COL_OUT + cq * 32, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(out_free);                                     // MMA2 of the next tile may start accumulating
+          if (warp == 0) TR(0, 8);
+          const bool live = erow0 + r < a.L;
+  #pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = *reinterpret_cast<const float4*>(sBias + col0 + 4 * j);
+            float4* slot = reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2));
+            const float4 res = *slot;
+            const float4 o = make_float4(__uint_as_float(v[4 * j]) + bb.x + res.x, __uint_as_float(v[4 * j + 1]) + bb.y + res.y,
+                                         __uint_as_float(v[4 * j + 2]) + bb.z + res.z, __uint_as_float(v[4 * j + 3]) + bb.w + res.w);
+            if (a.out_img) {                                         // kept in registers: the image is assembled below
+              v[4 * j] = __float_as_uint(live ? o.x : 0.f); v[4 * j + 1] = __float_as_uint(live ? o.y : 0.f);
+              v[4 * j + 2] = __float_as_uint(live ? o.z : 0.f); v[4 * j + 3] = __float_as_uint(live ? o.w : 0.f);
+            } else {
+              *slot = o;
+            }
+          }
+          __syncwarp();
+          if (warp == 0) TR(0, 9);
           if (a.out_img) {
-            if (lane == 0) bulk_wait_read();
+            // Split fp16 image (x = hi + lo): fp16 swizzle atoms are 64 columns wide, so warps (q, 2m) and (q, 2m + 1) share the 32-row blocks of
+            // atom m.  Their two 4 KB staging tiles become that block of the hi image (even warp's tile) and of the lo image (odd warp's tile);
+            // each warp then ships the block that sits in its own tile.
+            const int m = cq >> 1;
+            const int pair_bar = 1 + m * 4 + q;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // both warps have read their residual rows out of the tiles
+            if (warp == 0) TR(0, 10);
+            uint8_t* blk_hi = (uint8_t*)(sStg + ((2 * m) * 4 + q) * 1024);
+            uint8_t* blk_lo = (uint8_t*)(sStg + ((2 * m + 1) * 4 + q) * 1024);
+  #pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              uint4 H, Lw;
+              split_f16x2(__uint_as_float(v[8 * jj]), __uint_as_float(v[8 * jj + 1]), H.x, Lw.x);
+              split_f16x2(__uint_as_float(v[8 * jj + 2]), __uint_as_float(v[8 * jj + 3]), H.y, Lw.y);
+              split_f16x2(__uint_as_float(v[8 * jj + 4]), __uint_as_float(v[8 * jj + 5]), H.z, Lw.z);
+              split_f16x2(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7]), H.w, Lw.w);
+              const uint32_t off = swz_off(lane, (cq & 1) * 4 + jj);
+              *reinterpret_cast<uint4*>(blk_hi + off) = H;
+              *reinterpret_cast<uint4*>(blk_lo + off) = Lw;
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            if (warp == 0) TR(0, 11);
+            // 16 x 4 KB bulk stores in flight, no CTA-wide barrier: tile layout [hi atom 0 | hi atom 1 | lo atom 0 | lo atom 1], 16 KB each
+            if (lane == 0) {
+              uint8_t* img = (uint8_t*)(a.out_img + (size_t)eg * (128 * 128));
+              bulk_s2g(img + (cq & 1) * 32768 + (cq >> 1) * 16384 + q * 4096, stg, 4096);
+              bulk_commit();
+            }
+            __syncwarp();
+          } else {
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rw = i * 4 + srow;
+              if (erow0 + q * 32 + rw < a.L)
+                *reinterpret_cast<float4*>(a.out + gbase + (size_t)rw * 128 + sj * 4) = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
+            }
             __syncwarp();
           }
-          const size_t gb = ((size_t)pair * a.L + row0 + q * 32) * 128 + cq * 32;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rw = i * 4 + srow;
-            const bool ok = row0 + q * 32 + rw < a.L;
-            cp_async16(stg + rw * 32 + ((sj ^ (rw & 7)) << 2), a.x + (ok ? gb + (size_t)rw * 128 + sj * 4 : 0), ok);
-          }
-          cp_async_commit();
-        }
-        if (warp == 0) TR(3, 4 * p);
-        mbar_wait(&acc1_full[b], (p >> 1) & 1);
-        tc_fence_after();
-        if (warp == 0) TR(3, 4 * p + 1);
-        uint32_t v[16], gt[16];
-        tmem_ld16(trow + b * 128 + cq * 16, v);
-        tmem_ld16(trow + b * 128 + 64 + cq * 16, gt);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&acc1_free[b]);                              // MMA1 two passes on may overwrite the accumulator
-        uint32_t hw[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b1 = b1v[i], b2 = b1g[i];
-          float o0, o1, o2, o3;
-          unpack2(geglu2(pack2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), pack2(b1.x, b1.y),
-                         pack2(__uint_as_float(gt[4 * i]), __uint_as_float(gt[4 * i + 1])), pack2(b2.x, b2.y)), o0, o1);
-          unpack2(geglu2(pack2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), pack2(b1.z, b1.w),
-                         pack2(__uint_as_float(gt[4 * i + 2]), __uint_as_float(gt[4 * i + 3])), pack2(b2.z, b2.w)), o2, o3);
-          hw[2 * i] = pack_f16(o0, o1);
-          hw[2 * i + 1] = pack_f16(o2, o3);
-        }
-        if (warp == 0) TR(3, 4 * p + 2);
-        if (it > 0 || p >= 2) { mbar_wait(&h_free[b], ((p >> 1) - 1) & 1); tc_fence_after(); }   // MMA2 two passes back has read H[b]
-        if (warp == 0) TR(3, 4 * p + 3);
-        tmem_st8(trow + Cfg::COL_H + b * 32 + cq * 8, hw);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&h_ready[b]);
-      }
-      // ---------------- out = OUT + b2 (+ b3) + x, assembled through the per-warp staging tile (one 32-column chunk per warp) ----------------
-      if (warp == 0) TR(0, 2);
-      const int col0 = cq * 32;
-      const size_t gbase = ((size_t)pair * a.L + row0 + q * 32) * 128 + col0;
-      cp_async_wait_all();                                       // residual rows have landed in the staging tile
-      __syncwarp();
-      if (warp == 0) TR(0, 7);
-      mbar_wait(out_full, it & 1);
-      tc_fence_after();
-      if (warp == 0) TR(0, 3);
-      uint32_t v[32];
-      tmem_ld32(trow + Cfg::COL_OUT + cq * 32, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(out_free);                                     // MMA2 of the next tile may start accumulating
-      if (warp == 0) TR(0, 8);
-      const bool live = row0 + r < a.L;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 bb = *reinterpret_cast<const float4*>(sBias + col0 + 4 * j);
-        float4* slot = reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2));
-        const float4 res = *slot;
-        const float4 o = make_float4(__uint_as_float(v[4 * j]) + bb.x + res.x, __uint_as_float(v[4 * j + 1]) + bb.y + res.y,
-                                     __uint_as_float(v[4 * j + 2]) + bb.z + res.z, __uint_as_float(v[4 * j + 3]) + bb.w + res.w);
-        if (a.out_img) {                                         // kept in registers: the image is assembled below
-          v[4 * j] = __float_as_uint(live ? o.x : 0.f); v[4 * j + 1] = __float_as_uint(live ? o.y : 0.f);
-          v[4 * j + 2] = __float_as_uint(live ? o.z : 0.f); v[4 * j + 3] = __float_as_uint(live ? o.w : 0.f);
-        } else {
-          *slot = o;
+          if (warp == 0) TR(0, 4);
         }
       }
-      __syncwarp();
-      if (warp == 0) TR(0, 9);
-      if (a.out_img) {
-        // Split fp16 image (x = hi + lo): fp16 swizzle atoms are 64 columns wide, so warps (q, 2m) and (q, 2m + 1) share the 32-row blocks of
-        // atom m.  Their two 4 KB staging tiles become that block of the hi image (even warp's tile) and of the lo image (odd warp's tile);
-        // each warp then ships the block that sits in its own tile.
-        const int m = cq >> 1;
-        const int pair_bar = 1 + m * 4 + q;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // both warps have read their residual rows out of the tiles
-        if (warp == 0) TR(0, 10);
-        uint8_t* blk_hi = (uint8_t*)(sStg + ((2 * m) * 4 + q) * 1024);
-        uint8_t* blk_lo = (uint8_t*)(sStg + ((2 * m + 1) * 4 + q) * 1024);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          uint4 H, Lw;
-          split_f16x2(__uint_as_float(v[8 * jj]), __uint_as_float(v[8 * jj + 1]), H.x, Lw.x);
-          split_f16x2(__uint_as_float(v[8 * jj + 2]), __uint_as_float(v[8 * jj + 3]), H.y, Lw.y);
-          split_f16x2(__uint_as_float(v[8 * jj + 4]), __uint_as_float(v[8 * jj + 5]), H.z, Lw.z);
-          split_f16x2(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7]), H.w, Lw.w);
-          const uint32_t off = swz_off(lane, (cq & 1) * 4 + jj);
-          *reinterpret_cast<uint4*>(blk_hi + off) = H;
-          *reinterpret_cast<uint4*>(blk_lo + off) = Lw;
-        }
-        fence_proxy_async();
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        if (warp == 0) TR(0, 11);
-        // 16 x 4 KB bulk stores in flight, no CTA-wide barrier: tile layout [hi atom 0 | hi atom 1 | lo atom 0 | lo atom 1], 16 KB each
-        if (lane == 0) {
-          uint8_t* img = (uint8_t*)(a.out_img + (size_t)g * (128 * 128));
-          bulk_s2g(img + (cq & 1) * 32768 + (cq >> 1) * 16384 + q * 4096, stg, 4096);
-          bulk_commit();
-        }
-        __syncwarp();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rw = i * 4 + srow;
-          if (row0 + q * 32 + rw < a.L)
-            *reinterpret_cast<float4*>(a.out + gbase + (size_t)rw * 128 + sj * 4) = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
-        }
-        __syncwarp();
-      }
-      if (warp == 0) TR(0, 4);
     }
     if (a.out_img && lane == 0) bulk_wait_read();
   }
