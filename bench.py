@@ -80,7 +80,7 @@ def per_kernel_roofline(prof, a, steps, peak_tf, hbm):
         "ffn_geglu": ("tensor", (2.0 * t * C * 1024 + 2.0 * t * 512 * C) + L * (2.0 * n * C * 1024 + 2.0 * n * 512 * C + 2.0 * n * 64 * C)),
         "pcn_qkv": ("hbm", L * (4.0 * C * n + 4.0 * C * n + 3 * 2.0 * C * n)),                    # feat in; feat1 fp32 + Q,K,V^T bf16 out
         "fusion_q_proj": ("hbm", (4.0 * C * t + 2.0 * 64 * t) + L * (4.0 * C * n + 4.0 * C * n + 2.0 * 64 * n)),   # x in; (x + dwconv) fp32 + Q bf16 out
-        "fusion_kv_proj": ("hbm", (1 + L) * (4.0 * C * t + 2 * 2.0 * 64 * t)),                    # context in; K, V^T bf16 out
+        "fusion_kv_proj": ("hbm", 2 * 4.0 * C * t + (1 + L) * 2 * 2.0 * 64 * t),                  # Fusion-1 context in + encoder context in ONCE for all layers; K, V^T 16-bit out per layer
         "prep_layer0": ("hbm", 24.0 * n * 2 + 24.0 * n + 4.0 * C * n + 2 * 2.0 * 64 * n + 32.0 * n),
         "classify": ("hbm", 4.0 * C * n + 4.0 * C * n + 4.0 * n),
         "pick_seeds": ("hbm", 16.0 * n + 4.0 * S),

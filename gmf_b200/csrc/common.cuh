@@ -432,6 +432,29 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ------------------------------------------------------------------------------------------------
 // small math helpers
 // ------------------------------------------------------------------------------------------------
+// Warp-wide sums of EIGHT values at once (v[i] <- sum over the 32 lanes of v[i], for every lane).  Transposing reduction: each exchange step
+// halves the number of live values (xor 16: 8 -> 4, xor 8: 4 -> 2, xor 4: 2 -> 1), two more steps finish the row a lane ended up with
+// ((lane >> 2) & 7), eight indexed shuffles hand every total to every lane: 17 SHFL with a dependent chain of 6, instead of 8 x 5 butterfly steps
+// - which ptxas, under register pressure, schedules as eight SERIAL 5-step chains (~150 cycles each; LayerNorm of an 8-row batch took ~2.5 k).
+__device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+  float w[4], u[2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = h4 ? v[j] : v[j + 4], keep = h4 ? v[j + 4] : v[j];
+    w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);        // rows j + 4 h4
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = h3 ? w[j] : w[j + 2], keep = h3 ? w[j + 2] : w[j];
+    u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);         // rows j + 2 h3 + 4 h4
+  }
+  float t = (h2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, h2 ? u[0] : u[1], 4);   // row h2 + 2 h3 + 4 h4
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __shfl_sync(0xffffffffu, t, i << 2);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -269,15 +269,12 @@ __global__ void __launch_bounds__(FfnCfg::THREADS, 1) ffn_fused_kernel(const Ffn
           rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (rbase + i < rows_left) rv[i] = *reinterpret_cast<const float4*>(xp + (size_t)(rbase + i) * 128 + c4);
         }
-        // branch-free sweeps so that the shuffle-reduction chains of the 8 rows interleave (rows past L are zeros)
+        // the 8 rows of a batch are reduced together (common.cuh warp_sum8; rows past L are zeros)
         float mean[RPW], rs[RPW];
         uint64_t d01[RPW], d23[RPW];
 #pragma unroll
         for (int i = 0; i < RPW; ++i) mean[i] = (rv[i].x + rv[i].y) + (rv[i].z + rv[i].w);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int i = 0; i < RPW; ++i) mean[i] += __shfl_xor_sync(0xffffffffu, mean[i], o);
+        warp_sum8(mean, lane);
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
           const float nm = mean[i] * (-1.0f / 128.0f);
@@ -288,10 +285,7 @@ __global__ void __launch_bounds__(FfnCfg::THREADS, 1) ffn_fused_kernel(const Ffn
           unpack2(ffma2(d23[i], d23[i], fmul2(d01[i], d01[i])), s0, s1);
           rs[i] = s0 + s1;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int i = 0; i < RPW; ++i) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+        warp_sum8(rs, lane);
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
           const float r_ = rsqrtf(rs[i] * (1.0f / 128.0f) + 1e-5f);

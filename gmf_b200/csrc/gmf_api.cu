@@ -13,6 +13,7 @@
 #include "sc_attn_v9.cuh"
 #include "fus_attn_v2.cuh"
 #include "ffn_fused.cuh"
+#include "kv_proj_all.cuh"
 #include "pcn_qkv.cuh"
 #include "tail.cuh"
 #include "dgr_head.cuh"
@@ -223,6 +224,7 @@ struct FusionW {
   const float *lnq_g, *lnq_b, *lnc_g, *lnc_b, *lnf_g, *lnf_b;
   const float *wq, *wkv, *wo, *bo, *b1, *b2;
   const float *w1f, *w2f;   // fused-FFN packing (8 passes of 64 hidden columns)
+  const float* wkv16 = nullptr;   // to_kv.weight as one fp16 image (kv_proj_all.cuh)
 };
 struct LayerW {
   const float *pcn_b, *qkv_w, *qkv_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
@@ -381,6 +383,9 @@ int run_fusion_kv(const FusionW& f, const float* ctxk, int B, int Lk, __nv_bfloa
 int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* resid0, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
                     float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3, float* out_img = nullptr);
 
+// context K / V^T of every encoder layer from the Fusion-1 output, one persistent kernel (kv_proj_all.cuh)
+int run_fusion_kv_all(const gmf_ctx* ctx, Work& w, const float* ctxk, int B, int Lk, cudaStream_t st);
+
 // FusionLayer.forward (fusion_layer.py:172-201), everything on one stream
 int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st,
                const float* tail_m2 = nullptr, const float* tail_w3 = nullptr, const float* tail_b3 = nullptr) {
@@ -477,8 +482,39 @@ int run_sc_attention(const gmf_ctx* ctx, const LayerW& lw, Work& w, const float*
 }
 
 // PointCN_layer_i + NonLocal_layer_i (PointDSC.py:140-142, 40-74)
+int run_fusion_kv_all(const gmf_ctx* ctx, Work& w, const float* ctxk, int B, int Lk, cudaStream_t st) {
+  const int L = ctx->cfg.num_layers;
+  if (L > KvAllCfg::MAX_LAYERS) return fail(GMF_ERR_INVALID, "run_fusion_kv_all: too many layers");
+  KvAllArgs a{};
+  a.x = ctxk; a.L = Lk; a.tiles = cdiv(Lk, 128); a.pairs = B; a.layers = L;
+  for (int li = 0; li < L; ++li) {
+    const FusionW& f = ctx->layers[li].f2;
+    a.layer[li] = KvLayer{f.cpe_c_w, f.cpe_c_b, f.lnc_g, f.lnc_b, f.wkv16, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride};
+  }
+#ifdef GMF_FFN_TRACE
+  static int n_kv = 0;
+  const bool do_trace = (++n_kv == 3);
+  if (do_trace) { cudaMalloc(&a.trace, 512 * 8); cudaMemsetAsync(a.trace, 0, 512 * 8, st); }
+#endif
+  ProfScope ps(CAT_KVFUS, st);
+  cudaError_t e = launch_kv_proj_all(a, st);
+#ifdef GMF_FFN_TRACE
+  if (do_trace) {
+    cudaStreamSynchronize(st);
+    long long h[512];
+    cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen("gpurun_out/kv_trace.bin", "wb")) { fwrite(h, 1, sizeof(h), f); fclose(f); }
+  }
+#endif
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail_cuda(e, "kv_proj_all launch");
+  return 0;
+}
+
+// kv_ready: this layer's context K / V^T already sit in w.kf_all / w.vtf_all (run_fusion_kv_all)
 int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in, const float* image_feat, int B, int N, int T,
-                      float* feat_out, cudaStream_t st, const gmf_ctx::Lane* lane = nullptr, bool in_img = false, bool out_img = false) {
+                      float* feat_out, cudaStream_t st, const gmf_ctx::Lane* lane = nullptr, bool in_img = false, bool out_img = false,
+                      bool kv_ready = false) {
   const bool overlapped = lane != nullptr;
   const LayerW& lw = ctx->layers[li];
   {   // PointCN (conv + folded BN + ReLU) chained with the Q/K/V projections
@@ -504,9 +540,13 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
   // fc_message.6(m2) + fusion_layer_2 output (PointDSC.py:73) are folded into the fused FFN kernel's tail
   if (overlapped) {
     CU(cudaStreamWaitEvent(st, lane->ev_q, 0));
-    CU(cudaStreamWaitEvent(st, lane->ev_kv[li], 0));
     return run_fusion_core(ctx, lw.f2, w, resid0, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
                            lw.fc3_w, lw.fc3_b, out_img ? w.feat_img : nullptr);
+  }
+  if (kv_ready) {
+    TRY(run_fusion_q(lw.f2, w, w.feat1, B, N, &resid0, st));
+    return run_fusion_core(ctx, lw.f2, w, resid0, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
+                           lw.fc3_w, lw.fc3_b, nullptr);
   }
   return run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, feat_out, st, w.m2, lw.fc3_w, lw.fc3_b);
 }
@@ -606,19 +646,12 @@ int forward_chunk(gmf_ctx* ctx, gmf_ctx::Lane* lane, Work& w, const float* corr,
   const int L = ctx->cfg.num_layers;
   // per-launch profiling (gmf_profile_enable) times every kernel alone: it uses the single-stream schedule
   const bool overlapped = lane && !ctx->prof.on;
-  if (overlapped) {
-    // every layer's context K / V^T depends only on the Fusion-1 output: project them all on a side stream, behind the encoder
-    CU(cudaEventRecord(lane->ev_img, st));
-    CU(cudaStreamWaitEvent(lane->aux[0], lane->ev_img, 0));
-    for (int li = 0; li < L; ++li) {
-      TRY(run_fusion_kv(ctx->layers[li].f2, w.imgfeat, B, T, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, lane->aux[0]));
-      CU(cudaEventRecord(lane->ev_kv[li], lane->aux[0]));
-    }
-  }
+  // every layer's context K / V^T depends only on the Fusion-1 output: one persistent kernel projects them all, reading the context once
+  TRY(run_fusion_kv_all(ctx, w, w.imgfeat, B, T, st));
   // between layers the features travel as the tf32 tile image the next PointCN/QKV kernel consumes (last layer: row-major)
   const bool img = overlapped;
   for (int li = 0; li < L; ++li)
-    TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped ? lane : nullptr, img && li > 0, img && li + 1 < L));
+    TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped ? lane : nullptr, img && li > 0, img && li + 1 < L, true));
   if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
   TRY(run_classify(ctx, w.featA, (long long)B * N, w.normed, conf_out, st));
   TRY(run_pick_seeds(ctx, w, conf_out, B, N, S, testing ? 1 : 0, seeds_out, st));
@@ -770,7 +803,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
   auto vec = [](const float* p, size_t n) { return std::vector<float>(p, p + n); };
 
   Blob blob;
-  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wkv, wo, bo, b1, b2, w1f, w2f; };
+  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wkv, wkv16, wo, bo, b1, b2, w1f, w2f; };
   auto pack_fusion = [&](bool pe) {
     FusionOff o{};
     o.pe = pe;
@@ -784,7 +817,11 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     const float qs = kLog2e / 8.0f;   // dim_head ** -0.5 (fusion_layer.py:76) in log2 units
     for (auto& v : wq) v *= qs;
     o.wq = blob.push(pack_linear(wq, 64, 128, 32, 64));
-    o.wkv = blob.push(pack_linear(vec(next("to_kv.weight"), 128 * 128), 128, 128, 32, 128));
+    {
+      const std::vector<float> Wkv = vec(next("to_kv.weight"), 128 * 128);
+      o.wkv = blob.push(pack_linear(Wkv, 128, 128, 32, 128));
+      o.wkv16 = blob.push(pack_linear_f16(Wkv, 128, 128, 128));
+    }
     o.wo = blob.push(pack_linear(vec(next("to_out.weight"), 128 * 64), 128, 64, 64, 128));
     o.bo = blob.push(next("to_out.bias"), 128);
     o.lfg = blob.push(next("1.norm.weight"), 128); o.lfb = blob.push(next("1.norm.bias"), 128);
@@ -875,7 +912,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     if (o.pe) { f.cpe_q_w = d + o.cqw; f.cpe_q_b = d + o.cqb; f.cpe_c_w = d + o.ccw; f.cpe_c_b = d + o.ccb; }
     f.lnq_g = d + o.lqg; f.lnq_b = d + o.lqb; f.lnc_g = d + o.lcg; f.lnc_b = d + o.lcb; f.lnf_g = d + o.lfg; f.lnf_b = d + o.lfb;
     f.wq = d + o.wq; f.wkv = d + o.wkv; f.wo = d + o.wo; f.bo = d + o.bo; f.b1 = d + o.b1; f.b2 = d + o.b2;
-    f.w1f = d + o.w1f; f.w2f = d + o.w2f;
+    f.w1f = d + o.w1f; f.w2f = d + o.w2f; f.wkv16 = d + o.wkv16;
     return f;
   };
   ctx->sigma = sigma; ctx->sigma_spat = sigma_spat;
