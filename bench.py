@@ -76,7 +76,7 @@ def per_kernel_roofline(prof, a, steps, peak_tf, hbm):
     k = 40
     per_step = {   # (bound, algorithmic FLOPs or bytes per pair per step)
         "attn_sc": ("tensor", L * (4.0 * n * n * C + 2.0 * n * (C * 64 + 64 * 64))),
-        "attn_fusion": ("tensor", (4.0 * t * t * 64 + 2.0 * t * 64 * C) + L * (4.0 * n * t * 64 + 2.0 * n * 64 * C)),
+        "attn_fusion": ("tensor", (4.0 * t * t * 64 + 2 * 2.0 * t * 64 * C) + L * (4.0 * n * t * 64 + 2 * 2.0 * n * 64 * C)),   # scores + P.V, to_q (fused prologue) + to_out
         "ffn_geglu": ("tensor", (2.0 * t * C * 1024 + 2.0 * t * 512 * C) + L * (2.0 * n * C * 1024 + 2.0 * n * 512 * C + 2.0 * n * 64 * C)),
         "pcn_qkv": ("hbm", L * (4.0 * C * n + 4.0 * C * n + 3 * 2.0 * C * n)),                    # feat in; feat1 fp32 + Q,K,V^T bf16 out
         "fusion_q_proj": ("hbm", (4.0 * C * t + 2.0 * 64 * t) + L * (4.0 * C * n + 4.0 * C * n + 2.0 * 64 * n)),   # x in; (x + dwconv) fp32 + Q bf16 out

@@ -17,6 +17,17 @@ struct AttnArgs {
   const float* bo;            // [128]
   const float* resid;         // [B, Lq, 128]
   float* xout;                // [B, Lq, 128]
+  // fused query side (fusion_layer.py:172-183).  xq != NULL switches it on: the kernel itself computes
+  //   x0 = xq + dwconv(xq) (conditional position encoding, k = 3 along the row axis; skipped when cpe_w == NULL),  Q = LN_q(x0) . Wq^T
+  // for its two row tiles (q_t unused).  With the fused output projection it also writes x0 to `x0` (the caller passes resid == x0, or
+  // resid == xq and x0 == NULL when there is no position encoding): the rows come back out of L2 in the epilogue of the same CTA.
+  const float* xq;            // [B, Lq, 128]
+  float* x0;                  // [B, Lq, 128] or NULL
+  const float* cpe_w;         // [128][3] or NULL
+  const float* cpe_b;         // [128]
+  const float* lnq_g;
+  const float* lnq_b;
+  const float* wq16;          // to_q.weight x (log2 e / 8) as one fp16 image: 2 atoms of [64 rows x 64 k] (pack_linear_f16(wq, 64, 128, 64))
 };
 
 }  // namespace gmf

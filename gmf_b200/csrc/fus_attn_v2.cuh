@@ -21,7 +21,8 @@ struct Fa2Cfg {
   static constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;         // [max | sum][row tile][half][row]
   static constexpr int WO_BYTES = 128 * 64 * 4;                 // to_out weight (tf32) for the fused output projection
   static constexpr int STG_BYTES = 16 * 32 * 32 * 4;            // per-warp 32 x 32 transpose tiles for coalesced epilogue I/O
-  static constexpr int SMEM = 1024 + NR * K_BYTES + NR * V_BYTES + WO_BYTES + STG_BYTES + XCH_BYTES + 512;
+  static constexpr int WQ_BYTES = 64 * 128 * 2;                 // to_q weight (fp16) for the fused query projection
+  static constexpr int SMEM = 1024 + NR * K_BYTES + NR * V_BYTES + WO_BYTES + WQ_BYTES + STG_BYTES + XCH_BYTES + 512;
   static constexpr int COL_O = 256, COL_P = 384, COL_Q = 448;
   static constexpr float WINDOW = 80.f;
 };
@@ -88,7 +89,8 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   uint8_t* sK = smem;                                    // [NR] x K (64 keys x 64)
   uint8_t* sV = sK + NR * Cfg::K_BYTES;                  // [NR] x V^T (64 x 64 keys)
   uint8_t* sWo = sV + NR * Cfg::V_BYTES;                 // to_out weight image (fused output projection)
-  float* sStg = (float*)(sWo + Cfg::WO_BYTES);           // [16 warps][32][32]
+  uint8_t* sWq = sWo + Cfg::WO_BYTES;                    // to_q weight image (fused query projection)
+  float* sStg = (float*)(sWq + Cfg::WQ_BYTES);           // [16 warps][32][32]; before the main loop: LN(x0) operand images of the two row tiles
   float* sX = (float*)((uint8_t*)sStg + Cfg::STG_BYTES); // [2][2][2][128]
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::XCH_BYTES);
   const BarArr q_full{smem_u32(bars)};   // [2]  every barrier below is "this address + constant" (no shared-window re-derivation per operation)
@@ -104,11 +106,22 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   const BarArr on_ready = o_full + 2;    // [2] normalised, tf32-rounded O written back to TMEM
   const BarArr x_full = on_ready + 2;    // [2] O . Wo^T complete
   const BarArr wo_full = x_full + 2;     // 1
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 + 4 * NR + 4 + 4 + 2 + 2 + 2 + 2 + 2 + 1);
+  const BarArr wq_full = wo_full + 1;    // 1
+  const BarArr qa_ready = wq_full + 1;   // [2] LN(x0) operand image of a row tile written (256 threads)
+  const BarArr qacc_full = qa_ready + 2; // [2] Q = LN(x0) . Wq^T in the (still idle) first score buffer of the row tile
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 + 4 * NR + 4 + 4 + 2 + 2 + 2 + 2 + 2 + 1 + 1 + 2 + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pair = blockIdx.y;
   const int qt0 = blockIdx.x * 2;
+#ifdef GMF_FFN_TRACE
+  __shared__ long long ftr_[8];
+  const bool ftr_on = blockIdx.x == 5 && blockIdx.y == 33 && a.cpe_w;
+#define FTR(i) do { if (ftr_on && tid == 0) ftr_[i] = clock64(); } while (0)
+#else
+#define FTR(i) do { } while (0)
+#endif
+  FTR(0);
   const int ntile = (qt0 + 1 < a.q_tiles) ? 2 : 1;                  // active row tiles
   const int nt = (a.Lk + BN - 1) / BN;
 
@@ -120,6 +133,7 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   if (tid == 0) {
     mbar_init(&q_full[0], 256); mbar_init(&q_full[1], 256);
     mbar_init(&on_ready[0], 256); mbar_init(&on_ready[1], 256); mbar_init(&x_full[0], 1); mbar_init(&x_full[1], 1); mbar_init(wo_full, 1);
+    mbar_init(wq_full, 1); mbar_init(&qa_ready[0], 256); mbar_init(&qa_ready[1], 256); mbar_init(&qacc_full[0], 1); mbar_init(&qacc_full[1], 1);
     init_bars();
     fence_mbar_init();
   }
@@ -137,7 +151,100 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   float ref = 0.f, l_sum = 0.f, rmax = -INFINITY;
   int pass = 0;
 
-  if (softmax_role) {
+  FTR(1);
+  if (softmax_role && a.xq) {
+    // ---------------- fused query side: x0 = x + dwconv(x), LN_q(x0) -> fp16 operand image, Q = LN(x0) . Wq^T -> fp16 -> tensor memory ----------------
+    // The 8 warps of a row tile own 16 rows each (two batches of 8, lanes across the 128 channels).
+    const int c4 = lane * 4;
+    const int row_lo = (qt0 + t) * 128 + (warp & 7) * 16;        // first row of this warp
+    const float* xp = a.xq + (size_t)pair * a.Lq * 128;
+    for (int i = lane >> 2; i < 18; i += 8) {                    // pull the 18 rows (16 + halo) into L2 ahead of the two batches
+      const int gr = row_lo - 1 + i;
+      if (gr >= 0 && gr < a.Lq) asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + (size_t)gr * 128 + (lane & 3) * 32));
+    }
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.lnq_g + c4)), b4 = __ldg(reinterpret_cast<const float4*>(a.lnq_b + c4));
+    const uint64_t g01 = pack2(g4.x, g4.y), g23 = pack2(g4.z, g4.w), b01 = pack2(b4.x, b4.y), b23 = pack2(b4.z, b4.w);
+    uint64_t w0a = pack2(0.f, 0.f), w0b = w0a, w2a = w0a, w2b = w0a, cba = w0a, cbb = w0a, w1a = pack2(1.f, 1.f), w1b = w1a;
+    if (a.cpe_w) {                                               // taps of channel c at cpe_w[3 c ..]: previous, current, next row
+      const float* cw = a.cpe_w + c4 * 3;
+      const float4 cw0 = __ldg(reinterpret_cast<const float4*>(cw)), cw1 = __ldg(reinterpret_cast<const float4*>(cw + 4)), cw2 = __ldg(reinterpret_cast<const float4*>(cw + 8));
+      const float4 cb = __ldg(reinterpret_cast<const float4*>(a.cpe_b + c4));
+      w0a = pack2(cw0.x, cw0.w); w0b = pack2(cw1.z, cw2.y);
+      w1a = pack2(1.0f + cw0.y, 1.0f + cw1.x); w1b = pack2(1.0f + cw1.w, 1.0f + cw2.z);
+      w2a = pack2(cw0.z, cw1.y); w2b = pack2(cw2.x, cw2.w);
+      cba = pack2(cb.x, cb.y); cbb = pack2(cb.z, cb.w);
+    }
+    uint8_t* img = (uint8_t*)sStg + t * 32768 + (lane >> 4) * 16384 + (lane & 1) * 8;
+    const uint32_t piece = (lane & 15) >> 1;
+#pragma unroll 1
+    for (int bt = 0; bt < 2; ++bt) {
+      const int rb = (warp & 7) * 16 + bt * 8;                   // tile row of rv[1]
+      const int g0 = (qt0 + t) * 128 + rb - 1;                   // global row of rv[0]
+      float4 rv[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g0 + i >= 0 && g0 + i < a.Lq) rv[i] = *reinterpret_cast<const float4*>(xp + (size_t)(g0 + i) * 128 + c4);
+      }
+      uint64_t d01[8], d23[8];
+      float mean[8], rs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        d01[i] = ffma2(w0a, pack2(rv[i].x, rv[i].y), ffma2(w1a, pack2(rv[i + 1].x, rv[i + 1].y), ffma2(w2a, pack2(rv[i + 2].x, rv[i + 2].y), cba)));
+        d23[i] = ffma2(w0b, pack2(rv[i].z, rv[i].w), ffma2(w1b, pack2(rv[i + 1].z, rv[i + 1].w), ffma2(w2b, pack2(rv[i + 2].z, rv[i + 2].w), cbb)));
+        float s0, s1;
+        unpack2(fadd2(d01[i], d23[i]), s0, s1);
+        mean[i] = s0 + s1;
+        if (a.x0 && g0 + 1 + i < a.Lq) {                           // residual stream of the output epilogue: stays in L2 until this CTA reads it back
+          float4 o;
+          unpack2(d01[i], o.x, o.y);
+          unpack2(d23[i], o.z, o.w);
+          *reinterpret_cast<float4*>(a.x0 + ((size_t)pair * a.Lq + g0 + 1 + i) * 128 + c4) = o;
+        }
+      }
+      warp_sum8(mean, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float nm = mean[i] * (-1.0f / 128.0f);
+        const uint64_t nm2 = pack2(nm, nm);
+        d01[i] = fadd2(d01[i], nm2);
+        d23[i] = fadd2(d23[i], nm2);
+        float s0, s1;
+        unpack2(ffma2(d23[i], d23[i], fmul2(d01[i], d01[i])), s0, s1);
+        rs[i] = s0 + s1;
+      }
+      warp_sum8(rs, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float r_ = rsqrtf(rs[i] * (1.0f / 128.0f) + 1e-5f);
+        const uint64_t r2 = pack2(r_, r_);
+        float y0, y1, y2, y3;
+        unpack2(ffma2(fmul2(d01[i], r2), g01, b01), y0, y1);
+        unpack2(ffma2(fmul2(d23[i], r2), g23, b23), y2, y3);
+        uint2 pk;
+        pk.x = pack_f16(y0, y1);
+        pk.y = pack_f16(y2, y3);
+        *reinterpret_cast<uint2*>(img + (rb + i) * 128 + ((piece ^ (uint32_t)i) << 4)) = pk;      // (row & 7) == i
+      }
+    }
+    FTR(2);
+    fence_proxy_async();
+    mbar_arrive(&qa_ready[t]);
+    // this thread's half of Q row r: accumulator (score buffer 0 of the row tile) -> fp16 pairs -> Q columns
+    mbar_wait(&qacc_full[t], 0);
+    tc_fence_after();
+    uint32_t u[32], w[16];
+    tmem_ld32(tlane + (uint32_t)(2 * t) * 64u + h * 32, u);
+    tmem_ld_wait();
+    const bool live = (qt0 + t) * 128 + r < a.Lq;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) w[c] = live ? pack_f16(__uint_as_float(u[2 * c]), __uint_as_float(u[2 * c + 1])) : 0u;
+    tmem_st16(tlane + Cfg::COL_Q + t * 32 + h * 16, w);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&q_full[t]);
+    FTR(3);
+  } else if (softmax_role) {
     // this thread's half of Q row r -> tensor memory (two bf16 per 32-bit column)
     const uint8_t* qsrc = (const uint8_t*)(a.q_t + (size_t)(pair * a.q_tiles + qt0 + t) * (128 * D));
     uint32_t w[16];
@@ -157,6 +264,10 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
     if (warp == WP) {
       // ------------------------------------ producer ------------------------------------
       const uint32_t leader = elect_one() ? 1u : 0u;
+      if (pass == 0 && a.xq) {                                 // needed first: the query projection precedes every score MMA
+        mbar_expect_tx_p(wq_full, Cfg::WQ_BYTES, leader);
+        bulk_g2s_p(sWq, a.wq16, Cfg::WQ_BYTES, wq_full, leader);
+      }
       if (pass == 0 && a.wo_packed) {
         mbar_expect_tx_p(wo_full, Cfg::WO_BYTES, leader);
         bulk_g2s_p(sWo, a.wo_packed, Cfg::WO_BYTES, wo_full, leader);
@@ -196,6 +307,20 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
       m.p_ready = p_ready; m.pv_done = pv_done; m.o_full = o_full; m.nt = nt;
       if (m.t < ntile) {
         if (!is_pv) {
+          if (pass == 0 && a.xq) {
+            // Q_t = LN(x0_t) . Wq^T: A = the row tile's fp16 operand image (staging area), B = Wq, D = score buffer 0 of the row tile
+            mbar_wait2(&qa_ready[m.t], 0, wq_full, 0);
+            tc_fence_after();
+            if (m.leader) {
+              const uint64_t ad = umma_desc_sw128(smem_u32(sStg) + (uint32_t)m.t * 32768u), wd = umma_desc_sw128(smem_u32(sWq));
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                tc_mma_bf16(m.tmem + (uint32_t)(2 * m.t) * 64u, umma_desc_adv(ad, (i >> 2) * 16384 + (i & 3) * 32), umma_desc_adv(wd, (i >> 2) * 8192 + (i & 3) * 32),
+                            m.idesc_s, i ? 1u : 0u);
+              tc_commit(&qacc_full[m.t]);
+            }
+            __syncwarp();
+          }
           if (pass == 0) { mbar_wait(&q_full[m.t], 0); tc_fence_after(); }
           fa2_issue_s<0>(m, 0u);
           if (nt > 1) fa2_issue_s<1>(m, 0u);
@@ -272,6 +397,7 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
     __syncthreads();
   }
 
+  FTR(4);
   const bool fused_out = a.wo_packed != nullptr;
   if (fused_out && (warp == 17 || warp == 18) && (warp - 17) < ntile) {
     // ------------------------------------ P.V issuer of row tile tt: X = (O / l) . Wo^T  (tf32, A operand = O in tensor memory) -----------
@@ -318,29 +444,33 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&on_ready[t]);
-      mbar_wait(&x_full[t], 0);
-      tc_fence_after();
       // coalesced I/O through a per-warp XOR-swizzled 32 x 32 staging tile (global accesses touch 4 rows x 128 B per instruction)
       float* stg = sStg + warp * 1024;
       const int srow = lane >> 3, sj = lane & 7;
       const int grow0 = (qt0 + t) * 128 + (warp & 3) * 32;             // first row of this warp's lane quadrant
-#pragma unroll 1
+      // the residual rows of both 32-column chunks are fetched while the output projection runs (u[] is dead until X is read back)
+      float4 rr[2][8];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rw = i * 4 + srow;
+          rr[c][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow0 + rw < a.Lq)
+            rr[c][i] = *reinterpret_cast<const float4*>(a.resid + ((size_t)pair * a.Lq + grow0 + rw) * 128 + h * 64 + c * 32 + sj * 4);
+        }
+      mbar_wait(&x_full[t], 0);
+      tc_fence_after();
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
         tmem_ld32(tlane + (uint32_t)t * 128u + h * 64 + c * 32, u);      // X lives in the (now idle) score buffers of row tile t
         tmem_ld_wait();
         const int col0 = h * 64 + c * 32;
         const size_t gbase = ((size_t)pair * a.Lq + grow0) * 128 + col0;
-        float4 rr[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rw = i * 4 + srow;
-          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (grow0 + rw < a.Lq) rr[i] = *reinterpret_cast<const float4*>(a.resid + gbase + (size_t)rw * 128 + sj * 4);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rw = i * 4 + srow;
-          *reinterpret_cast<float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2)) = rr[i];
+          *reinterpret_cast<float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2)) = rr[c][i];
         }
         __syncwarp();
 #pragma unroll
@@ -362,8 +492,14 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
       }
     }
   }
+  FTR(5);
   tc_fence_before();
   __syncthreads();
+#ifdef GMF_FFN_TRACE
+  if (ftr_on && tid == 0)
+    printf("fus_attn trace: setup %lld | LN done %lld | Q in TMEM %lld | main loop done %lld | epilogue done %lld\n", ftr_[1] - ftr_[0], ftr_[2] - ftr_[0], ftr_[3] - ftr_[0],
+           ftr_[4] - ftr_[0], ftr_[5] - ftr_[0]);
+#endif
   if (warp == WP) tmem_dealloc(tmem, 512);
 }
 

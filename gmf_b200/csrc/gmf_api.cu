@@ -225,6 +225,7 @@ struct FusionW {
   const float *wq, *wkv, *wo, *bo, *b1, *b2;
   const float *w1f, *w2f;   // fused-FFN packing (8 passes of 64 hidden columns)
   const float* wkv16 = nullptr;   // to_kv.weight as one fp16 image (kv_proj_all.cuh)
+  const float* wq16 = nullptr;    // scaled to_q.weight as one fp16 image (query projection fused into fus_attn_v2.cuh)
 };
 struct LayerW {
   const float *pcn_b, *qkv_w, *qkv_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
@@ -251,12 +252,6 @@ struct gmf_ctx {
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
-  // side streams: the context K/V projections of all layers and each layer's Fusion-2 query projection run next to the SC attention
-  struct Lane {
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_img = nullptr, ev_f1 = nullptr, ev_q = nullptr;
-    std::vector<cudaEvent_t> ev_kv;
-  } lane;
   cudaStream_t copy_stream = nullptr;   // uploads of the next chunk overlap the current chunk's kernels
   cudaEvent_t copy_ev[64] = {};
   cudaEvent_t start_ev = nullptr;
@@ -355,19 +350,6 @@ LinArgs lin(const float* x, int L, const float* w, const float* bias) {
   return a;
 }
 
-// queries: (CPE) -> LN -> to_q => bf16 Q tiles (scale folded); returns the residual stream (x, or x + dwconv(x) when pe)
-int run_fusion_q(const FusionW& f, Work& w, const float* xq, int B, int Lq, const float** resid0, cudaStream_t st) {
-  *resid0 = xq;
-  LinArgs a = lin(xq, Lq, f.wq, nullptr);
-  a.ln_g = f.lnq_g; a.ln_b = f.lnq_b; a.t0 = w.qf;
-  if (f.pe) {
-    a.cpe_w = f.cpe_q_w; a.cpe_b = f.cpe_q_b; a.x0_out = w.x0; *resid0 = w.x0;
-    TRY((run_linear<128, 64, PRO_CPE_LN, EPI_Q_FUS>(a, B, st, CAT_QFUS)));
-  } else {
-    TRY((run_linear<128, 64, PRO_LN, EPI_Q_FUS>(a, B, st, CAT_QFUS)));
-  }
-  return 0;
-}
 // context: (CPE) -> LN_ctx -> to_kv => bf16 K tiles, V^T tiles
 int run_fusion_kv(const FusionW& f, const float* ctxk, int B, int Lk, __nv_bfloat16* kf, __nv_bfloat16* vtf, cudaStream_t st) {
   LinArgs a = lin(ctxk, Lk, f.wkv, nullptr);
@@ -380,7 +362,7 @@ int run_fusion_kv(const FusionW& f, const float* ctxk, int B, int Lk, __nv_bfloa
   }
   return 0;
 }
-int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* resid0, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
+int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
                     float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3, float* out_img = nullptr);
 
 // context K / V^T of every encoder layer from the Fusion-1 output, one persistent kernel (kv_proj_all.cuh)
@@ -389,20 +371,20 @@ int run_fusion_kv_all(const gmf_ctx* ctx, Work& w, const float* ctxk, int B, int
 // FusionLayer.forward (fusion_layer.py:172-201), everything on one stream
 int run_fusion(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const float* ctxk, int B, int Lq, int Lk, float* out, cudaStream_t st,
                const float* tail_m2 = nullptr, const float* tail_w3 = nullptr, const float* tail_b3 = nullptr) {
-  const float* resid0 = nullptr;
-  TRY(run_fusion_q(f, w, xq, B, Lq, &resid0, st));
   TRY(run_fusion_kv(f, ctxk, B, Lk, w.kf, w.vtf, st));
-  return run_fusion_core(ctx, f, w, resid0, w.kf, w.vtf, B, Lq, Lk, out, st, tail_m2, tail_w3, tail_b3);
+  return run_fusion_core(ctx, f, w, xq, w.kf, w.vtf, B, Lq, Lk, out, st, tail_m2, tail_w3, tail_b3);
 }
 
-// attention (+ to_out + residual) and the GEGLU feed-forward block
-int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* resid0, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
+// query side (position encoding, LayerNorm, to_q) + attention (+ to_out + residual) in one kernel, then the GEGLU feed-forward block
+int run_fusion_core(const gmf_ctx* ctx, const FusionW& f, Work& w, const float* xq, const __nv_bfloat16* kf, const __nv_bfloat16* vtf, int B, int Lq, int Lk,
                     float* out, cudaStream_t st, const float* tail_m2, const float* tail_w3, const float* tail_b3, float* out_img) {
   {
     AttnArgs a{};
-    a.q_t = w.qf; a.k_t = kf; a.vt_t = vtf; a.out = nullptr;
+    a.k_t = kf; a.vt_t = vtf; a.out = nullptr;
     a.Lq = Lq; a.Lk = Lk; a.q_tiles = cdiv(Lq, 128); a.k_tiles = cdiv(Lk, 128);
-    a.wo_packed = f.wo; a.bo = f.bo; a.resid = resid0; a.xout = w.x1;                                // to_out + bias + residual fused
+    a.wo_packed = f.wo; a.bo = f.bo; a.xout = w.x1;                                                   // to_out + bias + residual fused
+    a.xq = xq; a.cpe_w = f.pe ? f.cpe_q_w : nullptr; a.cpe_b = f.pe ? f.cpe_q_b : nullptr; a.lnq_g = f.lnq_g; a.lnq_b = f.lnq_b; a.wq16 = f.wq16;
+    a.x0 = f.pe ? w.x0 : nullptr; a.resid = f.pe ? w.x0 : xq;                                         // residual stream: x + dwconv(x) when there is a position encoding
     ProfScope ps(CAT_ATTN_FUS, st);
     cudaError_t e = launch_fus_attn_v2(a, B, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -513,9 +495,7 @@ int run_fusion_kv_all(const gmf_ctx* ctx, Work& w, const float* ctxk, int B, int
 
 // kv_ready: this layer's context K / V^T already sit in w.kf_all / w.vtf_all (run_fusion_kv_all)
 int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in, const float* image_feat, int B, int N, int T,
-                      float* feat_out, cudaStream_t st, const gmf_ctx::Lane* lane = nullptr, bool in_img = false, bool out_img = false,
-                      bool kv_ready = false) {
-  const bool overlapped = lane != nullptr;
+                      float* feat_out, cudaStream_t st, bool in_img = false, bool out_img = false, bool kv_ready = false) {
   const LayerW& lw = ctx->layers[li];
   {   // PointCN (conv + folded BN + ReLU) chained with the Q/K/V projections
     PcnQkvArgs a{};
@@ -526,28 +506,13 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "pcn_qkv launch");
   }
-  const float* resid0 = nullptr;
-  if (overlapped) {
-    // the Fusion-2 query projection only needs feat1: it runs on a side stream next to the SC attention (whose last, partial wave
-    // of CTAs leaves most SMs idle); the context K / V^T of this layer were projected up front (forward_chunk)
-    CU(cudaEventRecord(lane->ev_f1, st));
-    CU(cudaStreamWaitEvent(lane->aux[1], lane->ev_f1, 0));
-    TRY(run_fusion_q(lw.f2, w, w.feat1, B, N, &resid0, lane->aux[1]));
-    CU(cudaEventRecord(lane->ev_q, lane->aux[1]));
-  }
   // SC attention with fc_message.0/.3 as the kernel's tail: writes m2
   TRY(run_sc_attention(ctx, lw, w, w.feat1, B, N, nullptr, st, w.m2, true));
-  // fc_message.6(m2) + fusion_layer_2 output (PointDSC.py:73) are folded into the fused FFN kernel's tail
-  if (overlapped) {
-    CU(cudaStreamWaitEvent(st, lane->ev_q, 0));
-    return run_fusion_core(ctx, lw.f2, w, resid0, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
+  // fc_message.6(m2) + fusion_layer_2 output (PointDSC.py:73) are folded into the fused FFN kernel's tail; the query side of fusion_layer_2
+  // (position encoding, LayerNorm, to_q) is the prologue of the attention kernel
+  if (kv_ready)
+    return run_fusion_core(ctx, lw.f2, w, w.feat1, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
                            lw.fc3_w, lw.fc3_b, out_img ? w.feat_img : nullptr);
-  }
-  if (kv_ready) {
-    TRY(run_fusion_q(lw.f2, w, w.feat1, B, N, &resid0, st));
-    return run_fusion_core(ctx, lw.f2, w, resid0, w.kf_all + (size_t)li * w.kv_stride, w.vtf_all + (size_t)li * w.kv_stride, B, N, T, feat_out, st, w.m2,
-                           lw.fc3_w, lw.fc3_b, nullptr);
-  }
   return run_fusion(ctx, lw.f2, w, w.feat1, image_feat, B, N, T, feat_out, st, w.m2, lw.fc3_w, lw.fc3_b);
 }
 
@@ -630,7 +595,7 @@ int run_score(const gmf_ctx* ctx, Work& w, const float* seed_trans, int B, int N
   return 0;
 }
 
-int forward_chunk(gmf_ctx* ctx, gmf_ctx::Lane* lane, Work& w, const float* corr, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
+int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, const float* tgt, const float* p_tok, const float* q_tok,
                   int B, int N, int T, int testing, float* final_trans, float* labels, float* conf_out, int* seeds_out, float* feat_out,
                   cudaStream_t st) {
   const int S = num_seeds(ctx, N), k = eff_k(ctx, N);
@@ -644,14 +609,11 @@ int forward_chunk(gmf_ctx* ctx, gmf_ctx::Lane* lane, Work& w, const float* corr,
   // Fusion-1: queries = q-image tokens, context = p-image tokens (PointDSC.py:137)
   TRY(run_fusion(ctx, ctx->f1, w, q_tok, p_tok, B, T, T, w.imgfeat, st));
   const int L = ctx->cfg.num_layers;
-  // per-launch profiling (gmf_profile_enable) times every kernel alone: it uses the single-stream schedule
-  const bool overlapped = lane && !ctx->prof.on;
   // every layer's context K / V^T depends only on the Fusion-1 output: one persistent kernel projects them all, reading the context once
   TRY(run_fusion_kv_all(ctx, w, w.imgfeat, B, T, st));
-  // between layers the features travel as the tf32 tile image the next PointCN/QKV kernel consumes (last layer: row-major)
-  const bool img = overlapped;
+  // between layers the features travel as the split fp16 tile image the next PointCN/QKV kernel consumes (last layer: row-major)
   for (int li = 0; li < L; ++li)
-    TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, overlapped ? lane : nullptr, img && li > 0, img && li + 1 < L, true));
+    TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, li > 0, li + 1 < L, true));
   if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
   TRY(run_classify(ctx, w.featA, (long long)B * N, w.normed, conf_out, st));
   TRY(run_pick_seeds(ctx, w, conf_out, B, N, S, testing ? 1 : 0, seeds_out, st));
@@ -766,12 +728,6 @@ void gmf_destroy(gmf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->blob) cudaFree(ctx->blob);
   if (ctx->stage) cudaFree(ctx->stage);
-  if (ctx->lane.aux[0]) {
-    gmf_ctx::Lane& ln = ctx->lane;
-    cudaStreamDestroy(ln.aux[0]); cudaStreamDestroy(ln.aux[1]);
-    cudaEventDestroy(ln.ev_img); cudaEventDestroy(ln.ev_f1); cudaEventDestroy(ln.ev_q);
-    for (auto e : ln.ev_kv) cudaEventDestroy(e);
-  }
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);
     for (auto e : ctx->copy_ev) if (e) cudaEventDestroy(e);
@@ -803,7 +759,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
   auto vec = [](const float* p, size_t n) { return std::vector<float>(p, p + n); };
 
   Blob blob;
-  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wkv, wkv16, wo, bo, b1, b2, w1f, w2f; };
+  struct FusionOff { bool pe; size_t cqw, cqb, ccw, ccb, lqg, lqb, lcg, lcb, lfg, lfb, wq, wq16, wkv, wkv16, wo, bo, b1, b2, w1f, w2f; };
   auto pack_fusion = [&](bool pe) {
     FusionOff o{};
     o.pe = pe;
@@ -817,6 +773,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     const float qs = kLog2e / 8.0f;   // dim_head ** -0.5 (fusion_layer.py:76) in log2 units
     for (auto& v : wq) v *= qs;
     o.wq = blob.push(pack_linear(wq, 64, 128, 32, 64));
+    o.wq16 = blob.push(pack_linear_f16(wq, 64, 128, 64));
     {
       const std::vector<float> Wkv = vec(next("to_kv.weight"), 128 * 128);
       o.wkv = blob.push(pack_linear(Wkv, 128, 128, 32, 128));
@@ -912,7 +869,7 @@ int gmf_load_weights(gmf_ctx* ctx, const float* host, int64_t numel) {
     if (o.pe) { f.cpe_q_w = d + o.cqw; f.cpe_q_b = d + o.cqb; f.cpe_c_w = d + o.ccw; f.cpe_c_b = d + o.ccb; }
     f.lnq_g = d + o.lqg; f.lnq_b = d + o.lqb; f.lnc_g = d + o.lcg; f.lnc_b = d + o.lcb; f.lnf_g = d + o.lfg; f.lnf_b = d + o.lfb;
     f.wq = d + o.wq; f.wkv = d + o.wkv; f.wo = d + o.wo; f.bo = d + o.bo; f.b1 = d + o.b1; f.b2 = d + o.b2;
-    f.w1f = d + o.w1f; f.w2f = d + o.w2f; f.wkv16 = d + o.wkv16;
+    f.w1f = d + o.w1f; f.w2f = d + o.w2f; f.wkv16 = d + o.wkv16; f.wq16 = d + o.wq16;
     return f;
   };
   ctx->sigma = sigma; ctx->sigma_spat = sigma_spat;
@@ -952,14 +909,6 @@ int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, 
   const int S = num_seeds(ctx, N);
   const int Bc = std::min(B, ctx->chunk_pairs);
   const int L = ctx->cfg.num_layers;
-  {
-    gmf_ctx::Lane& ln = ctx->lane;
-    if (!ln.aux[0]) {
-      for (auto& a : ln.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-      for (cudaEvent_t* e : {&ln.ev_img, &ln.ev_f1, &ln.ev_q}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    }
-    while ((int)ln.ev_kv.size() < L) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.ev_kv.push_back(e); }
-  }
   Work w;
   {
     if (!workspace) return fail(GMF_ERR_INVALID, "workspace is NULL");
@@ -970,7 +919,7 @@ int gmf_pointdsc_forward(gmf_ctx* ctx, const float* corr_pos, const float* src, 
   }
   for (int b0 = 0; b0 < B; b0 += Bc) {
     const int nb = std::min(Bc, B - b0);
-    TRY(forward_chunk(ctx, &ctx->lane, w, corr_pos + (size_t)b0 * N * 6, src + (size_t)b0 * N * 3, tgt + (size_t)b0 * N * 3,
+    TRY(forward_chunk(ctx, w, corr_pos + (size_t)b0 * N * 6, src + (size_t)b0 * N * 3, tgt + (size_t)b0 * N * 3,
                       p_tok + (size_t)b0 * T * 128, q_tok + (size_t)b0 * T * 128, nb, N, T, testing, final_trans + (size_t)b0 * 16,
                       final_labels + (size_t)b0 * N, confidence + (size_t)b0 * N, seeds + (size_t)b0 * S,
                       feat ? feat + (size_t)b0 * N * 128 : nullptr, st));

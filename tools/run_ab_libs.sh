@@ -13,7 +13,7 @@ v = sys.argv[1]
 try:
     d = json.loads(open(f'gpurun_out/bench_{v}.json').read().strip().splitlines()[-1])
     pk = d['roofline']['per_kernel']
-    print(v, 'ms/step', round(d['ms_per_step'], 2), ' '.join(f"{k}={pk[k]['ms_per_step']:.2f}" for k in ('attn_sc', 'attn_fusion', 'ffn_geglu', 'pcn_qkv', 'fusion_q_proj', 'fusion_kv_proj')))
+    print(v, 'ms/step', round(d['ms_per_step'], 2), ' '.join(f"{k}={pk[k]['ms_per_step']:.2f}" for k in ('attn_sc', 'attn_fusion', 'ffn_geglu', 'pcn_qkv', 'fusion_q_proj', 'fusion_kv_proj') if k in pk))
 except Exception as e:
     print(v, 'parse failed', e)
 PY
