@@ -23,6 +23,9 @@ struct AttnArgs {
   // resid == xq and x0 == NULL when there is no position encoding): the rows come back out of L2 in the epilogue of the same CTA.
   const float* xq;            // [B, Lq, 128]
   float* x0;                  // [B, Lq, 128] or NULL
+#ifdef GMF_FFN_TRACE
+  long long* trace;           // development build: clock64 stamps of one CTA (tools/fa_trace.py)
+#endif
   const float* cpe_w;         // [128][3] or NULL
   const float* cpe_b;         // [128]
   const float* lnq_g;

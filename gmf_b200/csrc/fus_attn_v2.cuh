@@ -115,9 +115,7 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   const int pair = blockIdx.y;
   const int qt0 = blockIdx.x * 2;
 #ifdef GMF_FFN_TRACE
-  __shared__ long long ftr_[8];
-  const bool ftr_on = blockIdx.x == 5 && blockIdx.y == 33 && a.cpe_w;
-#define FTR(i) do { if (ftr_on && tid == 0) ftr_[i] = clock64(); } while (0)
+#define FTR(i) do { if (a.trace && blockIdx.x == 5 && blockIdx.y == 33 && tid == 0) a.trace[i] = clock64(); } while (0)
 #else
 #define FTR(i) do { } while (0)
 #endif
@@ -495,11 +493,6 @@ __global__ void __launch_bounds__(672, 1) fus_attn_v2_kernel(const AttnArgs a) {
   FTR(5);
   tc_fence_before();
   __syncthreads();
-#ifdef GMF_FFN_TRACE
-  if (ftr_on && tid == 0)
-    printf("fus_attn trace: setup %lld | LN done %lld | Q in TMEM %lld | main loop done %lld | epilogue done %lld\n", ftr_[1] - ftr_[0], ftr_[2] - ftr_[0], ftr_[3] - ftr_[0],
-           ftr_[4] - ftr_[0], ftr_[5] - ftr_[0]);
-#endif
   if (warp == WP) tmem_dealloc(tmem, 512);
 }
 

@@ -148,3 +148,28 @@ def test_host_chunk_plan_properties(lib):
             assert all(sizes[i + 1] <= 2.6 * sizes[i] + 1 for i in range(n - 2)), sizes   # uploads stay ahead of the kernels
     assert lib.gmf_debug_plan_host_chunks(64, 5000, 48, 148, buf, 256) == 3 and [buf[i] for i in range(3)] == [7, 14, 43]
     assert lib.gmf_debug_plan_host_chunks(0, 5000, 48, 148, buf, 256) < 0
+
+
+def test_gelu_polynomial_constants_match_erf_gelu():
+    """gelu_erf / geglu2 (gmf_b200/csrc/linear_tc.cuh) evaluate F.gelu (erf form, fusion_layer.py:57) as max(x, 0) - |x| 2^(q(|x|) - 1) with a
+    degree-5 polynomial q ~ log2 erfc(|x| / sqrt2) (tools/fit_gelu.py).  The compiled-in coefficients are checked here in fp32 arithmetic against
+    the exact function over the whole range the kernels can see: |error| <= 2e-6 (the TF32 / fp16 rounding of the product is ~5e-4 relative)."""
+    import math
+    import os
+    import re
+
+    import numpy as np
+
+    src = open(os.path.join(os.path.dirname(__file__), "..", "gmf_b200", "csrc", "linear_tc.cuh")).read()
+    c = [np.float32(re.search(r"#define GMF_GELU_C%d \(([-+0-9.e]+)f\)" % i, src).group(1)) for i in range(1, 6)]
+    x = np.concatenate([np.linspace(-60, 60, 600001), [1e4, -1e4, 0.0]]).astype(np.float32)
+    n = -np.abs(x)
+    q = (-c[4]) * n + c[3]
+    q = q * n - c[2]
+    q = q * n + c[1]
+    q = q * n - c[0]
+    with np.errstate(over="ignore", under="ignore"):
+        g = n * np.exp2(q * n - np.float32(1.0)) + np.maximum(x, np.float32(0.0))
+    ref = np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in x.astype(np.float64)])
+    assert not np.isnan(g).any()
+    assert np.abs(g - ref).max() <= 2e-6
