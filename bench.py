@@ -456,14 +456,14 @@ def main():
         sc_flops = 4.0 * a.corr * a.corr * 128 * a.pairs * a.layers * a.steps           # 4 N^2 C per pair-layer
         ach = sc_flops / (sc_ms / 1000.0) / 1e12
         # DRAM bytes of one launch from the committed `ncu --set full` capture of this configuration
-        # (profiles/r02_top4_cfg2_ncu_raw.csv: dram__bytes_read.sum 333.03 MB + dram__bytes_write.sum 70.21 MB at 64 pairs, N=5000;
+        # (profiles/r02_top5_cfg2_ncu_raw.csv: dram__bytes_read.sum 333.15 MB + dram__bytes_write.sum 71.51 MB at 64 pairs, N=5000;
         #  algorithmic: Q/K fp16 + V^T bf16 + distance features 5.8 MB in, m2 fp32 1.3 MB out per pair = 454 MB)
-        traffic = 403.24e6 if (a.pairs == 64 and a.corr == 5000) else None
+        traffic = 404.66e6 if (a.pairs == 64 and a.corr == 5000) else None
         # co-limit: every score element costs one MUFU.SQRT and one MUFU.EX2 at the measured 16 MUFU/clk/SM (tools/ubench/sm_rates.cu)
         mufu_floor_ms = 2.0 * a.corr * a.corr * a.pairs / (16.0 * 148 * 1.965e9) * 1e3
         roof = {"kernel": "sc_attn_v9_kernel<0,2> (SC-guided non-local flash attention, compat on the fly, gen 9)", "bound": "tensor",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_top4_cfg2_ncu_raw.csv)",
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_top5_cfg2_ncu_raw.csv)",
                 "peak_source": how, "avg_launch_ms": sc_ms / max(sc_n, 1), "launches": sc_n,
                 "algorithmic_flops_per_launch": sc_flops / max(sc_n, 1),
                 "mufu_colimit": {"floor_ms_per_launch": mufu_floor_ms, "frac": mufu_floor_ms / (sc_ms / max(sc_n, 1))},
