@@ -55,13 +55,13 @@ struct FfnArgs {
 };
 
 // residual rows [32 x 32 floats] of one worker warp -> its swizzled staging tile, 8 x 16-byte asynchronous copies per lane
-__device__ __noinline__ void ffn_stage_residual(float* stg, const float* src, int rows_left, int lane) {
+__device__ __noinline__ void ffn_stage_residual(float* stg, const float* src, const float* valid_ptr, int rows_left, int lane) {
   const int srow = lane >> 3, sj = lane & 7;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rw = i * 4 + srow;
-    const bool ok = rw < rows_left;
-    cp_async16(stg + rw * 32 + ((sj ^ (rw & 7)) << 2), ok ? src + (size_t)rw * 128 + sj * 4 : src, ok);
+    const bool ok = rw < rows_left;                              // rows past L: zero fill, the (unread) source address stays inside the tensor
+    cp_async16(stg + rw * 32 + ((sj ^ (rw & 7)) << 2), ok ? src + (size_t)rw * 128 + sj * 4 : valid_ptr, ok);
   }
   cp_async_commit();
 }
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(FfnCfg::THREADS, 1) ffn_fused_kernel(const Ffn
               if (lane == 0) bulk_wait_read();
               __syncwarp();
             }
-            ffn_stage_residual(stg, a.x + ((size_t)pair * a.L + row0 + q * 32) * 128 + cq * 32, a.L - (row0 + q * 32), lane);
+            ffn_stage_residual(stg, a.x + ((size_t)pair * a.L + row0 + q * 32) * 128 + cq * 32, a.x, a.L - (row0 + q * 32), lane);
           }
           if (warp == 0) TR(3, 4 * p);
           mbar_wait(&acc1_full[b], (p >> 1) & 1);

@@ -4,9 +4,10 @@
 // memory as fp32 (with its two halo rows) and pushed through the 12 layers' position encoding / LayerNorm / GEMM / tile-image epilogue,
 // instead of 12 launches that each re-read the 157 MB context and expose their LayerNorm prologue (round 1-2: 12 x 0.115 ms at 0.31 of the
 // HBM roofline; an in-CTA layer loop without role overlap did not help).  Roles, one CTA per SM, 640 threads:
-//   warps 0-15  workers: position encoding + LayerNorm of step n + 1 -> A[(n+1)&1] (fp16, swizzled; 8 rows per warp), then the epilogue of
-//               step n: ACC[n&1] -> K tile image (fp16, K-major) | V^T tile image (bf16) in a staging buffer -> two 16 KB bulk stores
-//               (four dedicated LayerNorm warps needed 6.4 k cycles per layer with everything else waiting for them)
+//   warps 0-7   position encoding + LayerNorm of layer l -> A[n&1] (fp16, swizzled; 16 rows per warp), one step ahead of the MMA
+//   warps 8-15  epilogue of step n: ACC[n&1] -> K tile image (fp16, K-major) | V^T tile image (bf16) in a staging buffer -> two 16 KB bulk stores
+//               (history: four LayerNorm warps + 16 epilogue warps: 6.4 k cycles per layer, everything waiting for the LayerNorm; 16 warps
+//               alternating both jobs: 5.2 k, the two phases serialised in every warp)
 //   warp  16    MMA issuer: ACC[n&1] = A[n&1] . W_l^T   (8 fp16 MMAs, N = 128, K = 128; fp16 operands = the 11-bit significand of TF32)
 //   warp  17    weight producer (32 KB per layer through a 2-deep ring)
 //   warp  18    context loader (one bulk copy per tile: 130 rows x 512 B, rows outside the sequence zero-filled)
@@ -57,14 +58,14 @@ __global__ void __launch_bounds__(KvAllCfg::THREADS, 1) kv_proj_all_kernel(const
   float* sX = (float*)(sOut + Cfg::OUT_BYTES);            // [130][128] fp32, row s = token row0 - 1 + s
   uint64_t* bars = (uint64_t*)((uint8_t*)sX + Cfg::X_BYTES);
   const uint32_t bar0 = smem_u32(bars);
-  const BarArr a_ready{bar0};                      // [2] 512  workers (LayerNorm) -> MMA
+  const BarArr a_ready{bar0};                      // [2] 256  LayerNorm warps -> MMA
   const BarArr a_free = BarArr{bar0} + 2;          // [2]      MMA retired -> LayerNorm warps (step + 2)
   const BarArr w_full = BarArr{bar0} + 4;          // [2]
   const BarArr w_empty = BarArr{bar0} + 6;         // [2]
   const BarArr acc_full = BarArr{bar0} + 8;        // [2]
-  const BarArr acc_free = BarArr{bar0} + 10;       // [2] 512
+  const BarArr acc_free = BarArr{bar0} + 10;       // [2] 256  epilogue warps
   const BarArr x_full = BarArr{bar0} + 12;         //          context tile landed
-  const BarArr x_free = BarArr{bar0} + 13;         // 512      workers have read the tile for the last layer
+  const BarArr x_free = BarArr{bar0} + 13;         // 256      LayerNorm warps have read the tile for the last layer
   uint32_t* tmem_slot = (uint32_t*)(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(KvAllCfg::THREADS, 1) kv_proj_all_kernel(const
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_ready[i], 512); mbar_init(&a_free[i], 1); mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 512);
+      mbar_init(&a_ready[i], 256); mbar_init(&a_free[i], 1); mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 256);
     }
-    mbar_init(x_full, 1); mbar_init(x_free, 512);
+    mbar_init(x_full, 1); mbar_init(x_free, 256);
     fence_mbar_init();
   }
   if (warp == 16) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -156,24 +157,15 @@ __global__ void __launch_bounds__(KvAllCfg::THREADS, 1) kv_proj_all_kernel(const
         }
         __syncwarp();
       }
-  } else if (warp < 16) {
-    // ------------------------------- workers: position encoding + LayerNorm of step n + 1, then the epilogue of step n -------------------------------
-    // LayerNorm: warp w owns tile rows 8 w .. 8 w + 7 (one batch, lanes across the 128 channels).  Epilogue: 4 lane quadrants x 4 column
-    // quarters (0, 1 -> K; 2, 3 -> V).  While the workers normalise step n + 1 the tensor pipe multiplies step n.
-    const int q = warp & 3, cq = warp >> 2;
-    const int r = q * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+  } else if (warp < 8) {
+    // ------------------------------- LayerNorm warps: position encoding + LayerNorm of layer l -> A[n & 1] (fp16, swizzled) -------------------------------
+    // Warp w owns tile rows 16 w .. 16 w + 15: two batches of 8 rows, lanes across the 128 channels.  They run one step ahead of the MMA.
     const int c4 = lane * 4;
     constexpr int RPW = 8;
-    const int rbase = warp * RPW;                                // tile row of rv[1]; shared row = tile row + 1
     const uint32_t lane_off = (lane >> 4) * 16384 + (lane & 1) * 8;
     const uint32_t piece = (lane & 15) >> 1;
-    const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int steps = my_tiles * NL;
-    int it = 0, l = -1;                                          // (it, l): tile iteration and layer of step n
-    int itn = 0, ln = 0;                                         // ... of step n + 1
-    // per-layer parameters of this lane's 4 channels: 3 KB per layer and 12 layers do not stay in the 28 KB L1, so the next LayerNorm's set is
-    // fetched while the epilogue in between runs (fetched at the point of use it cost 1.5 k cycles per step)
+    // per-layer parameters of this lane's 4 channels: 3 KB per layer and 12 layers do not stay in the 28 KB L1, so the next layer's set is
+    // fetched while this one is normalised (fetched at the point of use it cost 1.5 k cycles per step)
     float4 pg4, pb4, pcw0, pcw1, pcw2, pcb;
     auto fetch_params = [&](int layer) {
       const KvLayer& ly = a.layer[layer];
@@ -184,117 +176,129 @@ __global__ void __launch_bounds__(KvAllCfg::THREADS, 1) kv_proj_all_kernel(const
       pcb = __ldg(reinterpret_cast<const float4*>(ly.cpe_b + c4));
     };
     fetch_params(0);
+    int n = 0, it = 0;
 #pragma unroll 1
-    for (int n = -1; n < steps; ++n) {
-      if (n + 1 < steps) {
-        // ---------------- LayerNorm_l(x + dwconv_l(x)) -> A[(n + 1) & 1] ----------------
-        const int m = n + 1, ab = m & 1;
-        const float4 g4 = pg4, b4 = pb4, cw0 = pcw0, cw1 = pcw1, cw2 = pcw2, cb = pcb;   // this layer's parameters, fetched one step ago
+    for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
+#pragma unroll 1
+      for (int l = 0; l < NL; ++l, ++n) {
+        const int ab = n & 1;
+        const float4 g4 = pg4, b4 = pb4, cw0 = pcw0, cw1 = pcw1, cw2 = pcw2, cb = pcb;
+        fetch_params(l + 1 == NL ? 0 : l + 1);
         // x + dwconv(x) = w0 x[r-1] + (1 + w1) x[r] + w2 x[r+1] + b, two channels per packed operand; taps of channel c at cw[3 c ..]
         const uint64_t w0a = pack2(cw0.x, cw0.w), w0b = pack2(cw1.z, cw2.y);
         const uint64_t w1a = pack2(1.0f + cw0.y, 1.0f + cw1.x), w1b = pack2(1.0f + cw1.w, 1.0f + cw2.z);
         const uint64_t w2a = pack2(cw0.z, cw1.y), w2b = pack2(cw2.x, cw2.w);
         const uint64_t cba = pack2(cb.x, cb.y), cbb = pack2(cb.z, cb.w);
-        if (warp == 0) KTR(0, 3 * ln);
-        if (ln == 0) mbar_wait(x_full, itn & 1);
-        if (m >= 2) mbar_wait(&a_free[ab], ((m >> 1) - 1) & 1);
-        if (warp == 0) KTR(0, 3 * ln + 1);
-        uint8_t* img = sA + ab * Cfg::A_BYTES + lane_off;
-        float4 rv[RPW + 2];
-#pragma unroll
-        for (int i = 0; i < RPW + 2; ++i) rv[i] = *reinterpret_cast<const float4*>(sX + (rbase + i) * 128 + c4);
-        uint64_t d01[RPW], d23[RPW];
-        float mean[RPW], rs[RPW];
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-          d01[i] = ffma2(w0a, pack2(rv[i].x, rv[i].y), ffma2(w1a, pack2(rv[i + 1].x, rv[i + 1].y), ffma2(w2a, pack2(rv[i + 2].x, rv[i + 2].y), cba)));
-          d23[i] = ffma2(w0b, pack2(rv[i].z, rv[i].w), ffma2(w1b, pack2(rv[i + 1].z, rv[i + 1].w), ffma2(w2b, pack2(rv[i + 2].z, rv[i + 2].w), cbb)));
-          float s0, s1;
-          unpack2(fadd2(d01[i], d23[i]), s0, s1);
-          mean[i] = s0 + s1;
-        }
-        warp_sum8(mean, lane);
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-          const float nm = mean[i] * (-1.0f / 128.0f);
-          const uint64_t nm2 = pack2(nm, nm);
-          d01[i] = fadd2(d01[i], nm2);
-          d23[i] = fadd2(d23[i], nm2);
-          float s0, s1;
-          unpack2(ffma2(d23[i], d23[i], fmul2(d01[i], d01[i])), s0, s1);
-          rs[i] = s0 + s1;
-        }
-        warp_sum8(rs, lane);
         const uint64_t g01 = pack2(g4.x, g4.y), g23 = pack2(g4.z, g4.w), b01 = pack2(b4.x, b4.y), b23 = pack2(b4.z, b4.w);
+        if (warp == 0) KTR(0, 3 * l);
+        if (l == 0) mbar_wait(x_full, it & 1);
+        if (n >= 2) mbar_wait(&a_free[ab], ((n >> 1) - 1) & 1);
+        if (warp == 0) KTR(0, 3 * l + 1);
+        uint8_t* img = sA + ab * Cfg::A_BYTES + lane_off;
+#pragma unroll 1
+        for (int bt = 0; bt < 2; ++bt) {
+          const int rbase = warp * 16 + bt * RPW;                // tile row of rv[1]; shared row = tile row + 1
+          float4 rv[RPW + 2];
 #pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-          const float r_ = rsqrtf(rs[i] * (1.0f / 128.0f) + 1e-5f);
-          const uint64_t r2 = pack2(r_, r_);
-          float y0, y1, y2, y3;
-          unpack2(ffma2(fmul2(d01[i], r2), g01, b01), y0, y1);
-          unpack2(ffma2(fmul2(d23[i], r2), g23, b23), y2, y3);
-          uint2 pk;
-          pk.x = pack_f16(y0, y1);
-          pk.y = pack_f16(y2, y3);
-          *reinterpret_cast<uint2*>(img + (rbase + i) * 128 + ((piece ^ (uint32_t)i) << 4)) = pk;   // (row & 7) == i
+          for (int i = 0; i < RPW + 2; ++i) rv[i] = *reinterpret_cast<const float4*>(sX + (rbase + i) * 128 + c4);
+          uint64_t d01[RPW], d23[RPW];
+          float mean[RPW], rs[RPW];
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) {
+            d01[i] = ffma2(w0a, pack2(rv[i].x, rv[i].y), ffma2(w1a, pack2(rv[i + 1].x, rv[i + 1].y), ffma2(w2a, pack2(rv[i + 2].x, rv[i + 2].y), cba)));
+            d23[i] = ffma2(w0b, pack2(rv[i].z, rv[i].w), ffma2(w1b, pack2(rv[i + 1].z, rv[i + 1].w), ffma2(w2b, pack2(rv[i + 2].z, rv[i + 2].w), cbb)));
+            float s0, s1;
+            unpack2(fadd2(d01[i], d23[i]), s0, s1);
+            mean[i] = s0 + s1;
+          }
+          warp_sum8(mean, lane);
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) {
+            const float nm = mean[i] * (-1.0f / 128.0f);
+            const uint64_t nm2 = pack2(nm, nm);
+            d01[i] = fadd2(d01[i], nm2);
+            d23[i] = fadd2(d23[i], nm2);
+            float s0, s1;
+            unpack2(ffma2(d23[i], d23[i], fmul2(d01[i], d01[i])), s0, s1);
+            rs[i] = s0 + s1;
+          }
+          warp_sum8(rs, lane);
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) {
+            const float r_ = rsqrtf(rs[i] * (1.0f / 128.0f) + 1e-5f);
+            const uint64_t r2 = pack2(r_, r_);
+            float y0, y1, y2, y3;
+            unpack2(ffma2(fmul2(d01[i], r2), g01, b01), y0, y1);
+            unpack2(ffma2(fmul2(d23[i], r2), g23, b23), y2, y3);
+            uint2 pk;
+            pk.x = pack_f16(y0, y1);
+            pk.y = pack_f16(y2, y3);
+            *reinterpret_cast<uint2*>(img + (rbase + i) * 128 + ((piece ^ (uint32_t)i) << 4)) = pk;   // (row & 7) == i
+          }
         }
         fence_proxy_async();
         mbar_arrive(&a_ready[ab]);
-        if (warp == 0) KTR(0, 3 * ln + 2);
-        if (ln == NL - 1) mbar_arrive(x_free);                   // the loader may overwrite the context tile
-        fetch_params(ln + 1 == NL ? 0 : ln + 1);
+        if (warp == 0) KTR(0, 3 * l + 2);
+        if (l == NL - 1) mbar_arrive(x_free);                    // the loader may overwrite the context tile
       }
-      if (n >= 0) {
-        // ---------------- epilogue of step n: ACC[n & 1] -> K | V^T tile images -> two bulk stores ----------------
+    }
+  } else if (warp < 16) {
+    // ------------------------------- epilogue warps: ACC[n & 1] -> K | V^T tile images -> two bulk stores -------------------------------
+    // 4 lane quadrants x 2 halves: half 0 = the 64 K columns (fp16, K-major rows), half 1 = the 64 V columns (bf16, transposed)
+    const int e = warp - 8;
+    const int q = e & 3, half = e >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    int n = 0, it = 0;
+#pragma unroll 1
+    for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
+      const int pair = g / a.tiles, tile = g - pair * a.tiles;
+      const bool valid = tile * 128 + r < a.L;
+#pragma unroll 1
+      for (int l = 0; l < NL; ++l, ++n) {
         const int b = n & 1;
-        const int g = blockIdx.x + it * gridDim.x;
-        const int pair = g / a.tiles, tile = g - pair * a.tiles;
-        const bool valid = tile * 128 + r < a.L;
-        if (warp == 0) KTR(2, 4 * l);
+        if (warp == 8) KTR(2, 4 * l);
         mbar_wait(&acc_full[b], (n >> 1) & 1);
         tc_fence_after();
-        if (warp == 0) KTR(2, 4 * l + 1);
-        uint32_t v[32];
-        tmem_ld32(trow + b * 128 + cq * 32, v);
+        if (warp == 8) KTR(2, 4 * l + 1);
+        uint32_t v[64];
+        tmem_ld32(trow + b * 128 + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(trow + b * 128 + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&acc_free[b]);
-        if (tid == 0) bulk_wait_read();                          // the previous step's images have left the staging buffer
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (warp == 0) KTR(2, 4 * l + 2);
-        if (cq < 2) {                                            // K: fp16, K-major rows (token r, dims cq * 32 ..)
-          uint8_t* dst = sOut;
+        if (tid == 256) bulk_wait_read();                        // the previous step's images have left the staging buffer
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 8) KTR(2, 4 * l + 2);
+        if (half == 0) {                                         // K: token r, dims 0..63
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 8; ++j) {
             uint4 pk;
             pk.x = valid ? pack_f16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])) : 0u;
             pk.y = valid ? pack_f16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])) : 0u;
             pk.z = valid ? pack_f16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])) : 0u;
             pk.w = valid ? pack_f16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])) : 0u;
-            *reinterpret_cast<uint4*>(dst + swz_off(r, cq * 4 + j)) = pk;
+            *reinterpret_cast<uint4*>(sOut + swz_off(r, j)) = pk;
           }
-        } else {                                                 // V^T: bf16, rows = dims, 64 tokens per 128-byte row, two token halves
+        } else {                                                 // V^T: rows = dims, 64 tokens per 128-byte row, two token halves
           uint8_t* dst = sOut + 16384 + (r >> 6) * 8192 + (r & 7) * 2;
           const int kchunk = (r & 63) >> 3;
-          const int d0 = (cq - 2) * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            *reinterpret_cast<__nv_bfloat16*>(dst + swz_off(d0 + i, kchunk)) = __float2bfloat16_rn(valid ? __uint_as_float(v[i]) : 0.f);
+          for (int i = 0; i < 64; ++i)
+            *reinterpret_cast<__nv_bfloat16*>(dst + swz_off(i, kchunk)) = __float2bfloat16_rn(valid ? __uint_as_float(v[i]) : 0.f);
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (tid == 0) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 256) {
           const size_t tix = (size_t)g * (128 * 64);
           bulk_s2g(a.layer[l].k_out + tix, sOut, 16384);
           bulk_s2g(a.layer[l].v_out + tix, sOut + 16384, 16384);
           bulk_commit();
         }
-        if (warp == 0) KTR(2, 4 * l + 3);
+        if (warp == 8) KTR(2, 4 * l + 3);
       }
-      it = itn; l = ln;
-      if (++ln == NL) { ln = 0; ++itn; }
     }
-    if (tid == 0) bulk_wait_read();
+    if (tid == 256) bulk_wait_read();
   }
   tc_fence_before();
   __syncthreads();
