@@ -643,8 +643,10 @@ int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, co
   TRY(run_prep(ctx, w, src, tgt, B, N, st));
   {
     ProfScope ps(CAT_PREP, st);
-    const long long rows = (long long)B * N;
-    layer0_kernel<<<(unsigned)std::min<long long>((rows + 7) / 8, 148 * 16), 256, 0, st>>>(corr, ctx->l0_w, ctx->l0_b, w.featA, rows, 6);
+    // written straight as the split fp16 tile image the first encoder layer's persistent PointCN / QKV kernel consumes
+    const int tiles = cdiv(N, 128);
+    const long long rows = (long long)B * tiles * 128;
+    layer0_kernel<<<(unsigned)std::min<long long>((rows + 7) / 8, 148 * 16), 256, 0, st>>>(corr, ctx->l0_w, ctx->l0_b, nullptr, rows, 6, w.feat_img, N, tiles);
     LAUNCHED();
   }
   // Fusion-1: queries = q-image tokens, context = p-image tokens (PointDSC.py:137)
@@ -654,7 +656,7 @@ int forward_chunk(gmf_ctx* ctx, Work& w, const float* corr, const float* src, co
   TRY(run_fusion_kv_all(ctx, w, w.imgfeat, B, T, st));
   // between layers the features travel as the split fp16 tile image the next PointCN/QKV kernel consumes (last layer: row-major)
   for (int li = 0; li < L; ++li)
-    TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, li > 0, li + 1 < L, true));
+    TRY(run_encoder_layer(ctx, li, w, w.featA, w.imgfeat, B, N, T, w.featA, st, true, li + 1 < L, true));
   if (feat_out) CU(cudaMemcpyAsync(feat_out, w.featA, (size_t)B * N * 128 * 4, cudaMemcpyDeviceToDevice, st));
   TRY(run_classify(ctx, w.featA, (long long)B * N, w.normed, conf_out, st));
   TRY(run_pick_seeds(ctx, w, conf_out, B, N, S, testing ? 1 : 0, seeds_out, st));

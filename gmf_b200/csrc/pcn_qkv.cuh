@@ -289,7 +289,266 @@ __global__ void __launch_bounds__(544, 1) pcn_qkv_kernel(const PcnQkvArgs a) {
   if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// PERSISTENT variant for layers whose input arrives as the split fp16 tile image (all but the first): one CTA per SM walks the tiles.
+// The one-tile-per-CTA kernel above spends 2.3-4 k cycles waiting for its tile image, ~3 k in ring-slot reuse stalls of the second GEMM,
+// ~2.8 k draining its image stores and ~2.5 k in launch / setup per 15-18 k cycle tile (GMF_PCN_TRACE).  Here the image of tile t+1 lands in
+// the second 64 KB buffer and its PointCN GEMM runs while the workers still assemble the Q / K / V images of tile t; weights stream
+// continuously through a 3-deep ring from their own warp; bulk stores drain under the next tile.
+//   warps 0-15 workers (epilogues), 16 MMA issuer, 17 weight producer, 18 tile-image loader.
+//   Shared memory: A[2] 64 KB each (image -> feat1 fp32 staging -> Q | K images -> V image), ring 3 x 32 KB, biases, barriers = 227 KB
+//   (the dynamic window starts 1 KB into the SM's shared memory, i.e. 1024-aligned: the kernel traps if more than 768 B of padding were needed).
+// ------------------------------------------------------------------------------------------------
+struct PcnQkvPCfg {
+  static constexpr int A_BYTES = 128 * 128 * 4, W_BYTES = 128 * 64 * 4, NBUF = 3, NCHUNK = 8;
+  static constexpr int BIAS_BYTES = 512 * 4;
+  static constexpr int SMEM = 2 * A_BYTES + NBUF * W_BYTES + BIAS_BYTES + 256 + 768;
+  static constexpr int THREADS = 608;
+};
+
+__global__ void __launch_bounds__(PcnQkvPCfg::THREADS, 1) pcn_qkv_persist_kernel(const PcnQkvArgs a, const int pairs) {
+  using Cfg = PcnQkvPCfg;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  if (pad > 768u) __trap();
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* sA = smem;                                     // [2]
+  uint8_t* sB = sA + 2 * Cfg::A_BYTES;                    // [3]
+  float* sBias = (float*)(sB + Cfg::NBUF * Cfg::W_BYTES); // PointCN bias [128] | Q,K,V biases [384]
+  uint64_t* bars = (uint64_t*)((uint8_t*)sBias + Cfg::BIAS_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  const BarArr img_full{bar0};                      // [2]      tile image landed in A[b]
+  const BarArr st_ready = BarArr{bar0} + 2;        // [3] 512  Q / K / V image of the tile assembled in A[b] -> the loader thread bulk-stores it
+  const BarArr q_drained = BarArr{bar0} + 19;      //          Q's bulk store has read its 32 KB: the V image may be written there
+  const BarArr w_full = BarArr{bar0} + 5;          // [3]
+  const BarArr w_empty = BarArr{bar0} + 8;         // [3]
+  const BarArr acc0_full = BarArr{bar0} + 11;      //          PointCN accumulator complete
+  const BarArr f1_ready = BarArr{bar0} + 12;       // 512      feat1 (fp16 hi | lo) back in tensor memory
+  const BarArr blk_full = BarArr{bar0} + 13;       // [3]      Q / K / V accumulator complete
+  const BarArr blk_free = BarArr{bar0} + 16;       // [3] 512  workers have read the Q / K / V accumulator of the previous tile
+  uint32_t* tmem_slot = (uint32_t*)(bars + 20);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total = a.tiles * pairs;
+  if (tid < 512) sBias[tid] = tid < 128 ? a.pcn_bias[tid] : a.qkv_bias[tid - 128];
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) mbar_init(&img_full[i], 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&blk_full[i], 1); mbar_init(&blk_free[i], 512); mbar_init(&st_ready[i], 512); }
+    mbar_init(acc0_full, 1); mbar_init(f1_ready, 512); mbar_init(q_drained, 1);
+    fence_mbar_init();
+  }
+  if (warp == 16) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 18) {
+    // ------------------------------- tile-image loader AND image storer: one thread owns every bulk copy that touches A[] -------------------------------
+    // so it knows without asking when a buffer's stores have drained (bulk async-groups are per thread) and no worker ever waits for a store.
+    if (elect_one()) {
+      const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      mbar_expect_tx(&img_full[0], Cfg::A_BYTES);
+      bulk_g2s(sA, a.x_img + (size_t)blockIdx.x * (128 * 128), Cfg::A_BYTES, &img_full[0]);
+#pragma unroll 1
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        const size_t g = blockIdx.x + (size_t)it * gridDim.x;
+        if (it + 1 < my_tiles) {                                 // image of the next tile -> the other buffer, once the stores of tile it - 1 have read it
+          if (it >= 1) bulk_wait_read();
+          mbar_expect_tx(&img_full[b ^ 1], Cfg::A_BYTES);
+          bulk_g2s(sA + (b ^ 1) * Cfg::A_BYTES, a.x_img + (g + gridDim.x) * (128 * 128), Cfg::A_BYTES, &img_full[b ^ 1]);
+        }
+#pragma unroll 1
+        for (int which = 0; which < 3; ++which) {
+          mbar_wait(&st_ready[which], it & 1);
+          bulk_s2g((which == 0 ? a.tq : which == 1 ? a.tk : a.tv) + g * (128 * 128), sA + b * Cfg::A_BYTES + (which == 1 ? 32768 : 0), 32768);
+          bulk_commit();
+          if (which == 1) {                                      // Q's store (all but the most recent group) has read its half of A[b]
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            mbar_arrive(q_drained);
+          }
+        }
+      }
+      bulk_wait_read();
+    }
+    __syncwarp();
+  } else if (warp == 17) {
+    // ------------------------------- weight producer: 8 chunks per tile through a 3-deep ring, running across tiles -------------------------------
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint8_t* wsrc = (const uint8_t*)a.w_packed;
+    int s = 0;
+#pragma unroll 1
+    for (int g = blockIdx.x; g < total; g += gridDim.x)
+#pragma unroll 1
+      for (int c = 0; c < Cfg::NCHUNK; ++c, ++s) {
+        const int slot = s % Cfg::NBUF;
+        if (s >= Cfg::NBUF) mbar_wait(&w_empty[slot], ((s / Cfg::NBUF) - 1) & 1);
+        mbar_expect_tx_p(&w_full[slot], Cfg::W_BYTES, leader);
+        bulk_g2s_p(sB + slot * Cfg::W_BYTES, wsrc + (size_t)c * Cfg::W_BYTES, Cfg::W_BYTES, &w_full[slot], leader);
+      }
+  } else if (warp == 16) {
+    // ------------------------------- MMA issuer -------------------------------
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = umma_idesc(128, 128, kFmtF16);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
+    int it = 0, s = 0;
+#pragma unroll 1
+    for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t tpar = it & 1;
+      mbar_wait(&img_full[b], (it >> 1) & 1);
+#pragma unroll 1
+      for (int c = 0; c < Cfg::NCHUNK; ++c, ++s) {
+        const int slot = s % Cfg::NBUF;
+        const int kc = c & 1;
+        if (c == 2) mbar_wait(f1_ready, tpar);                                   // feat1 (fp16 hi | lo) is back in TMEM columns 0..127
+        if (c >= 2 && kc == 0 && it > 0) mbar_wait(&blk_free[(c - 2) >> 1], (it - 1) & 1);   // the previous tile's block has been read out
+        mbar_wait(&w_full[slot], (s / Cfg::NBUF) & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t bd = umma_desc_adv(b_desc0, slot * Cfg::W_BYTES);
+          // chunk = k-half kc: {w_hi atom | w_lo atom}; three products per K16 step: hi hi, lo hi, hi lo
+          if (c < 2) {                                           // PointCN: A = split tile image in shared memory (hi atoms 0,1 | lo atoms 0,1)
+            const uint64_t ad = umma_desc_adv(a_desc0, b * Cfg::A_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ah = umma_desc_adv(ad, kc * 16384 + ks * 32), al = umma_desc_adv(ad, 32768 + kc * 16384 + ks * 32);
+              const uint64_t bh = umma_desc_adv(bd, ks * 32), bl = umma_desc_adv(bd, 16384 + ks * 32);
+              tc_mma_bf16(tm, ah, bh, idesc, (kc | ks) ? 1u : 0u);
+              tc_mma_bf16(tm, al, bh, idesc, 1u);
+              tc_mma_bf16(tm, ah, bl, idesc, 1u);
+            }
+          } else {                                               // Q / K / V: A = feat1 in tensor memory (hi: columns 0..63, lo: 64..127)
+            const int nb = (c - 2) >> 1;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ah = tm + kc * 32 + ks * 8, al = tm + 64 + kc * 32 + ks * 8;
+              const uint64_t bh = umma_desc_adv(bd, ks * 32), bl = umma_desc_adv(bd, 16384 + ks * 32);
+              tc_mma_bf16_ts(tm + 128 + nb * 128, ah, bh, idesc, (kc | ks) ? 1u : 0u);
+              tc_mma_bf16_ts(tm + 128 + nb * 128, al, bh, idesc, 1u);
+              tc_mma_bf16_ts(tm + 128 + nb * 128, ah, bl, idesc, 1u);
+            }
+          }
+          tc_commit(&w_empty[slot]);
+          if (c == 1) tc_commit(acc0_full);
+          if (c >= 3 && kc == 1) tc_commit(&blk_full[(c - 2) >> 1]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 16) {
+    // ------------------------------- workers -------------------------------
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const int srow = lane >> 3, sj = lane & 7;
+    int it = 0;
+#pragma unroll 1
+    for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t tpar = it & 1;
+      const int pair = g / a.tiles, tile = g - pair * a.tiles;
+      const int row0 = tile * 128;
+      const bool valid = row0 + r < a.L;
+      uint8_t* sAb = sA + b * Cfg::A_BYTES;
+      // ---------------- epilogue 0: feat1 = ReLU(acc + b) -> HBM (coalesced) and back to TMEM as fp16 hi | lo ----------------
+      mbar_wait(acc0_full, tpar);
+      tc_fence_after();
+      {
+        float* stg = (float*)sAb + warp * 1024;                  // the tile image is dead once acc0_full fired
+        uint32_t v[32], hw[16], lw[16];
+        tmem_ld32(trow + part * 32, v);
+        tmem_ld_wait();
+        const int col0 = part * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(sBias + col0 + 4 * j);
+          const float4 o = make_float4(fmaxf(__uint_as_float(v[4 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f),
+                                       fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f));
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+          split_f16x2(o.x, o.y, hw[2 * j], lw[2 * j]);
+          split_f16x2(o.z, o.w, hw[2 * j + 1], lw[2 * j + 1]);
+        }
+        // the packed operand (hi: columns 0..63, lo: 64..127) overwrites accumulator columns the other three warps of this lane quadrant may
+        // still be reading
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+        tmem_st16(trow + part * 16, hw);
+        tmem_st16(trow + 64 + part * 16, lw);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(f1_ready);
+        __syncwarp();
+        const size_t gbase = ((size_t)pair * a.L + row0 + q * 32) * 128 + col0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rw = i * 4 + srow;
+          if (row0 + q * 32 + rw < a.L)
+            *reinterpret_cast<float4*>(a.feat1 + gbase + (size_t)rw * 128 + sj * 4) = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
+        }
+      }
+      // ---------------- epilogue 1: Q / K / V^T tile images: Q -> A[b] lower half, K -> upper half, V -> lower half once Q's store has drained ------
+#pragma unroll 1
+      for (int which = 0; which < 3; ++which) {
+        mbar_wait(&blk_full[which], tpar);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(trow + 128 + which * 128 + part * 32, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&blk_free[which]);
+        uint8_t* img = sAb + (which == 1 ? 32768 : 0);
+        const int col0 = which * 128 + part * 32, dcol0 = part * 32;
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sBias + 128 + col0 + 4 * i);
+          o[4 * i] = valid ? __uint_as_float(v[4 * i]) + b4.x : 0.f;
+          o[4 * i + 1] = valid ? __uint_as_float(v[4 * i + 1]) + b4.y : 0.f;
+          o[4 * i + 2] = valid ? __uint_as_float(v[4 * i + 2]) + b4.z : 0.f;
+          o[4 * i + 3] = valid ? __uint_as_float(v[4 * i + 3]) + b4.w : 0.f;
+        }
+        // Q (and K, in the upper half) overwrite the feat1 staging tiles: every warp must have stored its feat1 rows; V overwrites the Q image:
+        // its bulk store must have read it
+        if (which == 0) asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (which == 2) mbar_wait(q_drained, tpar);
+        if (which < 2) {
+          uint8_t* dst = img + (dcol0 >> 6) * 16384;
+          const int cc0 = (dcol0 & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = pack_f16(o[8 * j], o[8 * j + 1]); pk.y = pack_f16(o[8 * j + 2], o[8 * j + 3]);
+            pk.z = pack_f16(o[8 * j + 4], o[8 * j + 5]); pk.w = pack_f16(o[8 * j + 6], o[8 * j + 7]);
+            *reinterpret_cast<uint4*>(dst + swz_off(r, cc0 + j)) = pk;
+          }
+        } else {
+          uint8_t* dst = img + (r >> 6) * (128 * 128) + (r & 7) * 2;
+          const int kchunk = (r & 63) >> 3;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) *reinterpret_cast<__nv_bfloat16*>(dst + swz_off(dcol0 + i, kchunk)) = __float2bfloat16_rn(o[i]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&st_ready[which]);                           // the loader thread ships the image
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
 inline cudaError_t launch_pcn_qkv(const PcnQkvArgs& a, int pairs, cudaStream_t st) {
+  if (a.x_img) {                                                 // tile-image input: persistent kernel
+    static std::atomic<unsigned long long> configured_p{0};
+    if (cudaError_t e = ensure_dyn_smem(pcn_qkv_persist_kernel, PcnQkvPCfg::SMEM, configured_p)) return e;
+    const int total = a.tiles * pairs;
+    if (total <= 0) return cudaSuccess;
+    pcn_qkv_persist_kernel<<<min(total, device_sm_count()), PcnQkvPCfg::THREADS, PcnQkvPCfg::SMEM, st>>>(a, pairs);
+    return cudaGetLastError();
+  }
   static std::atomic<unsigned long long> configured{0};
   if (cudaError_t e = ensure_dyn_smem(pcn_qkv_kernel, PcnQkvCfg::SMEM, configured)) return e;
   pcn_qkv_kernel<<<dim3(a.tiles, pairs), 544, PcnQkvCfg::SMEM, st>>>(a);

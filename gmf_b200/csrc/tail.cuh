@@ -136,8 +136,11 @@ __global__ void prep_points_kernel(const float* __restrict__ src, const float* _
 // layer0: Conv1d(6 -> 128, k=1)  (PointDSC.py:88,139).  One thread = one token x 4 channels.
 // One warp per row (lane = 4 output channels), weights and bias held in registers across a grid-stride loop over rows, four rows in
 // flight per iteration: the kernel is a pure 512-byte-per-row store stream (HBM bound) instead of 30 scattered loads per output float4.
+// img != NULL (forward path): the rows are written as the split fp16 tile image [B][tiles][hi 2 x 16 KB | lo 2 x 16 KB] the persistent PointCN / QKV
+// kernel loads with one bulk copy (pcn_qkv.cuh); `rows` then counts PADDED rows (B x tiles x 128) and rows >= L of a pair's last tile are zeros.
 __global__ void __launch_bounds__(256) layer0_kernel(const float* __restrict__ corr, const float* __restrict__ w, const float* __restrict__ b,
-                                                     float* __restrict__ out, long long rows, int in_dim) {
+                                                     float* __restrict__ out, long long rows, int in_dim, float* __restrict__ img = nullptr, int L = 0,
+                                                     int tiles = 0) {
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
   const int c4 = lane * 4;
@@ -150,10 +153,17 @@ __global__ void __launch_bounds__(256) layer0_kernel(const float* __restrict__ c
   }
   for (long long row = gw; row < rows; row += 4 * nw) {
     float xv[4];
+    long long src_row[4];                                        // row of `corr` (-1: padding row of an image tile)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long rr = row + u * nw;
-      xv[u] = (rr < rows && lane < in_dim) ? corr[rr * in_dim + lane] : 0.f;
+      src_row[u] = rr;
+      if (img) {
+        const long long pair = rr / ((long long)tiles * 128);
+        const int r = (int)(rr - pair * tiles * 128);
+        src_row[u] = r < L ? pair * L + r : -1;
+      }
+      xv[u] = (rr < rows && src_row[u] >= 0 && lane < in_dim) ? corr[src_row[u] * in_dim + lane] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -167,7 +177,17 @@ __global__ void __launch_bounds__(256) layer0_kernel(const float* __restrict__ c
           for (int j = 0; j < 4; ++j) o[j] = fmaf(wr[j][k], x, o[j]);
         }
       }
-      if (rr < rows) *reinterpret_cast<float4*>(out + rr * 128 + c4) = make_float4(o[0], o[1], o[2], o[3]);
+      if (rr < rows && !img) *reinterpret_cast<float4*>(out + rr * 128 + c4) = make_float4(o[0], o[1], o[2], o[3]);
+      if (rr < rows && img) {
+        if (src_row[u] < 0) o[0] = o[1] = o[2] = o[3] = 0.f;
+        uint2 H, Lw;
+        split_f16x2(o[0], o[1], H.x, Lw.x);
+        split_f16x2(o[2], o[3], H.y, Lw.y);
+        // channels 4 lane .. 4 lane + 3 -> fp16 atom lane / 16, 16-byte chunk (lane & 15) / 2, 8-byte half (lane & 1)
+        uint8_t* base = (uint8_t*)(img + (rr >> 7) * (128 * 128)) + (lane >> 4) * 16384 + swz_off((int)(rr & 127), (lane & 15) >> 1) + (lane & 1) * 8;
+        *reinterpret_cast<uint2*>(base) = H;
+        *reinterpret_cast<uint2*>(base + 32768) = Lw;
+      }
     }
   }
 }
