@@ -531,8 +531,26 @@ int run_encoder_layer(const gmf_ctx* ctx, int li, Work& w, const float* feat_in,
     PcnQkvArgs a{};
     a.x = feat_in; a.x_img = in_img ? w.feat_img : nullptr; a.L = N; a.tiles = cdiv(N, 128); a.w_packed = lw.pq_w; a.pcn_bias = lw.pcn_b; a.qkv_bias = lw.qkv_b;
     a.feat1 = w.feat1; a.tq = w.qs; a.tk = w.ks; a.tv = w.vts;
+#ifdef GMF_FFN_TRACE
+    static int n_pcn = 0;
+    const bool pcn_trace = (++n_pcn == 20);
+    if (pcn_trace) { cudaMalloc(&a.trace, 64 * 8); cudaMemsetAsync(a.trace, 0, 64 * 8, st); }
+#endif
     ProfScope ps(CAT_QKV, st);
     cudaError_t e = launch_pcn_qkv(a, B, st);
+#ifdef GMF_FFN_TRACE
+    if (pcn_trace) {
+      cudaStreamSynchronize(st);
+      long long h[64];
+      cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost);
+      const long long t0 = h[0];
+      fprintf(stderr, "pcn trace worker: start 0 | acc0 got %lld | f1 back %lld |", h[1] - t0, h[2] - t0);
+      for (int w = 0; w < 3; ++w) fprintf(stderr, " blk%d wait %lld got %lld image done %lld |", w, h[3 + 3 * w] - t0, h[4 + 3 * w] - t0, h[5 + 3 * w] - t0);
+      fprintf(stderr, "\npcn trace mma: tile start %lld img got %lld |", h[32 + 16] - t0, h[32 + 17] - t0);
+      for (int c = 0; c < 8; ++c) fprintf(stderr, " c%d start %lld W got %lld |", c, h[32 + 2 * c] - t0, h[32 + 2 * c + 1] - t0);
+      fprintf(stderr, "\n");
+    }
+#endif
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail_cuda(e, "pcn_qkv launch");
   }

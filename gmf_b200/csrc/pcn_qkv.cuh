@@ -30,6 +30,9 @@ struct PcnQkvArgs {
   const float* qkv_bias;   // [384] (q part pre-scaled)
   float* feat1;            // [B, L, 128]
   __nv_bfloat16 *tq, *tk, *tv;   // [B][tiles][128*128] tile images
+#ifdef GMF_FFN_TRACE
+  long long* trace;        // development build: clock64 stamps of CTA 3's third tile (tools/pcn_trace.py)
+#endif
 };
 
 // 17 warps: 16 workers (TMEM lane quadrant = warp & 3, 32-column chunk = warp >> 2) + one control warp
@@ -306,6 +309,57 @@ struct PcnQkvPCfg {
   static constexpr int THREADS = 608;
 };
 
+// The 8 weight chunks of one tile, fully unrolled with COMPILE-TIME ring slots ((S0 + c) % 3; S0 = first slot of the tile, period 3 tiles): with
+// run-time slots every MMA paid ~80 cycles of vector -> uniform register traffic for its descriptors (1 k cycles per 12-MMA chunk).
+struct PcnIssue {
+  uint32_t tm, idesc, leader, tpar, ppar;      // ppar: parity of the previous tile (blk_free)
+  uint64_t a_desc, b_desc0;                    // A = this tile's image buffer
+  BarArr w_full, w_empty, acc0_full, f1_ready, blk_full, blk_free;
+  int s, it;                                   // ring stage of chunk 0
+};
+template <int S0>
+__device__ __forceinline__ void pcn_issue_tile(const PcnIssue& m) {
+  using Cfg = PcnQkvPCfg;
+#pragma unroll
+  for (int c = 0; c < Cfg::NCHUNK; ++c) {
+    constexpr int dummy = 0; (void)dummy;
+    const int slot = (S0 + c) % Cfg::NBUF;                       // compile-time after unrolling
+    const int kc = c & 1;
+    if (c == 2) mbar_wait(m.f1_ready, m.tpar);                   // feat1 (fp16 hi | lo) is back in TMEM columns 0..127
+    if (c >= 2 && kc == 0 && m.it > 0) mbar_wait(&m.blk_free[(c - 2) >> 1], m.ppar);   // the previous tile's block has been read out
+    mbar_wait(&m.w_full[slot], (uint32_t)((m.s + c) / Cfg::NBUF) & 1u);
+    tc_fence_after();
+    if (m.leader) {
+      const uint64_t bd = umma_desc_adv(m.b_desc0, slot * Cfg::W_BYTES);
+      // chunk = k-half kc: {w_hi atom | w_lo atom}; three products per K16 step: hi hi, lo hi, hi lo
+      if (c < 2) {                                               // PointCN: A = split tile image in shared memory (hi atoms 0,1 | lo atoms 0,1)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ah = umma_desc_adv(m.a_desc, kc * 16384 + ks * 32), al = umma_desc_adv(m.a_desc, 32768 + kc * 16384 + ks * 32);
+          const uint64_t bh = umma_desc_adv(bd, ks * 32), bl = umma_desc_adv(bd, 16384 + ks * 32);
+          tc_mma_bf16(m.tm, ah, bh, m.idesc, (kc | ks) ? 1u : 0u);
+          tc_mma_bf16(m.tm, al, bh, m.idesc, 1u);
+          tc_mma_bf16(m.tm, ah, bl, m.idesc, 1u);
+        }
+      } else {                                                   // Q / K / V: A = feat1 in tensor memory (hi: columns 0..63, lo: 64..127)
+        const int nb = (c - 2) >> 1;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ah = m.tm + kc * 32 + ks * 8, al = m.tm + 64 + kc * 32 + ks * 8;
+          const uint64_t bh = umma_desc_adv(bd, ks * 32), bl = umma_desc_adv(bd, 16384 + ks * 32);
+          tc_mma_bf16_ts(m.tm + 128 + nb * 128, ah, bh, m.idesc, (kc | ks) ? 1u : 0u);
+          tc_mma_bf16_ts(m.tm + 128 + nb * 128, al, bh, m.idesc, 1u);
+          tc_mma_bf16_ts(m.tm + 128 + nb * 128, ah, bl, m.idesc, 1u);
+        }
+      }
+      tc_commit(&m.w_empty[slot]);
+      if (c == 1) tc_commit(m.acc0_full);
+      if (c >= 3 && kc == 1) tc_commit(&m.blk_full[(c - 2) >> 1]);
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(PcnQkvPCfg::THREADS, 1) pcn_qkv_persist_kernel(const PcnQkvArgs a, const int pairs) {
   using Cfg = PcnQkvPCfg;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -330,6 +384,11 @@ __global__ void __launch_bounds__(PcnQkvPCfg::THREADS, 1) pcn_qkv_persist_kernel
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total = a.tiles * pairs;
+#ifdef GMF_FFN_TRACE
+#define PTRC(role, idx) do { if (a.trace && blockIdx.x == 3 && it == 2 && lane == 0) a.trace[(role) * 32 + (idx)] = clock64(); } while (0)
+#else
+#define PTRC(role, idx) do {} while (0)
+#endif
   if (tid < 512) sBias[tid] = tid < 128 ? a.pcn_bias[tid] : a.qkv_bias[tid - 128];
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) mbar_init(&img_full[i], 1);
@@ -389,55 +448,24 @@ __global__ void __launch_bounds__(PcnQkvPCfg::THREADS, 1) pcn_qkv_persist_kernel
       }
   } else if (warp == 16) {
     // ------------------------------- MMA issuer -------------------------------
-    const uint32_t leader = elect_one() ? 1u : 0u;
-    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t idesc = umma_idesc(128, 128, kFmtF16);
+    PcnIssue m;
+    m.leader = elect_one() ? 1u : 0u;
+    m.tm = __shfl_sync(0xffffffffu, tmem, 0);
+    m.idesc = umma_idesc(128, 128, kFmtF16);
     const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
-    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
-    int it = 0, s = 0;
+    m.b_desc0 = umma_desc_sw128(smem_u32(sB));
+    m.w_full = w_full; m.w_empty = w_empty; m.acc0_full = acc0_full; m.f1_ready = f1_ready; m.blk_full = blk_full; m.blk_free = blk_free;
+    int it = 0, ph = 0;
 #pragma unroll 1
     for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
       const int b = it & 1;
-      const uint32_t tpar = it & 1;
+      m.tpar = it & 1; m.ppar = (it - 1) & 1; m.it = it; m.s = it * Cfg::NCHUNK;
+      m.a_desc = umma_desc_adv(a_desc0, b * Cfg::A_BYTES);
       mbar_wait(&img_full[b], (it >> 1) & 1);
-#pragma unroll 1
-      for (int c = 0; c < Cfg::NCHUNK; ++c, ++s) {
-        const int slot = s % Cfg::NBUF;
-        const int kc = c & 1;
-        if (c == 2) mbar_wait(f1_ready, tpar);                                   // feat1 (fp16 hi | lo) is back in TMEM columns 0..127
-        if (c >= 2 && kc == 0 && it > 0) mbar_wait(&blk_free[(c - 2) >> 1], (it - 1) & 1);   // the previous tile's block has been read out
-        mbar_wait(&w_full[slot], (s / Cfg::NBUF) & 1);
-        tc_fence_after();
-        if (leader) {
-          const uint64_t bd = umma_desc_adv(b_desc0, slot * Cfg::W_BYTES);
-          // chunk = k-half kc: {w_hi atom | w_lo atom}; three products per K16 step: hi hi, lo hi, hi lo
-          if (c < 2) {                                           // PointCN: A = split tile image in shared memory (hi atoms 0,1 | lo atoms 0,1)
-            const uint64_t ad = umma_desc_adv(a_desc0, b * Cfg::A_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ah = umma_desc_adv(ad, kc * 16384 + ks * 32), al = umma_desc_adv(ad, 32768 + kc * 16384 + ks * 32);
-              const uint64_t bh = umma_desc_adv(bd, ks * 32), bl = umma_desc_adv(bd, 16384 + ks * 32);
-              tc_mma_bf16(tm, ah, bh, idesc, (kc | ks) ? 1u : 0u);
-              tc_mma_bf16(tm, al, bh, idesc, 1u);
-              tc_mma_bf16(tm, ah, bl, idesc, 1u);
-            }
-          } else {                                               // Q / K / V: A = feat1 in tensor memory (hi: columns 0..63, lo: 64..127)
-            const int nb = (c - 2) >> 1;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t ah = tm + kc * 32 + ks * 8, al = tm + 64 + kc * 32 + ks * 8;
-              const uint64_t bh = umma_desc_adv(bd, ks * 32), bl = umma_desc_adv(bd, 16384 + ks * 32);
-              tc_mma_bf16_ts(tm + 128 + nb * 128, ah, bh, idesc, (kc | ks) ? 1u : 0u);
-              tc_mma_bf16_ts(tm + 128 + nb * 128, al, bh, idesc, 1u);
-              tc_mma_bf16_ts(tm + 128 + nb * 128, ah, bl, idesc, 1u);
-            }
-          }
-          tc_commit(&w_empty[slot]);
-          if (c == 1) tc_commit(acc0_full);
-          if (c >= 3 && kc == 1) tc_commit(&blk_full[(c - 2) >> 1]);
-        }
-        __syncwarp();
-      }
+      if (ph == 0) pcn_issue_tile<0>(m);                         // first ring slot of tile it = (8 it) % 3 = 0, 2, 1, 0, ...
+      else if (ph == 1) pcn_issue_tile<2>(m);
+      else pcn_issue_tile<1>(m);
+      ph = ph == 2 ? 0 : ph + 1;
     }
   } else if (warp < 16) {
     // ------------------------------- workers -------------------------------
@@ -455,8 +483,10 @@ __global__ void __launch_bounds__(PcnQkvPCfg::THREADS, 1) pcn_qkv_persist_kernel
       const bool valid = row0 + r < a.L;
       uint8_t* sAb = sA + b * Cfg::A_BYTES;
       // ---------------- epilogue 0: feat1 = ReLU(acc + b) -> HBM (coalesced) and back to TMEM as fp16 hi | lo ----------------
+      if (warp == 0) PTRC(0, 0);
       mbar_wait(acc0_full, tpar);
       tc_fence_after();
+      if (warp == 0) PTRC(0, 1);
       {
         float* stg = (float*)sAb + warp * 1024;                  // the tile image is dead once acc0_full fired
         uint32_t v[32], hw[16], lw[16];
@@ -480,6 +510,7 @@ __global__ void __launch_bounds__(PcnQkvPCfg::THREADS, 1) pcn_qkv_persist_kernel
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(f1_ready);
+        if (warp == 0) PTRC(0, 2);
         __syncwarp();
         const size_t gbase = ((size_t)pair * a.L + row0 + q * 32) * 128 + col0;
 #pragma unroll
@@ -492,8 +523,10 @@ __global__ void __launch_bounds__(PcnQkvPCfg::THREADS, 1) pcn_qkv_persist_kernel
       // ---------------- epilogue 1: Q / K / V^T tile images: Q -> A[b] lower half, K -> upper half, V -> lower half once Q's store has drained ------
 #pragma unroll 1
       for (int which = 0; which < 3; ++which) {
+        if (warp == 0) PTRC(0, 3 + 3 * which);
         mbar_wait(&blk_full[which], tpar);
         tc_fence_after();
+        if (warp == 0) PTRC(0, 4 + 3 * which);
         uint32_t v[32];
         tmem_ld32(trow + 128 + which * 128 + part * 32, v);
         tmem_ld_wait();
@@ -532,6 +565,7 @@ __global__ void __launch_bounds__(PcnQkvPCfg::THREADS, 1) pcn_qkv_persist_kernel
         }
         fence_proxy_async();
         mbar_arrive(&st_ready[which]);                           // the loader thread ships the image
+        if (warp == 0) PTRC(0, 5 + 3 * which);
       }
     }
   }
