@@ -13,5 +13,5 @@ timeout 600 $SMALL > gpurun_out/plain_small.log 2>&1 && \
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu.log 2>&1; echo "[ncu list exit $?]"
 BIG="python bench.py --pairs 64 --steps 1 --warmup 1 --min-warmup 1 $Q"
 timeout 600 $BIG > gpurun_out/plain_big.log 2>&1 && \
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"sc_attn_v9|fus_attn_v2|ffn_fused|pcn_qkv|kv_proj_all" -s 53 -c 5 -o gpurun_out/top5_cfg2 -f $BIG > gpurun_out/ncu_full.log 2>&1; echo "[ncu full exit $?]"
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"sc_attn_v9|fus_attn_v2|ffn_fused|pcn_qkv_persist|kv_proj_all" -s 53 -c 5 -o gpurun_out/top5_cfg2 -f $BIG > gpurun_out/ncu_full.log 2>&1; echo "[ncu full exit $?]"
 python __graft_entry__.py smoke
