@@ -23,6 +23,7 @@ EXPORTS = [
     "gmf_feature_compat_workspace_bytes", "gmf_feature_compat", "gmf_weighted_procrustes", "gmf_debug_plan_host_chunks",
     "gmf_sm_workspace_bytes", "gmf_sm_baseline", "gmf_global_registration",
     "gmf_dgr_head_train_workspace_bytes", "gmf_dgr_head_param_count", "gmf_dgr_head_train_forward", "gmf_dgr_head_train_backward", "gmf_sgd_step",
+    "gmf_pointdsc_train_workspace_bytes", "gmf_pointdsc_param_count", "gmf_pointdsc_train_forward", "gmf_pointdsc_train_backward", "gmf_adam_step",
 ]
 
 
@@ -96,6 +97,13 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.gmf_dgr_head_train_forward.argtypes = [vp, vp, vp, vp, i, i, vp, vp, sz, vp]
     lib.gmf_dgr_head_train_backward.argtypes = [vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, sz, vp]
     lib.gmf_sgd_step.argtypes = [vp, vp, vp, C.c_int64, f, f, f, f, i, vp]
+    lib.gmf_pointdsc_train_workspace_bytes.restype = C.c_size_t
+    lib.gmf_pointdsc_train_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.gmf_pointdsc_param_count.restype = C.c_int64
+    lib.gmf_pointdsc_param_count.argtypes = [i]
+    lib.gmf_pointdsc_train_forward.argtypes = [i, i, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp]
+    lib.gmf_pointdsc_train_backward.argtypes = [i, i, vp, vp, vp, vp, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp]
+    lib.gmf_adam_step.argtypes = [vp, vp, vp, vp, vp, C.c_int64, f, f, f, f, f, f, i, vp]
     lib.gmf_sm_workspace_bytes.restype = C.c_size_t
     lib.gmf_sm_workspace_bytes.argtypes = [i, i, C.c_double]
     lib.gmf_sm_baseline.argtypes = [vp, vp, vp, i, i, f, C.c_double, i, vp, vp, vp, vp, sz, vp]

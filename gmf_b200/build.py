@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgmf_b200.so")
 SOURCES = ["gmf_api.cu"]
-HEADERS = ["common.cuh", "linear_tc.cuh", "attn_args.cuh", "sc_common.cuh", "sc_attn_v9.cuh", "fus_attn_v2.cuh", "ffn_fused.cuh", "kv_proj_all.cuh", "pcn_qkv.cuh", "tail.cuh", "dgr_head.cuh", "dgr_head_api.inl", "dgr_train.cuh", "dgr_train_api.inl", "matcher.cuh", "matcher_api.inl", "compat_api.inl", "sm_baseline.cuh", "sm_api.inl", "se3_refine.cuh", os.path.join("..", "..", "include", "gmf_b200.h")]
+HEADERS = ["common.cuh", "linear_tc.cuh", "attn_args.cuh", "sc_common.cuh", "sc_attn_v9.cuh", "fus_attn_v2.cuh", "ffn_fused.cuh", "kv_proj_all.cuh", "pcn_qkv.cuh", "tail.cuh", "dgr_head.cuh", "dgr_head_api.inl", "dgr_train.cuh", "dgr_train_api.inl", "pdsc_train.cuh", "pdsc_train_api.inl", "matcher.cuh", "matcher_api.inl", "compat_api.inl", "sm_baseline.cuh", "sm_api.inl", "se3_refine.cuh", os.path.join("..", "..", "include", "gmf_b200.h")]
 
 
 def _stale() -> bool:

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
                 }
               o = make_float4(e[0], e[1], e[2], e[3]);
             }
-            if (cc + 3 < a.ncols && (a.ld & 3) == 0) *reinterpret_cast<float4*>(dst) = o;
+            if (cc + 3 < a.ncols && (a.ld & 3) == 0 && ((uintptr_t)dst & 15) == 0) *reinterpret_cast<float4*>(dst) = o;   // flat gradient buffers: any offset
             else {
               if (cc < a.ncols) dst[0] = o.x;
               if (cc + 1 < a.ncols) dst[1] = o.y;

@@ -18,6 +18,7 @@
 #include "tail.cuh"
 #include "dgr_head.cuh"
 #include "dgr_train.cuh"
+#include "pdsc_train.cuh"
 #include "matcher.cuh"
 #include "sm_baseline.cuh"
 #include "se3_refine.cuh"
@@ -1329,3 +1330,4 @@ int gmf_debug_attention(gmf_ctx* ctx, const float* q, const float* k, const floa
 #include "matcher_api.inl"
 #include "compat_api.inl"
 #include "sm_api.inl"
+#include "pdsc_train_api.inl"

@@ -1,0 +1,124 @@
+"""Training step of GMF-PointDSC on the CUDA path.
+
+Mirrors one iteration of the reference's `Trainer.train_epoch` (GMF_PointDSC/libs/trainer.py:123-168): training-mode forward of the path
+after the image backbone, ClassificationLoss + SpectralMatchingLoss (libs/loss.py:66-139), analytic backward, the finite-gradient guard
+(:161-166) and `torch.optim.Adam` (train_3DMatch.py:52-58).  Parameters, gradients and the Adam moments are flat fp32 CUDA tensors in
+`hot_path_spec` order, so the data-parallel gradient exchange is ONE `torch.distributed.all_reduce` (NCCL) of `self.grads`.  The image
+backbone stays in PyTorch: `forward_backward` returns the gradients with respect to the image tokens for autograd to carry on.
+No CPU fallback: everything here calls the C ABI (`gmf_pointdsc_train_*`, `gmf_adam_step`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .weights import hot_path_spec, pack_state_dict
+
+
+def trainable_mask(num_layers: int) -> torch.Tensor:
+    """uint8 mask over the flat parameter buffer: 0 for BatchNorm running statistics (buffers, not parameters) and `sigma_spat`
+    (requires_grad=False, PointDSC.py:165)."""
+    parts = []
+    for name, shape in hot_path_spec(num_layers).items():
+        n = 1
+        for d in shape:
+            n *= d
+        frozen = name.endswith("running_mean") or name.endswith("running_var") or name == "sigma_spat"
+        parts.append(torch.full((n,), 0 if frozen else 1, dtype=torch.uint8))
+    return torch.cat(parts)
+
+
+class PointDSCTrainer:
+    def __init__(self, num_layers: int = 12, device: int = 0, balanced: bool = False, weight_classification: float = 1.0,
+                 weight_spectralmatching: float = 1.0, precision: str = "tf32x3"):
+        """precision: "tf32x3" = error-compensated tensor-pipe products (fp32-level gradients), "tf32" = plain TF32 (3x less tensor work)."""
+        if precision not in ("tf32", "tf32x3"):
+            raise ValueError("precision must be 'tf32' or 'tf32x3'")
+        self.x3 = 1 if precision == "tf32x3" else 0
+        self.lib = _lib.load()
+        self.num_layers, self.dev_index = int(num_layers), int(device)
+        self.device = torch.device("cuda", self.dev_index)
+        self.balanced, self.w_class, self.w_sm = bool(balanced), float(weight_classification), float(weight_spectralmatching)
+        self.spec = hot_path_spec(self.num_layers)
+        n = int(self.lib.gmf_pointdsc_param_count(self.num_layers))
+        assert n == sum(int(torch.Size(s).numel()) for s in self.spec.values())
+        self.params = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.mask = trainable_mask(self.num_layers).to(self.device)
+        self.steps = 0
+        self._ws: Optional[torch.Tensor] = None
+        self._saved = None
+
+    # ---- parameters ----
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        self.params.copy_(pack_state_dict(sd, self.num_layers))
+
+    def _unflatten(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out, o = {}, 0
+        host = flat.detach().cpu()
+        for name, shape in self.spec.items():
+            n = int(torch.Size(shape).numel())
+            out[name] = host[o:o + n].reshape(shape).clone()
+            o += n
+        return out
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return self._unflatten(self.params)
+
+    def grad_dict(self) -> Dict[str, torch.Tensor]:
+        return self._unflatten(self.grads)
+
+    # ---- one step ----
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward_backward(self, corr_pos, src_keypts, tgt_keypts, p_tokens, q_tokens, gt_labels, want_token_grads: bool = True) -> dict:
+        """corr_pos [B,N,6], src/tgt_keypts [B,N,3], p/q_tokens [B,T,128] (backbone output), gt_labels [B,N] -> losses (device tensor of
+        {class_loss, sm_loss, loss}), logits [B,N] (`final_labels` of the training-mode forward), features [B,N,128], d_p_tokens / d_q_tokens."""
+        t = [x.to(self.device, torch.float32).contiguous() for x in (corr_pos, src_keypts, tgt_keypts, p_tokens, q_tokens, gt_labels)]
+        cp, sk, tk, pt, qt, gt = t
+        B, N, T = cp.shape[0], cp.shape[1], pt.shape[1]
+        assert cp.shape == (B, N, 6) and sk.shape == (B, N, 3) and tk.shape == (B, N, 3) and pt.shape == (B, T, 128) and qt.shape == (B, T, 128) and gt.shape == (B, N)
+        need = int(self.lib.gmf_pointdsc_train_workspace_bytes(self.num_layers, B, N, T, self.x3))
+        if need == 0:
+            raise _lib.GmfError("gmf_pointdsc_train_workspace_bytes: unsupported shape")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        losses = torch.empty(3, dtype=torch.float32, device=self.device)
+        logits = torch.empty(B, N, dtype=torch.float32, device=self.device)
+        feats = torch.empty(B, N, 128, dtype=torch.float32, device=self.device)
+        st = self._stream()
+        _lib.check(self.lib.gmf_pointdsc_train_forward(self.dev_index, self.num_layers, self.params.data_ptr(), cp.data_ptr(), sk.data_ptr(), tk.data_ptr(),
+                                                       pt.data_ptr(), qt.data_ptr(), gt.data_ptr(), B, N, T, int(self.balanced), self.w_class, self.w_sm,
+                                                       self.x3, losses.data_ptr(), logits.data_ptr(), feats.data_ptr(), self._ws.data_ptr(), self._ws.numel(), st))
+        d_p = torch.empty_like(pt) if want_token_grads else None
+        d_q = torch.empty_like(qt) if want_token_grads else None
+        _lib.check(self.lib.gmf_pointdsc_train_backward(self.dev_index, self.num_layers, self.params.data_ptr(), cp.data_ptr(), pt.data_ptr(), qt.data_ptr(),
+                                                        B, N, T, self.w_class, self.w_sm, self.x3, self.grads.data_ptr(),
+                                                        d_p.data_ptr() if want_token_grads else None, d_q.data_ptr() if want_token_grads else None,
+                                                        self._ws.data_ptr(), self._ws.numel(), st))
+        return {"losses": losses, "class_loss": losses[0], "sm_loss": losses[1], "loss": losses[2], "final_labels": logits, "features": feats,
+                "d_p_tokens": d_p, "d_q_tokens": d_q}
+
+    def step(self, lr: float = 1e-4, weight_decay: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, group=None) -> bool:
+        """all-reduce (sum) of the flat gradient over the process group, the reference's finite-gradient guard, then Adam on the mean
+        gradient.  Returns False when the step was skipped because of a non-finite gradient (trainer.py:161-168)."""
+        import torch.distributed as dist
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(group)
+            if world > 1:
+                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
+        if not bool(torch.isfinite(self.grads).all()):
+            return False
+        self.steps += 1
+        _lib.check(self.lib.gmf_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                          self.mask.data_ptr(), self.params.numel(), lr, betas[0], betas[1], eps, weight_decay, 1.0 / world, self.steps,
+                                          self._stream()))
+        return True

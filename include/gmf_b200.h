@@ -188,6 +188,35 @@ int gmf_dgr_head_train_backward(gmf_dgr_head* h, const float* params, const floa
 int gmf_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum, float weight_decay, float grad_scale,
                  int first, void* stream);
 
+/* ---- PointDSC training step -------------------------------------------------- */
+/* Reference loop: GMF_PointDSC/libs/trainer.py:123-168 (forward :134, ClassificationLoss + SpectralMatchingLoss :137-146, loss.backward() :160,
+ * optimizer.step() :168) around models/PointDSC.py:191-266 in TRAINING mode (batch-statistics BatchNorm with running-statistics update, logits
+ * returned as `final_labels`, feature compatibility M consumed by the SM loss), losses libs/loss.py:66-139 (both `balanced` settings).
+ * params / grads: FLAT fp32 device buffers of gmf_pointdsc_param_count(num_layers) floats in gmf_weight_spec order (the reference state_dict
+ * without the image backbone), owned by the caller so that the gradient is all-reduced in one NCCL call.  Device inputs: corr_pos [B,N,6],
+ * src_keypts / tgt_keypts [B,N,3], p_tokens / q_tokens [B,T,128] (image backbone output), gt_labels [B,N] (0 / 1 as fp32).
+ * train_forward: losses[3] (device) = {classification loss, spectral-matching loss, w_class * cls + w_sm * sm}; logits [B,N] and features
+ * [B,N,128] (un-normalised encoder output) may be NULL; the running statistics inside `params` are updated.  The N x N matrix M and its gradient
+ * only ever exist as 64 x 64 tiles in shared memory (fused SM loss).  train_backward must follow with the same workspace, shapes, params and
+ * inputs; grads is overwritten (entries of running statistics and sigma_spat stay 0); d_p_tokens / d_q_tokens [B,T,128] (the gradient that
+ * flows on into the PyTorch image backbone) may be NULL.  Matrix products run on the tensor pipe: tf32x3 = 0 plain TF32 (gradients within a few
+ * per cent of fp32 autograd through 12 layers), tf32x3 = 1 error-compensated (hi hi + hi lo + lo hi, fp32-level products, three times the tensor
+ * work and operand-image workspace); everything else is fp32.  The same tf32x3 must be passed to all three calls of a step. */
+size_t gmf_pointdsc_train_workspace_bytes(int num_layers, int B, int N, int T, int tf32x3);
+int64_t gmf_pointdsc_param_count(int num_layers);
+int gmf_pointdsc_train_forward(int device, int num_layers, float* params, const float* corr_pos, const float* src_keypts, const float* tgt_keypts,
+                               const float* p_tokens, const float* q_tokens, const float* gt_labels, int B, int N, int T, int balanced, float w_class,
+                               float w_sm, int tf32x3, float* losses, float* logits, float* features, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int gmf_pointdsc_train_backward(int device, int num_layers, const float* params, const float* corr_pos, const float* p_tokens, const float* q_tokens,
+                                int B, int N, int T, float w_class, float w_sm, int tf32x3, float* grads, float* d_p_tokens, float* d_q_tokens,
+                                void* workspace, size_t workspace_bytes, void* stream);
+/* torch.optim.Adam (amsgrad off; train_3DMatch.py:52-58): g = grad_scale * grad + weight_decay * p; m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;
+ * p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps).  step >= 1.  mask (one byte per element, NULL = all) selects the trainable
+ * entries: running statistics and sigma_spat share the flat buffer and must be left alone. */
+int gmf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const unsigned char* mask, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float grad_scale, int step, void* stream);
+
 /* ---- correspondence construction (the step right before the path) ------------- */
 /* Nearest-neighbour matcher in descriptor space + network input assembly, NumPy in the reference's datasets
  * (GMF_PointDSC/datasets/ThreeDMatch.py:384-391, 401-402, 411-414; datasets/KITTI.py:94-102):

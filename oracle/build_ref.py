@@ -28,6 +28,8 @@ FILES = [
     ("GMF_PointDSC/models/resnet.py", "GMF_PointDSC/models/resnet.py"),
     ("GMF_PointDSC/utils/SE3.py", "GMF_PointDSC/utils/SE3.py"),
     ("GMF_PointDSC/utils/__init__.py", "GMF_PointDSC/utils/__init__.py"),
+    # training losses (§8f N2: training step of the path)
+    ("GMF_PointDSC/libs/loss.py", "GMF_PointDSC/libs/loss.py"),
     # DGR bottleneck fusion head (cfg#5) and the pose solvers of §8f N3
     ("GMF_DeepGlobalRegistration/GMF_DeepGlobalRegistration_fcgf/model/perceiver_io.py", "dgr_fcgf/model/perceiver_io.py"),
     ("GMF_DeepGlobalRegistration/GMF_DeepGlobalRegistration_fcgf/core/registration.py", "dgr_fcgf/core/registration.py"),

@@ -1,0 +1,201 @@
+"""Training step of the GMF-PointDSC path (reference libs/trainer.py:123-168, libs/loss.py:66-139, models/PointDSC.py in
+training mode).  Checker = torch autograd of the UNMODIFIED reference module + the reference's own loss classes (oracle/train_oracle.py,
+from /root/reference here and oracle/_ref on the GPU box), in float64.  CUDA path: gmf_pointdsc_train_forward / _backward / gmf_adam_step through
+the C ABI; matrix products are TF32 on the tensor pipe, so gradients are held to a fraction of each tensor's own max-norm."""
+import pytest
+import torch
+
+from conftest import record
+from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
+from gmf_b200.weights import hot_path_spec
+from oracle import ref_shim
+from oracle import train_oracle
+
+
+def _cfg(layers, thr=0.1):
+    return dict(num_layers=layers, num_iterations=10, ratio=0.1, inlier_threshold=thr, sigma_d=thr, k=40, nms_radius=thr)
+
+
+def _case(layers, B, N, T, seed):
+    sd = synth_state_dict(hot_path_spec(layers), seed=seed)
+    sd["sigma_spat"] = torch.tensor([0.1])
+    sd["sigma"] = torch.tensor([0.8])
+    data = synth_pairs(B, N, seed=seed + 1, noise=0.01)
+    data["p_tokens"], data["q_tokens"] = synth_tokens(B, T, seed + 2), synth_tokens(B, T, seed + 3)
+    return sd, data
+
+
+@pytest.mark.parametrize("balanced", [False, True])
+def test_loss_head_closed_form_matches_reference_losses(balanced):
+    """The formulas the CUDA loss kernels implement == autograd of the reference's ClassificationLoss / SpectralMatchingLoss on the M of
+    PointDSC.py:231-234."""
+    losses = train_oracle.load_reference_losses()
+    if losses is None:
+        pytest.skip("reference tree / oracle/_ref not present")
+    Cls, Sm = losses
+    g = torch.Generator().manual_seed(5)
+    B, N = 3, 70
+    # correlated features: <fh_i, fh_j> around 0.6, so that M is inside (0, 1) for most pairs and clamped at 0 for some
+    feat = (torch.randn(B, 1, 128, generator=g, dtype=torch.float64) + 0.8 * torch.randn(B, N, 128, generator=g, dtype=torch.float64)).requires_grad_(True)
+    logits = torch.randn(B, N, generator=g, dtype=torch.float64).requires_grad_(True)
+    gt = (torch.rand(B, N, generator=g) < 0.3).double()
+    gt[2] = 0                                                   # a pair without inliers (relu(... - 1) + 1 guards)
+    sigma = torch.tensor(0.8, dtype=torch.float64, requires_grad=True)
+    fh = torch.nn.functional.normalize(feat, p=2, dim=-1)
+    M = torch.clamp(1 - (1 - fh @ fh.transpose(1, 2)) / sigma ** 2, min=0, max=1)
+    M[:, torch.arange(N), torch.arange(N)] = 0
+    cl = Cls(balanced=balanced)(logits.float(), gt.float())["loss"]     # the reference losses are fp32-only (labels cast with .float())
+    sl = Sm(balanced=balanced)(M.float(), gt.float())
+    (0.7 * cl + 1.3 * sl).backward()
+    c_cl, c_sl, dlogit, dfeat, dsigma = train_oracle.loss_head_closed_form(feat.detach(), logits.detach(), gt, sigma.detach(), balanced, 0.7, 1.3)
+    assert abs(float(cl) - float(c_cl)) < 1e-6 and abs(float(sl) - float(c_sl)) < 1e-6
+    assert float((logits.grad - dlogit).abs().max()) < 1e-6 * float(dlogit.abs().max())
+    assert float(dfeat.abs().max()) > 0 and float((feat.grad - dfeat).abs().max()) < 1e-5 * float(dfeat.abs().max())
+    assert abs(float(sigma.grad) - float(dsigma)) < 1e-5 * abs(float(dsigma))
+
+
+def test_trainable_mask_freezes_buffers():
+    from gmf_b200.trainer import trainable_mask
+    spec = hot_path_spec(2)
+    mask = trainable_mask(2)
+    assert mask.numel() == sum(int(torch.Size(s).numel()) for s in spec.values())
+    o = 0
+    for name, shape in spec.items():
+        n = int(torch.Size(shape).numel())
+        frozen = name.endswith("running_mean") or name.endswith("running_var") or name == "sigma_spat"
+        assert int(mask[o:o + n].sum()) == (0 if frozen else n), name
+        o += n
+    assert int(mask[0]) == 1                                    # sigma is learnable (PointDSC.py:164)
+
+
+def test_reference_training_step_runs_in_training_mode():
+    """the oracle itself: training-mode forward of the unmodified reference returns M and logits, and every hot-path parameter except
+    sigma_spat receives a gradient"""
+    if not ref_shim.available() or train_oracle.load_reference_losses() is None:
+        pytest.skip("reference tree / oracle/_ref not present")
+    sd, data = _case(1, 2, 64, 40, 3)
+    torch.set_num_threads(4)
+    r = train_oracle.reference_training_step(sd, _cfg(1), data, dtype=torch.float32)
+    assert r["loss"] > 0 and r["logits"].shape == (2, 64)
+    for k, g in r["grads"].items():
+        if k.startswith("encoder.image_encoder."):
+            continue
+        if k == "sigma_spat":
+            assert g is None
+        else:
+            assert g is not None and torch.isfinite(g).all(), k
+
+
+def _compare(layers, B, N, T, balanced, seed, tol_grad, tol_logit, precision="tf32x3", tol_loss=2e-4, with_ref32=False):
+    from gmf_b200.trainer import PointDSCTrainer
+    if not ref_shim.available() or train_oracle.load_reference_losses() is None:
+        pytest.skip("reference tree / oracle/_ref not present")
+    sd, data = _case(layers, B, N, T, seed)
+    torch.set_num_threads(8)
+    ref = train_oracle.reference_training_step(sd, _cfg(layers), data, balanced=balanced)
+    tr = PointDSCTrainer(layers, 0, balanced=balanced, precision=precision)
+    tr.load_state_dict(sd)
+    out = tr.forward_backward(data["corr_pos"], data["src_keypts"], data["tgt_keypts"], data["p_tokens"], data["q_tokens"], data["gt_labels"])
+    torch.cuda.synchronize()
+    losses = out["losses"].cpu()
+    le = float((out["final_labels"].cpu().double() - ref["logits"]).abs().max())
+    grads = tr.grad_dict()
+    worst = ("", 0.0)
+    for k, gref in ref["grads"].items():
+        if k.startswith("encoder.image_encoder.") or gref is None:
+            continue
+        # denominators floored at 1e-3 (weight gradients are 1e-3 .. 1e-1 here): the biases in front of a BatchNorm (and projection_v.bias) have an exactly zero gradient
+        rel = float((grads[k].double().reshape(gref.shape) - gref).abs().max() / gref.abs().max().clamp_min(1e-3))
+        if rel > worst[1]:
+            worst = (k, rel)
+    rp = float((out["d_p_tokens"].cpu().double() - ref["d_p_tokens"]).abs().max() / ref["d_p_tokens"].abs().max())
+    rq = float((out["d_q_tokens"].cpu().double() - ref["d_q_tokens"]).abs().max() / ref["d_q_tokens"].abs().max())
+    new = tr.state_dict()
+    rs = max(float((new[k].double() - ref["state"][k]).abs().max()) for k in new if k.endswith("running_mean") or k.endswith("running_var"))
+    extra = {}
+    if with_ref32:      # how far the reference itself moves between float32 and float64 (conditioning of the case)
+        r32 = train_oracle.reference_training_step(sd, _cfg(layers), data, balanced=balanced, dtype=torch.float32)
+        extra["ref_fp32_vs_fp64_logit_max_abs"] = float((r32["logits"].double() - ref["logits"]).abs().max())
+        extra["ref_fp32_vs_fp64_worst_weight_grad_rel"] = max(
+            float((r32["grads"][k].double() - g).abs().max() / g.abs().max().clamp_min(1e-3)) for k, g in ref["grads"].items()
+            if g is not None and not k.startswith("encoder.image_encoder."))
+    record(f"pdsc_train_{precision}_l{layers}_b{B}_n{N}_t{T}_bal{int(balanced)}", **extra, class_loss=float(losses[0]), class_loss_ref=ref["class_loss"], sm_loss=float(losses[1]),
+           sm_loss_ref=ref["sm_loss"], logit_max_abs_err=le, worst_weight_grad=worst[0], worst_weight_grad_rel=worst[1], d_p_tokens_rel=rp,
+           d_q_tokens_rel=rq, running_stat_max_abs_err=rs)
+    assert abs(float(losses[0]) - ref["class_loss"]) < tol_loss * max(1.0, abs(ref["class_loss"]))
+    assert abs(float(losses[1]) - ref["sm_loss"]) < tol_loss * max(1.0, abs(ref["sm_loss"]))
+    assert abs(float(losses[2]) - ref["loss"]) < 2 * tol_loss * max(1.0, abs(ref["loss"]))
+    assert le < tol_logit, le
+    assert grads["sigma_spat"].abs().max() == 0
+    assert worst[1] < tol_grad, worst
+    assert rp < tol_grad and rq < tol_grad, (rp, rq)
+    assert rs < max(1e-3, 10 * tol_loss), rs
+    return tr, grads
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("balanced", [False, True])
+def test_cuda_training_step_matches_reference_autograd_2_layers(balanced):
+    _compare(2, 2, 256, 300, balanced, 21, tol_grad=1e-2, tol_logit=1e-3)
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_plain_tf32():
+    """precision="tf32": single-pass TF32 products; the budget is what TF32 rounding does to a 2-layer trunk with BatchNorm"""
+    _compare(2, 2, 256, 300, False, 21, tol_grad=1.5e-1, tol_logit=5e-2, precision="tf32", tol_loss=5e-3)
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_ragged_sizes():
+    """N, T not multiples of 4 / 64 / 128: scalar operand paths, padded SM-loss tiles, sequence ends of the position encoding"""
+    _compare(1, 3, 131, 77, False, 33, tol_grad=1e-2, tol_logit=1e-3)
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_4_layers():
+    """deepest case in which the float32 reference still agrees with the float64 one to 5e-5 (logits) / 4e-3 (gradients)"""
+    _compare(4, 2, 200, 150, False, 45, tol_grad=3e-2, tol_logit=2e-3, tol_loss=5e-4, with_ref32=True)
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_12_layers_and_adam():
+    # At 12 layers the training-mode network with random weights is chaotic in single precision: the UNMODIFIED reference run in float32 differs
+    # from itself in float64 by 0.28 in the logits and by several hundred per cent in some weight gradients (batch-statistics BatchNorm of the
+    # nearly constant attention messages amplifies rounding noise ~3x per layer; measured in DESIGN.md §8).  Element-wise gradient parity is
+    # therefore asserted at 1 / 2 / 4 layers (same per-layer code); here the losses are held to the reference and both deviations are recorded.
+    tr, grads = _compare(12, 2, 200, 150, False, 45, tol_grad=float("inf"), tol_logit=float("inf"), tol_loss=2e-2, with_ref32=True)
+    assert all(bool(torch.isfinite(g).all()) for g in grads.values())
+    # Adam (lr 1e-4, weight_decay 1e-6: config_3DMatch.py:61-62) == torch.optim.Adam on the same gradients; frozen entries untouched
+    before = tr.state_dict()
+    names = [k for k in before if not (k.endswith("running_mean") or k.endswith("running_var") or k == "sigma_spat")]
+    params = [torch.nn.Parameter(before[k].clone()) for k in names]
+    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-6)
+    for _ in range(2):
+        for p_, k in zip(params, names):
+            p_.grad = grads[k].clone()
+        opt.step()
+        assert tr.step(lr=1e-4, weight_decay=1e-6)
+    after = tr.state_dict()
+    for p_, k in zip(params, names):
+        assert torch.allclose(after[k], p_.detach(), atol=2e-7, rtol=1e-5), k
+    for k in before:
+        if k not in names:
+            assert torch.equal(after[k], before[k]), k
+    tr.grads[5] = float("nan")                                  # the reference's finite-gradient guard (trainer.py:161-166)
+    assert tr.step() is False
+
+
+@pytest.mark.gpu
+def test_cuda_training_error_paths():
+    from gmf_b200 import _lib
+    lib = _lib.load()
+    assert lib.gmf_pointdsc_train_workspace_bytes(0, 2, 100, 100, 1) == 0
+    assert lib.gmf_pointdsc_train_workspace_bytes(2, 2, 1, 100, 1) == 0
+    assert lib.gmf_pointdsc_train_workspace_bytes(2, 2, 100, 100, 1) > lib.gmf_pointdsc_train_workspace_bytes(2, 2, 100, 100, 0) > 0
+    assert lib.gmf_pointdsc_param_count(0) == 0
+    ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    z = torch.zeros(16, device="cuda")
+    assert lib.gmf_pointdsc_train_forward(0, 2, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 2, 100, 100, 0,
+                                          1.0, 1.0, 1, z.data_ptr(), None, None, ws.data_ptr(), ws.numel(), None) == -3   # workspace too small
+    assert b"workspace too small" in lib.gmf_last_error()
+    assert lib.gmf_adam_step(None, None, None, None, None, 0, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1.0, 1, None) == -1
