@@ -101,8 +101,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.gmf_pointdsc_train_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.gmf_pointdsc_param_count.restype = C.c_int64
     lib.gmf_pointdsc_param_count.argtypes = [i]
-    lib.gmf_pointdsc_train_forward.argtypes = [i, i, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp]
-    lib.gmf_pointdsc_train_backward.argtypes = [i, i, vp, vp, vp, vp, i, i, i, f, f, i, vp, vp, vp, vp, sz, vp]
+    lib.gmf_pointdsc_train_forward.argtypes = [i, i, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, i, vp, vp, vp, vp, vp, sz, vp]
+    lib.gmf_pointdsc_train_backward.argtypes = [i, i, vp, vp, vp, vp, i, i, i, f, f, i, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.gmf_adam_step.argtypes = [vp, vp, vp, vp, vp, C.c_int64, f, f, f, f, f, f, i, vp]
     lib.gmf_sm_workspace_bytes.restype = C.c_size_t
     lib.gmf_sm_workspace_bytes.argtypes = [i, i, C.c_double]

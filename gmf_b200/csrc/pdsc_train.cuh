@@ -436,6 +436,42 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, float w_cla
   if (dsigma) dsigma[0] = (float)(w_sm * acc[1]);
 }
 
+// Training-mode output M of PointDSC.forward (PointDSC.py:231-234) from S = fh fh^T, in place: clamp(1 - (1 - S) / sigma^2, 0, 1), zero diagonal
+__global__ void m_from_s_kernel(float* __restrict__ S, int N, long long n, const float* __restrict__ sigma) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long e = i % ((long long)N * N);
+  const int r = (int)(e / N), c = (int)(e % N);
+  const float sg = sigma[0];
+  S[i] = r == c ? 0.f : fminf(fmaxf(1.0f - (1.0f - S[i]) / (sg * sg), 0.f), 1.0f);
+}
+// autograd entry (d loss / d M given by the caller): S -> G = d loss / d S in place (clamp pass-through inside [0, 1], zero diagonal);
+// acc[0] += d loss / d sigma (double)
+__global__ void __launch_bounds__(256) ds_from_dm_kernel(float* __restrict__ S, const float* __restrict__ dM, int N, long long n, const float* __restrict__ sigma,
+                                                         double* __restrict__ acc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float sg = sigma[0], is2 = 1.0f / (sg * sg);
+  float ds = 0.f;
+  if (i < n) {
+    const long long e = i % ((long long)N * N);
+    const int r = (int)(e / N), c = (int)(e % N);
+    const float s = S[i], pre = 1.0f - (1.0f - s) * is2;
+    float g = 0.f;
+    if (r != c && pre >= 0.f && pre <= 1.0f) { g = dM[i] * is2; ds = dM[i] * 2.0f * (1.0f - s) * is2 / sg; }
+    S[i] = g;
+  }
+  __shared__ float red[8];
+  ds = warp_sum(ds);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    if (t != 0.f) atomicAdd(acc, (double)t);
+  }
+}
+__global__ void store_double_as_float_kernel(const double* __restrict__ src, float* __restrict__ dst) { dst[0] = (float)src[0]; }
+
 // torch.optim.Adam (amsgrad False): g = grad_scale * grad + weight_decay * p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)          (train_3DMatch.py:52-58: lr 1e-4, weight_decay 1e-6)
 __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,

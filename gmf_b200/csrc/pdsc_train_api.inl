@@ -239,8 +239,10 @@ int64_t gmf_pointdsc_param_count(int num_layers) { return num_layers < 1 ? 0 : (
 
 int gmf_pointdsc_train_forward(int device, int num_layers, float* params, const float* corr_pos, const float* src_keypts, const float* tgt_keypts,
                                const float* p_tokens, const float* q_tokens, const float* gt_labels, int B, int N, int T, int balanced, float w_class,
-                               float w_sm, int tf32x3, float* losses, float* logits, float* features, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!params || !corr_pos || !src_keypts || !tgt_keypts || !p_tokens || !q_tokens || !gt_labels || !losses) return fail(GMF_ERR_INVALID, "NULL argument");
+                               float w_sm, int tf32x3, float* losses, float* logits, float* features, float* M, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (!params || !corr_pos || !src_keypts || !tgt_keypts || !p_tokens || !q_tokens) return fail(GMF_ERR_INVALID, "NULL argument");
+  if ((gt_labels == nullptr) != (losses == nullptr)) return fail(GMF_ERR_INVALID, "gt_labels and losses go together (both NULL: no loss head, gradients come from the caller)");
   TRY(pt_check(num_layers, B, N, T));
   CU(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -281,17 +283,21 @@ int gmf_pointdsc_train_forward(int device, int num_layers, float* params, const 
   TRY(lin_fwd(w, w.c1, 32, R, 32, p + o.at("classification.2.weight"), 32, p + o.at("classification.2.bias"), w.c2, 32, nullptr, st));
   relu_inplace_kernel<<<nblk((long long)R * 32), 256, 0, st>>>(w.c2, (long long)R * 32); LAUNCHED();
   TRY(lin_fwd(w, w.c2, 32, R, 32, p + o.at("classification.4.weight"), 1, p + o.at("classification.4.bias"), w.logit, 1, nullptr, st));
-  CU(cudaMemsetAsync(w.cnt, 0, (B + 1) * sizeof(double), st));
   CU(cudaMemsetAsync(w.acc, 0, 4 * sizeof(double), st));
-  label_count_kernel<<<B, 256, 0, st>>>(gt_labels, B, N, w.cnt); LAUNCHED();
-  bce_kernel<<<nblk(R), 256, 0, st>>>(w.logit, gt_labels, R, balanced, w.cnt + B, w_class, w.acc + 2, w.dlogit); LAUNCHED();
-  {
+  if (gt_labels) {
+    CU(cudaMemsetAsync(w.cnt, 0, (B + 1) * sizeof(double), st));
+    label_count_kernel<<<B, 256, 0, st>>>(gt_labels, B, N, w.cnt); LAUNCHED();
+    bce_kernel<<<nblk(R), 256, 0, st>>>(w.logit, gt_labels, R, balanced, w.cnt + B, w_class, w.acc + 2, w.dlogit); LAUNCHED();
     static std::atomic<unsigned long long> configured{0};
     if (cudaError_t e = ensure_dyn_smem(sm_loss_fused_kernel, kSmlSmem, configured)) return fail_cuda(e, "sm_loss_fused_kernel attribute");
     sm_loss_fused_kernel<<<dim3(Np / 64, B), 256, kSmlSmem, st>>>(w.fh, w.fhT, gt_labels, B, N, Np, p + o.at("sigma"), balanced, w.cnt, w_sm, w.acc, w.dfh);
     LAUNCHED();
+    loss_finalize_kernel<<<1, 1, 0, st>>>(w.acc, w_class, w_sm, losses, nullptr); LAUNCHED();
   }
-  loss_finalize_kernel<<<1, 1, 0, st>>>(w.acc, w_class, w_sm, losses, nullptr); LAUNCHED();
+  if (M) {      // the materialised training-mode output, for callers that compute their own loss on it (the reference's trainer does)
+    TRY(pgemm(w, w.fh, 128, (size_t)N * 128, N, 128, 0, w.fh, 128, (size_t)N * 128, N, 0, M, N, (size_t)N * N, 1.f, nullptr, nullptr, B, st));
+    m_from_s_kernel<<<nblk((long long)B * N * N), 256, 0, st>>>(M, N, (long long)B * N * N, p + o.at("sigma")); LAUNCHED();
+  }
   if (logits) CU(cudaMemcpyAsync(logits, w.logit, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
   if (features) CU(cudaMemcpyAsync(features, fin, (size_t)R * 128 * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -300,8 +306,8 @@ int gmf_pointdsc_train_forward(int device, int num_layers, float* params, const 
 // Uses what gmf_pointdsc_train_forward left in `workspace` (same shapes, params and inputs).  grads (gmf_pointdsc_param_count floats) is
 // overwritten; d_p_tokens / d_q_tokens [B, T, 128] (gradients flowing on into the image backbone) may be NULL.
 int gmf_pointdsc_train_backward(int device, int num_layers, const float* params, const float* corr_pos, const float* p_tokens, const float* q_tokens, int B, int N,
-                                int T, float w_class, float w_sm, int tf32x3, float* grads, float* d_p_tokens, float* d_q_tokens, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                int T, float w_class, float w_sm, int tf32x3, const float* d_logits, const float* d_M, const float* d_features, float* grads,
+                                float* d_p_tokens, float* d_q_tokens, void* workspace, size_t workspace_bytes, void* stream) {
   if (!params || !corr_pos || !p_tokens || !q_tokens || !grads) return fail(GMF_ERR_INVALID, "NULL argument");
   TRY(pt_check(num_layers, B, N, T));
   CU(cudaSetDevice(device));
@@ -314,8 +320,28 @@ int gmf_pointdsc_train_backward(int device, int num_layers, const float* params,
   const int R = B * N, RT = B * T;
   CU(cudaMemsetAsync(G, 0, o.total * sizeof(float), st));
   CU(cudaMemsetAsync(w.dimg, 0, (size_t)RT * 128 * sizeof(float), st));
-  loss_finalize_kernel<<<1, 1, 0, st>>>(w.acc, w_class, w_sm, nullptr, G + o.at("sigma")); LAUNCHED();
   const float* feat = w.blk[num_layers - 1].out;
+  const bool external = d_logits || d_M || d_features;
+  if (!external) {
+    loss_finalize_kernel<<<1, 1, 0, st>>>(w.acc, w_class, w_sm, nullptr, G + o.at("sigma")); LAUNCHED();      // fused loss head of the forward
+  } else {
+    // autograd entry: d loss / d logits [B,N], d loss / d M [B,N,N], d loss / d features [B,N,128] come from the caller (any may be NULL)
+    if (d_logits) CU(cudaMemcpyAsync(w.dlogit, d_logits, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+    else CU(cudaMemsetAsync(w.dlogit, 0, (size_t)R * 4, st));
+    if (d_M) {
+      const size_t sp = (size_t)N * N, sf = (size_t)N * 128;
+      const long long nn = (long long)B * N * N;
+      CU(cudaMemsetAsync(w.acc + 3, 0, sizeof(double), st));
+      TRY(pgemm(w, w.fh, 128, sf, N, 128, 0, w.fh, 128, sf, N, 0, w.dP, N, sp, 1.f, nullptr, nullptr, B, st));                     // S = fh fh^T again
+      ds_from_dm_kernel<<<nblk(nn), 256, 0, st>>>(w.dP, d_M, N, nn, p + o.at("sigma"), w.acc + 3); LAUNCHED();
+      store_double_as_float_kernel<<<1, 1, 0, st>>>(w.acc + 3, G + o.at("sigma")); LAUNCHED();
+      TRY(pgemm(w, w.dP, N, sp, N, N, 0, w.fh, 128, sf, 128, 1, w.dfh, 128, sf, 1.f, nullptr, nullptr, B, st));                    // G fh
+      TRY(pgemm(w, w.dP, N, sp, N, N, 1, w.fh, 128, sf, 128, 1, w.dmsg, 128, sf, 1.f, nullptr, nullptr, B, st));                   // G^T fh
+      add_inplace_kernel<<<nblk((long long)R * 128), 256, 0, st>>>(w.dfh, w.dmsg, (long long)R * 128); LAUNCHED();
+    } else {
+      CU(cudaMemsetAsync(w.dfh, 0, (size_t)R * 128 * 4, st));
+    }
+  }
   // classifier 128-32-32-1 (PointDSC.py:175-181)
   TRY(lin_bwd(w, w.dlogit, 1, R, 1, w.c2, 32, 32, p + o.at("classification.4.weight"), w.dc2, nullptr, G + o.at("classification.4.weight"), G + o.at("classification.4.bias"), st));
   relu_bwd_kernel<<<nblk((long long)R * 32), 256, 0, st>>>(w.dc2, w.c2, (long long)R * 32); LAUNCHED();
@@ -323,6 +349,7 @@ int gmf_pointdsc_train_backward(int device, int num_layers, const float* params,
   relu_bwd_kernel<<<nblk((long long)R * 32), 256, 0, st>>>(w.dc1, w.c1, (long long)R * 32); LAUNCHED();
   TRY(lin_bwd(w, w.dc1, 32, R, 32, feat, 128, 128, p + o.at("classification.0.weight"), w.dA, nullptr, G + o.at("classification.0.weight"), G + o.at("classification.0.bias"), st));
   normalize_bwd_kernel<<<cdiv(R, 8), 256, 0, st>>>(w.dfh, w.fh, w.inv, R, w.dA, 1); LAUNCHED();
+  if (d_features) { add_inplace_kernel<<<nblk((long long)R * 128), 256, 0, st>>>(w.dA, d_features, (long long)R * 128); LAUNCHED(); }
   float *dcur = w.dA, *dnext = w.dB;
   for (int i = num_layers - 1; i >= 0; --i) {
     const BlkP bo = blk_offsets(o, i);

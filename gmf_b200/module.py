@@ -111,8 +111,13 @@ class _NonLocalNet(nn.Module):                     # PointDSC.py:77-112
 
 
 class PointDSC(nn.Module):
-    """B200-native GMF-PointDSC.  Inference (eval-mode BatchNorm) only; `data` without the 'testing' key returns the
-    training-mode outputs (logits as final_labels and the feature-similarity matrix M) but no gradients."""
+    """B200-native GMF-PointDSC.  `.eval()`: the inference path (eval-mode BatchNorm; `data` without the 'testing' key returns logits as
+    final_labels and the feature-similarity matrix M, no gradients).  `.train()`: the training-mode forward of the reference (batch-statistics
+    BatchNorm, running statistics updated, logits and M with autograd history), so that the reference's trainer - losses in Python,
+    `loss.backward()`, any torch optimiser (libs/trainer.py:134-168) - runs unchanged; forward and backward are the CUDA training step of
+    gmf_b200/trainer.py (`train_precision`: "tf32x3" or "tf32")."""
+
+    train_precision = "tf32x3"
 
     def __init__(self, in_dim=6, num_layers=6, num_channels=128, num_iterations=10, ratio=0.1, inlier_threshold=0.10,
                  sigma_d=0.10, k=40, nms_radius=0.10):
@@ -180,10 +185,40 @@ class PointDSC(nn.Module):
         g = self.backbone_mode == "bf16_graph"
         return enc.tokens_fast(p_image, g), enc.tokens_fast(q_image, g)
 
-    @torch.no_grad()
+    def _forward_train(self, data):
+        """PointDSC.forward in training mode (PointDSC.py:207-266 with self.training): `final_labels` = logits and `M` carry autograd history
+        back to the hot-path parameters and, through the image tokens, to the PyTorch backbone; `final_trans` (top-`ratio` seeds without NMS,
+        no post-refinement, :246,253) is computed without gradient, as in the reference where the hypothesis selection is not differentiable
+        with respect to anything the default losses use (weight_transformation = 0, config_3DMatch.py:52)."""
+        from .trainer import TrainState, train_forward
+        if "testing" in data.keys():
+            raise RuntimeError("'testing' data with a module in training mode: call .eval() first (the reference asserts bs == 1 there)")
+        corr_pos, src, tgt = data["corr_pos"], data["src_keypts"], data["tgt_keypts"]
+        eng = self.engine()
+        st = getattr(self, "_train_state", None)
+        if st is None or st.x3 != (1 if self.train_precision == "tf32x3" else 0):
+            st = self._train_state = TrainState(self.num_layers, self.train_precision)
+        with torch.cuda.device(corr_pos.device):
+            enc = self.encoder.image_encoder
+            p_tok, q_tok = enc.tokens(data["p_image"]), enc.tokens(data["q_image"])     # with autograd: the backbone trains too
+            logits, M, feats = train_forward(st, corr_pos, src, tgt, p_tok, q_tok, self.state_dict(keep_vars=True))
+            for m in self.modules():               # nn.BatchNorm1d bookkeeping of a training-mode forward (the hot-path BatchNorms ran in CUDA)
+                if isinstance(m, nn.BatchNorm1d) and m.num_batches_tracked is not None:
+                    m.num_batches_tracked += 1
+            with torch.no_grad():
+                normed = torch.nn.functional.normalize(feats, p=2, dim=-1)
+                seeds = eng.pick_seeds(src, logits.detach(), use_nms=False)
+                seed_trans = eng.seed_hypotheses(normed, src, tgt, seeds)[0]
+                final_trans = eng.score_hypotheses(seed_trans, src, tgt, refine=False)[0]
+        return {"final_trans": final_trans, "final_labels": logits, "M": M}
+
     def forward(self, data):
         if self.training:
-            raise RuntimeError("gmf_b200.PointDSC implements the eval-mode (inference) forward only")
+            return self._forward_train(data)
+        with torch.no_grad():
+            return self._forward_eval(data)
+
+    def _forward_eval(self, data):
         testing = "testing" in data.keys()
         corr_pos, src, tgt = data["corr_pos"], data["src_keypts"], data["tgt_keypts"]
         eng = self.engine()

@@ -96,11 +96,12 @@ class PointDSCTrainer:
         st = self._stream()
         _lib.check(self.lib.gmf_pointdsc_train_forward(self.dev_index, self.num_layers, self.params.data_ptr(), cp.data_ptr(), sk.data_ptr(), tk.data_ptr(),
                                                        pt.data_ptr(), qt.data_ptr(), gt.data_ptr(), B, N, T, int(self.balanced), self.w_class, self.w_sm,
-                                                       self.x3, losses.data_ptr(), logits.data_ptr(), feats.data_ptr(), self._ws.data_ptr(), self._ws.numel(), st))
+                                                       self.x3, losses.data_ptr(), logits.data_ptr(), feats.data_ptr(), None, self._ws.data_ptr(), self._ws.numel(),
+                                                       st))
         d_p = torch.empty_like(pt) if want_token_grads else None
         d_q = torch.empty_like(qt) if want_token_grads else None
         _lib.check(self.lib.gmf_pointdsc_train_backward(self.dev_index, self.num_layers, self.params.data_ptr(), cp.data_ptr(), pt.data_ptr(), qt.data_ptr(),
-                                                        B, N, T, self.w_class, self.w_sm, self.x3, self.grads.data_ptr(),
+                                                        B, N, T, self.w_class, self.w_sm, self.x3, None, None, None, self.grads.data_ptr(),
                                                         d_p.data_ptr() if want_token_grads else None, d_q.data_ptr() if want_token_grads else None,
                                                         self._ws.data_ptr(), self._ws.numel(), st))
         return {"losses": losses, "class_loss": losses[0], "sm_loss": losses[1], "loss": losses[2], "final_labels": logits, "features": feats,
@@ -122,3 +123,81 @@ class PointDSCTrainer:
                                           self.mask.data_ptr(), self.params.numel(), lr, betas[0], betas[1], eps, weight_decay, 1.0 / world, self.steps,
                                           self._stream()))
         return True
+
+
+class _TrainForward(torch.autograd.Function):
+    """Autograd node of the training-mode path: (image tokens, hot-path parameters) -> (logits, M, features).  Used by
+    `gmf_b200.PointDSC.forward` in training mode, so that the reference's own trainer (losses in Python on `final_labels` / `M`,
+    `loss.backward()`, any torch optimiser; libs/trainer.py:134-168) runs unchanged on the CUDA path."""
+
+    @staticmethod
+    def forward(ctx, st: "TrainState", corr_pos, src, tgt, p_tok, q_tok, *params):
+        lib, dev = st.lib, corr_pos.device
+        B, N, T = corr_pos.shape[0], corr_pos.shape[1], p_tok.shape[1]
+        flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+        need = int(lib.gmf_pointdsc_train_workspace_bytes(st.num_layers, B, N, T, st.x3))
+        if need == 0:
+            raise _lib.GmfError("gmf_pointdsc_train_workspace_bytes: unsupported shape")
+        if st.ws is None or st.ws.numel() < need or st.ws.device != dev:
+            st.ws = None
+            st.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        cp, sk, tk, pt, qt = (x.detach().float().contiguous() for x in (corr_pos, src, tgt, p_tok, q_tok))
+        logits = torch.empty(B, N, device=dev)
+        feats = torch.empty(B, N, 128, device=dev)
+        M = torch.empty(B, N, N, device=dev)
+        s_ = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.gmf_pointdsc_train_forward(dev.index or 0, st.num_layers, flat.data_ptr(), cp.data_ptr(), sk.data_ptr(), tk.data_ptr(), pt.data_ptr(),
+                                                  qt.data_ptr(), None, B, N, T, 0, 1.0, 1.0, st.x3, None, logits.data_ptr(), feats.data_ptr(), M.data_ptr(),
+                                                  st.ws.data_ptr(), st.ws.numel(), s_))
+        # BatchNorm running statistics were updated inside `flat`: write them back into the module's buffers
+        o = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                if getattr(p, "_gmf_running_stat", False):
+                    p.copy_(flat[o:o + n].reshape(p.shape))
+                o += n
+        ctx.st, ctx.flat, ctx.inputs, ctx.shapes = st, flat, (cp, pt, qt), [p.shape for p in params]
+        ctx.dims = (B, N, T)
+        return logits, M, feats
+
+    @staticmethod
+    def backward(ctx, d_logits, d_M, d_feats):
+        st, (cp, pt, qt), (B, N, T) = ctx.st, ctx.inputs, ctx.dims
+        dev = cp.device
+        grads = torch.empty_like(ctx.flat)
+        d_p, d_q = torch.empty_like(pt), torch.empty_like(qt)
+        ptr = lambda t: None if t is None else t.contiguous().float().data_ptr()
+        keep = [None if t is None else t.contiguous().float() for t in (d_logits, d_M, d_feats)]
+        if all(t is None for t in keep):
+            keep[0] = torch.zeros(B, N, device=dev)
+        s_ = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(st.lib.gmf_pointdsc_train_backward(dev.index or 0, st.num_layers, ctx.flat.data_ptr(), cp.data_ptr(), pt.data_ptr(), qt.data_ptr(), B, N, T,
+                                                      1.0, 1.0, st.x3, *(None if t is None else t.data_ptr() for t in keep), grads.data_ptr(), d_p.data_ptr(),
+                                                      d_q.data_ptr(), st.ws.data_ptr(), st.ws.numel(), s_))
+        out, o = [], 0
+        for shp in ctx.shapes:
+            n = int(torch.Size(shp).numel())
+            out.append(grads[o:o + n].reshape(shp))
+            o += n
+        return (None, None, None, None, d_p, d_q, *out)
+
+
+class TrainState:
+    """per-module state of the training-mode path (library handle, workspace, precision)"""
+
+    def __init__(self, num_layers: int, precision: str = "tf32x3"):
+        if precision not in ("tf32", "tf32x3"):
+            raise ValueError("precision must be 'tf32' or 'tf32x3'")
+        self.lib = _lib.load()
+        self.num_layers, self.x3, self.ws = int(num_layers), 1 if precision == "tf32x3" else 0, None
+
+
+def train_forward(st: TrainState, corr_pos, src, tgt, p_tok, q_tok, named_tensors: Dict[str, torch.Tensor]):
+    """named_tensors: the module's state (parameters and buffers, keep_vars=True).  Returns logits, M, features with autograd history."""
+    params = []
+    for name in hot_path_spec(st.num_layers):
+        t = named_tensors[name]
+        t._gmf_running_stat = name.endswith("running_mean") or name.endswith("running_var")
+        params.append(t)
+    return _TrainForward.apply(st, corr_pos, src, tgt, p_tok, q_tok, *params)

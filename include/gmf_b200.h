@@ -201,16 +201,20 @@ int gmf_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t
  * inputs; grads is overwritten (entries of running statistics and sigma_spat stay 0); d_p_tokens / d_q_tokens [B,T,128] (the gradient that
  * flows on into the PyTorch image backbone) may be NULL.  Matrix products run on the tensor pipe: tf32x3 = 0 plain TF32 (gradients within a few
  * per cent of fp32 autograd through 12 layers), tf32x3 = 1 error-compensated (hi hi + hi lo + lo hi, fp32-level products, three times the tensor
- * work and operand-image workspace); everything else is fp32.  The same tf32x3 must be passed to all three calls of a step. */
+ * work and operand-image workspace); everything else is fp32.  The same tf32x3 must be passed to all three calls of a step.
+ * Autograd entry (the reference's own trainer computes its losses in Python on `final_labels` and `M`): train_forward with gt_labels = losses =
+ * NULL skips the fused loss head and can write the materialised M [B,N,N] (`M`, may be NULL otherwise too); train_backward then takes the
+ * caller's d_logits [B,N] / d_M [B,N,N] / d_features [B,N,128] (any of them NULL = zero; all three NULL = use the fused loss head). */
 size_t gmf_pointdsc_train_workspace_bytes(int num_layers, int B, int N, int T, int tf32x3);
 int64_t gmf_pointdsc_param_count(int num_layers);
 int gmf_pointdsc_train_forward(int device, int num_layers, float* params, const float* corr_pos, const float* src_keypts, const float* tgt_keypts,
                                const float* p_tokens, const float* q_tokens, const float* gt_labels, int B, int N, int T, int balanced, float w_class,
-                               float w_sm, int tf32x3, float* losses, float* logits, float* features, void* workspace, size_t workspace_bytes,
-                               void* stream);
+                               float w_sm, int tf32x3, float* losses, float* logits, float* features, float* M, void* workspace,
+                               size_t workspace_bytes, void* stream);
 int gmf_pointdsc_train_backward(int device, int num_layers, const float* params, const float* corr_pos, const float* p_tokens, const float* q_tokens,
-                                int B, int N, int T, float w_class, float w_sm, int tf32x3, float* grads, float* d_p_tokens, float* d_q_tokens,
-                                void* workspace, size_t workspace_bytes, void* stream);
+                                int B, int N, int T, float w_class, float w_sm, int tf32x3, const float* d_logits, const float* d_M,
+                                const float* d_features, float* grads, float* d_p_tokens, float* d_q_tokens, void* workspace,
+                                size_t workspace_bytes, void* stream);
 /* torch.optim.Adam (amsgrad off; train_3DMatch.py:52-58): g = grad_scale * grad + weight_decay * p; m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;
  * p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps).  step >= 1.  mask (one byte per element, NULL = all) selects the trainable
  * entries: running statistics and sigma_spat share the flat buffer and must be left alone. */

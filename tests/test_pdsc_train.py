@@ -186,6 +186,73 @@ def test_cuda_training_step_12_layers_and_adam():
 
 
 @pytest.mark.gpu
+def test_module_in_training_mode_runs_the_reference_trainer_step():
+    """Drop-in use: `gmf_b200.PointDSC(...).train()` under the reference's own training iteration (libs/trainer.py:134-168: forward, the
+    reference loss classes in Python on `final_labels` / `M`, loss.backward(), torch.optim.Adam) against the unmodified reference module doing
+    the same.  The image backbone is bypassed on both sides (tokens in, token gradients out)."""
+    import gmf_b200
+    losses = train_oracle.load_reference_losses()
+    if not ref_shim.available() or losses is None:
+        pytest.skip("reference tree / oracle/_ref not present")
+    Cls, Sm = losses
+    layers, B, N, T = 2, 2, 256, 300
+    sd, data = _case(layers, B, N, T, 21)
+    torch.set_num_threads(8)
+    ref = train_oracle.reference_training_step(sd, _cfg(layers), data)
+    m = gmf_b200.PointDSC(num_layers=layers, num_iterations=10, ratio=0.1, inlier_threshold=0.1, sigma_d=0.1, k=40, nms_radius=0.1)
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith("encoder.image_encoder.") or k.endswith("num_batches_tracked") for k in res.missing_keys)
+    m = m.cuda().train()
+    m.encoder.image_encoder.tokens = lambda t: t                 # tokens in place of images
+    p_tok = data["p_tokens"].cuda().requires_grad_(True)
+    q_tok = data["q_tokens"].cuda().requires_grad_(True)
+    gt = data["gt_labels"].cuda()
+    inp = {"corr_pos": data["corr_pos"].cuda(), "src_keypts": data["src_keypts"].cuda(), "tgt_keypts": data["tgt_keypts"].cuda(), "p_image": p_tok, "q_image": q_tok}
+    hot = [p for n, p in m.named_parameters() if not n.startswith("encoder.image_encoder.")]
+    opt = torch.optim.Adam(hot, lr=1e-4, weight_decay=1e-6)
+
+    def iteration():
+        opt.zero_grad()
+        out = m(inp)
+        assert out["final_trans"].shape == (B, 4, 4) and out["M"].shape == (B, N, N)
+        cl = Cls(balanced=False)(out["final_labels"], gt)["loss"]
+        sl = Sm(balanced=False)(out["M"], gt)
+        (cl + sl).backward()
+        return out, float(cl), float(sl)
+    out, cl, sl = iteration()
+    assert abs(cl - ref["class_loss"]) < 2e-4 and abs(sl - ref["sm_loss"]) < 2e-4
+    assert float((out["final_labels"].detach().cpu().double() - ref["logits"]).abs().max()) < 1e-3
+    worst = ("", 0.0)
+    for k, p_ in m.named_parameters():
+        if k.startswith("encoder.image_encoder."):
+            continue
+        g = ref["grads"][k]
+        if g is None:
+            assert p_.grad is None or float(p_.grad.abs().max()) == 0, k
+            continue
+        rel = float((p_.grad.cpu().double() - g).abs().max() / g.abs().max().clamp_min(1e-3))
+        if rel > worst[1]:
+            worst = (k, rel)
+    rq = float((q_tok.grad.cpu().double() - ref["d_q_tokens"]).abs().max() / ref["d_q_tokens"].abs().max())
+    record("pdsc_module_training_mode_l2", worst_weight_grad=worst[0], worst_weight_grad_rel=worst[1], d_q_tokens_rel=rq, class_loss=cl, sm_loss=sl)
+    assert worst[1] < 1e-2 and rq < 1e-2, (worst, rq)
+    new = m.state_dict()
+    for k in new:
+        if k.endswith("running_mean") and not k.startswith("encoder.image_encoder."):
+            assert float((new[k].cpu().double() - ref["state"][k]).abs().max()) < 1e-3, k
+    first = cl + sl
+    opt.step()
+    for _ in range(4):                                            # a few Adam steps on the same batch: the loss goes down
+        _, cl, sl = iteration()
+        opt.step()
+    assert cl + sl < first, (first, cl + sl)
+    m.eval()                                                      # and the inference path picks up the trained weights / running statistics
+    with torch.no_grad():
+        ev = m({**{k: v[:1] for k, v in inp.items()}, "testing": True})
+    assert ev["final_trans"].shape == (1, 4, 4) and bool(torch.isfinite(ev["final_trans"]).all())
+
+
+@pytest.mark.gpu
 def test_cuda_training_error_paths():
     from gmf_b200 import _lib
     lib = _lib.load()
@@ -196,6 +263,6 @@ def test_cuda_training_error_paths():
     ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
     z = torch.zeros(16, device="cuda")
     assert lib.gmf_pointdsc_train_forward(0, 2, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 2, 100, 100, 0,
-                                          1.0, 1.0, 1, z.data_ptr(), None, None, ws.data_ptr(), ws.numel(), None) == -3   # workspace too small
+                                          1.0, 1.0, 1, z.data_ptr(), None, None, None, ws.data_ptr(), ws.numel(), None) == -3   # workspace too small
     assert b"workspace too small" in lib.gmf_last_error()
     assert lib.gmf_adam_step(None, None, None, None, None, 0, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1.0, 1, None) == -1
