@@ -104,6 +104,15 @@ __global__ void __launch_bounds__(256) col_sum_ld_kernel(const float* __restrict
   }
 }
 
+// out[i] = sum_z part[z * n + i]  (split-K reduction of the weight-gradient products)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int slices, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < slices; ++z) s += part[(size_t)z * n + i];
+  out[i] = s;
+}
+
 // y += x (n elements)
 __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

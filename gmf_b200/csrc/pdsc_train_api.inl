@@ -39,6 +39,8 @@ struct FusAct { float *x0, *c0, *xn, *cn, *stq, *stc, *q, *kv, *P, *a, *x1, *stf
 // ... and of one PointCN + NonLocalBlock
 struct BlkAct { float *z, *st, *a, *qkv, *P, *msg, *z1, *st1, *m1, *z2, *st2, *m2, *out; FusAct f; };
 
+constexpr int kSplitMax = 96;                            // split-K slices of a weight-gradient product (K = all rows of the step)
+
 struct PtWs {
   FusAct f1;
   std::vector<BlkAct> blk;
@@ -47,7 +49,7 @@ struct PtWs {
   double *cnt, *acc, *bnacc;
   float *dg, *du, *dh, *dx1, *da, *dq, *dkv, *dP, *dxn, *dcn, *dx0, *dc0;   // fusion backward scratch
   float *dA, *dB, *d64a, *d64b, *dmsg, *dqkv, *dasc, *dxf, *dimg, *dc1, *dc2;
-  float *imgA, *imgB;
+  float *imgA, *imgB, *part;                              // operand images; split-K partial products
   size_t img_cap;
   int x3;                                                  // error-compensated products (3xTF32)
 };
@@ -85,6 +87,7 @@ size_t pt_carve(PtWs& w, uint8_t* base, int L, int B, int N, int T, int x3) {
   w.x3 = x3 != 0;
   w.img_cap = std::max(std::max(Bn * p128(Lm) * p32(Lm), p128(Rm) * (size_t)1024), (size_t)1024 * p32(Rm)) * (x3 ? 3 : 1);
   w.imgA = b.take<float>(w.img_cap); w.imgB = b.take<float>(w.img_cap);
+  w.part = b.take<float>((size_t)(kSplitMax + 1) * 1024 * 128);
   return b.off + 1024;
 }
 int pt_ws(PtWs& w, void* ws, size_t bytes, int L, int B, int N, int T, int x3) {
@@ -123,7 +126,21 @@ int lin_fwd(PtWs& w, const float* x, int ldx, int rows, int nin, const float* W,
 int lin_bwd(PtWs& w, const float* dy, int ldy, int rows, int nout, const float* x, int ldx, int nin, const float* W, float* dx, const float* residual, float* dW,
             float* db, cudaStream_t st) {
   if (db) { col_sum_ld_kernel<<<dim3(cdiv(nout, 32), cdiv(rows, 256)), 256, 0, st>>>(dy, ldy, rows, nout, db); LAUNCHED(); }
-  if (dW) TRY(pgemm(w, dy, ldy, 0, nout, rows, 1, x, ldx, 0, nin, 1, dW, nin, 0, 1.f, nullptr, nullptr, 1, st));
+  if (dW) {
+    // dW = dy^T x has K = rows (up to B max(N, T)) and at most 8 output tiles: split K over `z` slices (the batched product does the slices, one
+    // more call the remainder), partial products summed by splitk_reduce_kernel - otherwise one CTA streams the whole K range
+    const int z = std::min(kSplitMax, rows / 1024);
+    if (z < 2 || (size_t)nout * nin > (size_t)1024 * 128) {
+      TRY(pgemm(w, dy, ldy, 0, nout, rows, 1, x, ldx, 0, nin, 1, dW, nin, 0, 1.f, nullptr, nullptr, 1, st));
+    } else {
+      const int kc = rows / z / 32 * 32, rem = rows - z * kc, mn = nout * nin;
+      TRY(pgemm(w, dy, ldy, (size_t)kc * ldy, nout, kc, 1, x, ldx, (size_t)kc * ldx, nin, 1, w.part, nin, (size_t)mn, 1.f, nullptr, nullptr, z, st));
+      if (rem > 0)
+        TRY(pgemm(w, dy + (size_t)z * kc * ldy, ldy, 0, nout, rem, 1, x + (size_t)z * kc * ldx, ldx, 0, nin, 1, w.part + (size_t)z * mn, nin, 0, 1.f, nullptr,
+                  nullptr, 1, st));
+      splitk_reduce_kernel<<<cdiv(mn, 256), 256, 0, st>>>(w.part, z + (rem > 0 ? 1 : 0), mn, dW); LAUNCHED();
+    }
+  }
   if (dx) TRY(pgemm(w, dy, ldy, 0, rows, nout, 0, W, nin, 0, nin, 1, dx, nin, 0, 1.f, nullptr, residual, 1, st));
   return 0;
 }
