@@ -22,22 +22,24 @@ __global__ void __launch_bounds__(256) mat_to_img_b_kernel(const float* __restri
   const int per = x3 ? 3 : 1;
   float* chunk0 = img0 + ((size_t)blockIdx.z * tiles * kch * per + ((size_t)tile * kch + kc) * per) * 4096;
   const bool vec = (ld & 3) == 0 && ((uintptr_t)src & 15) == 0;
+  __shared__ float tbuf[32][129];                          // transposed operands: coalesced reads along r, then the row-major write pattern
+  if (trans) {
+    for (int idx = threadIdx.x; idx < 32 * 128; idx += 256) {
+      const int kk = idx >> 7, rr = idx & 127, r = tile * 128 + rr, k = kc * 32 + kk;
+      tbuf[kk][rr] = (r < rows && k < K) ? src[(size_t)k * ld + r] : 0.f;
+    }
+    __syncthreads();
+  }
   for (int idx = threadIdx.x; idx < 1024; idx += 256) {
-    int rr, g;
-    if (trans) { rr = idx & 127; g = idx >> 7; } else { rr = idx >> 3; g = idx & 7; }
+    const int rr = idx >> 3, g = idx & 7;
     const int r = tile * 128 + rr, k0 = kc * 32 + g * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < rows) {
-      if (!trans) {
-        const float* p = src + (size_t)r * ld + k0;
-        if (k0 + 3 < K && vec) v = *reinterpret_cast<const float4*>(p);
-        else { if (k0 < K) v.x = p[0]; if (k0 + 1 < K) v.y = p[1]; if (k0 + 2 < K) v.z = p[2]; if (k0 + 3 < K) v.w = p[3]; }
-      } else {
-        if (k0 < K) v.x = src[(size_t)k0 * ld + r];
-        if (k0 + 1 < K) v.y = src[(size_t)(k0 + 1) * ld + r];
-        if (k0 + 2 < K) v.z = src[(size_t)(k0 + 2) * ld + r];
-        if (k0 + 3 < K) v.w = src[(size_t)(k0 + 3) * ld + r];
-      }
+    if (trans) {
+      v = make_float4(tbuf[g * 4][rr], tbuf[g * 4 + 1][rr], tbuf[g * 4 + 2][rr], tbuf[g * 4 + 3][rr]);
+    } else if (r < rows) {
+      const float* p = src + (size_t)r * ld + k0;
+      if (k0 + 3 < K && vec) v = *reinterpret_cast<const float4*>(p);
+      else { if (k0 < K) v.x = p[0]; if (k0 + 1 < K) v.y = p[1]; if (k0 + 2 < K) v.z = p[2]; if (k0 + 3 < K) v.w = p[3]; }
     }
     const float4 hi = to_tf32(v);
     const uint32_t off = swz_off(rr, g);
