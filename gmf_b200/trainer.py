@@ -107,6 +107,25 @@ class PointDSCTrainer:
         return {"losses": losses, "class_loss": losses[0], "sm_loss": losses[1], "loss": losses[2], "final_labels": logits, "features": feats,
                 "d_p_tokens": d_p, "d_q_tokens": d_q}
 
+    def final_trans(self, out: dict, src_keypts, tgt_keypts, num_iterations: int = 10, ratio: float = 0.1, inlier_threshold: float = 0.10, k: int = 40):
+        """`final_trans` of the training-mode forward (PointDSC.py:246-253: top-`ratio` seeds by confidence without NMS, per-seed spectral matching
+        + weighted Kabsch, best hypothesis by inlier count, no post-refinement) from the `features` / `final_labels` of `forward_backward`, on the
+        seed kernels of the inference engine - what the reference's TransformationLoss (libs/loss.py:12-63; logging only at weight 0) consumes."""
+        from .engine import Engine
+        eng = getattr(self, "_engine", None)
+        cfg = (num_iterations, ratio, inlier_threshold, k)
+        if eng is None or self._engine_cfg != cfg:
+            with torch.cuda.device(self.device):
+                eng = self._engine = Engine(self.num_layers, num_iterations, k, ratio, inlier_threshold, inlier_threshold, self.device)
+            self._engine_cfg = cfg
+        eng.load_state_dict(self.state_dict())                       # sigma / sigma_spat of the current step
+        src, tgt = src_keypts.to(self.device, torch.float32).contiguous(), tgt_keypts.to(self.device, torch.float32).contiguous()
+        with torch.no_grad(), torch.cuda.device(self.device):
+            normed = torch.nn.functional.normalize(out["features"], p=2, dim=-1)
+            seeds = eng.pick_seeds(src, out["final_labels"], use_nms=False)
+            seed_trans = eng.seed_hypotheses(normed, src, tgt, seeds)[0]
+            return eng.score_hypotheses(seed_trans, src, tgt, refine=False)[0]
+
     def step(self, lr: float = 1e-4, weight_decay: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, group=None) -> bool:
         """all-reduce (sum) of the flat gradient over the process group, the reference's finite-gradient guard, then Adam on the mean
         gradient.  Returns False when the step was skipped because of a non-finite gradient (trainer.py:161-168)."""

@@ -63,6 +63,7 @@ def reference_training_step(sd, cfg, data, balanced=False, w_class=1.0, w_sm=1.0
     grads = {k: (v.grad.detach().clone() if v.grad is not None else None) for k, v in m.named_parameters()}
     state = {k: v.detach().clone() for k, v in m.state_dict().items()}
     return {"class_loss": float(cl), "sm_loss": float(sl), "loss": float(loss), "logits": res["final_labels"].detach(), "grads": grads,
+            "final_trans": res["final_trans"].detach(),
             "d_p_tokens": p_tok.grad.detach(), "d_q_tokens": q_tok.grad.detach(), "state": state}
 
 

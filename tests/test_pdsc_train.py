@@ -130,6 +130,9 @@ def _compare(layers, B, N, T, balanced, seed, tol_grad, tol_logit, precision="tf
     assert worst[1] < tol_grad, worst
     assert rp < tol_grad and rq < tol_grad, (rp, rq)
     assert rs < max(1e-3, 10 * tol_loss), rs
+    if layers <= 2:      # the fused trainer's final_trans helper == the reference's training-mode final_trans
+        ft = tr.final_trans(out, data["src_keypts"], data["tgt_keypts"])
+        assert float((ft.cpu().double() - ref["final_trans"]).abs().max()) < 2e-3
     return tr, grads
 
 
@@ -220,6 +223,10 @@ def test_module_in_training_mode_runs_the_reference_trainer_step():
         (cl + sl).backward()
         return out, float(cl), float(sl)
     out, cl, sl = iteration()
+    # final_trans of the training-mode forward (top-ratio seeds without NMS, no refinement; PointDSC.py:246-253) against the reference's
+    dt = float((out["final_trans"].cpu().double() - ref["final_trans"]).abs().max())
+    record("pdsc_module_training_mode_final_trans", max_abs_diff=dt)
+    assert dt < 2e-3, dt
     assert abs(cl - ref["class_loss"]) < 2e-4 and abs(sl - ref["sm_loss"]) < 2e-4
     assert float((out["final_labels"].detach().cpu().double() - ref["logits"]).abs().max()) < 1e-3
     worst = ("", 0.0)
