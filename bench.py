@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-backbone", action="store_true", help="skip the separate timing of the PyTorch image backbone")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg#3 strong-scaling leg (256 KITTI-shaped pairs split over the ranks)")
     ap.add_argument("--cfg3-pairs", type=int, default=256)
+    ap.add_argument("--no-train", action="store_true", help="skip the separate timing of the PointDSC training step (SURVEY 8f N2)")
     return ap.parse_args()
 
 
@@ -212,6 +213,41 @@ def backbone_timing(dev, pairs, h=480, w=640, iters=3):
     ms_bf16 = run(bf16)
     return {"note": "PyTorch ResNet-34 trunk (conv1..layer2), excluded from `value` / `e2e`; 2 x %d images %dx%d per step" % (pairs, h, w),
             "fp32_eager_ms_per_step": ms_fp32, "channels_last_bf16_ms_per_step": ms_bf16}
+
+
+def training_step_timing(dev, layers, tokens, iters=3):
+    """SURVEY 8f N2, reported beside the headline like the backbone: one training step of the path (training-mode forward, losses, analytic
+    backward, finite-gradient guard, Adam; gmf_b200/trainer.py) at the reference's training shape (config_3DMatch.py: batch 16, num_node 1000).
+    Single GPU here; the NCCL gradient all-reduce legs are tools/bench_pdsc_train.py (profiles/r02_pdsc_train_{2,8}gpu.jsonl)."""
+    from gmf_b200 import _lib
+    from gmf_b200.synth import synth_pairs, synth_tokens
+    from gmf_b200.trainer import PointDSCTrainer
+    B, N = 16, 1000
+    tr = PointDSCTrainer(layers, dev.index or 0, precision="tf32x3")
+    tr.load_state_dict(synth_weights(layers))
+    d = synth_pairs(B, N, seed=100, noise=0.01)
+    args = [x.to(dev) for x in (d["corr_pos"], d["src_keypts"], d["tgt_keypts"], synth_tokens(B, tokens, 200), synth_tokens(B, tokens, 300), d["gt_labels"])]
+    lib = _lib.load()
+    for _ in range(2):
+        out = tr.forward_backward(*args)
+        tr.step(lr=1e-4, weight_decay=1e-6)
+    torch.cuda.synchronize()
+    lib.gmf_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = tr.forward_backward(*args)
+        tr.step(lr=1e-4, weight_decay=1e-6)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    res = {"note": "PointDSC training step on the CUDA path (forward + BCE / fused spectral-matching loss + analytic backward + guard + Adam), excluded from `value` / `e2e`",
+           "workload": f"{B} pairs x {N} correspondences, {tokens} image tokens, {layers} layers (the reference's training shape), 3xTF32 tensor-pipe products",
+           "ms_per_step": ms, "pairs_per_s": B * 1000.0 / ms, "gpu_launches_per_step": int(lib.gmf_launch_count(0)) // iters,
+           "loss": float(out["loss"]), "workspace_gb": tr._ws.numel() / 1e9, "parameters": int(tr.params.numel())}
+    del tr
+    torch.cuda.empty_cache()
+    return res
 
 
 def make_inputs(a, rank):
@@ -489,6 +525,13 @@ def main():
     if not a.no_cfg3:
         strong = cfg3_strong_scaling(a, eng, dev, rank, world, timed)
 
+    training = None
+    if rank == 0 and world == 1 and not a.no_train:
+        try:
+            training = training_step_timing(dev, a.layers, a.tokens)
+        except Exception as e:                                   # report, do not fail the bench
+            training = {"error": str(e)[:200]}
+
     # sanity on the last device result: poses must be finite and close to the synthetic ground truth
     tr = out["final_trans"].float().cpu()
     gt = pr["gt_trans"]
@@ -501,7 +544,7 @@ def main():
                 "config": config_dict(a, world),
                 "sanity": {"max_translation_error_vs_gt_mm": te_mm, "workspace_gb": ws_gb},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "strong_scaling": strong,
-                "backbone": backbone, "kernel_profile": prof_table}
+                "backbone": backbone, "training_step": training, "kernel_profile": prof_table}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

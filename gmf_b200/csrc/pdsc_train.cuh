@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256) sm_loss_fused_kernel(const float* __restr
   __shared__ float sgi[64], sgj[64];
   __shared__ double redd[16];
   const int b = blockIdx.y, i0 = blockIdx.x * 64, tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const float sg = sigma[0], is2 = 1.0f / (sg * sg);
+  const float sg = sigma[0], is2 = 1.0f / (sg * sg), dsc = 2.0f * is2 / sg;          // d M / d sigma = dsc (1 - S)
   const double k = cnt[b], kk = k * (k - 1.0);
   float cp, cn;                        // d loss / d M = cp (M - 1) on positive pairs, cn M on the others (before `weight`)
   if (balanced) {
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(256) sm_loss_fused_kernel(const float* __restr
           const float e = pos ? m - 1.0f : m;
           const float dm = (pos ? cp : cn) * e;                        // d loss / d M
           lsum = fmaf(0.5f * dm, e, lsum);                             // balanced: 0.5 c e^2; MSE: (2 / (B N^2)) / 2 * e^2
-          if (pre >= 0.f && pre <= 1.0f) { g = dm * is2; dsig = fmaf(dm, 2.0f * (1.0f - s[r][c]) * is2 / sg, dsig); }
+          if (pre >= 0.f && pre <= 1.0f) { g = dm * is2; dsig = fmaf(dm * dsc, 1.0f - s[r][c], dsig); }
         }
         sG[(ty * 4 + r) * 64 + tx * 4 + c] = g;
       }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of library variants on the same box: usage run_ab_libs.sh <variant> ... (build/libgmf_<variant>.so; "base" = the in-tree library); 2 rounds
 mkdir -p gpurun_out
-QUICK="--no-cpu-baseline --no-e2e --no-backbone --no-cfg3"
+QUICK="--no-cpu-baseline --no-e2e --no-backbone --no-cfg3 --no-train"
 cp gmf_b200/libgmf_b200.so /tmp/base.so
 for round in 1 2; do
 for v in "$@"; do

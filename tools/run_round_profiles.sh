@@ -7,7 +7,7 @@ timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; 
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "[ref exit $?]"
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "[bench exit $?]"
 tail -c 400 gpurun_out/bench_full.json; echo
-Q="--no-cpu-baseline --no-e2e --no-roofline --no-backbone --no-cfg3"
+Q="--no-cpu-baseline --no-e2e --no-roofline --no-backbone --no-cfg3 --no-train"
 SMALL="python bench.py --pairs 16 --steps 1 --warmup 1 --min-warmup 1 $Q"
 timeout 600 $SMALL > gpurun_out/plain_small.log 2>&1 && \
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu.log 2>&1; echo "[ncu list exit $?]"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # time the SC / fusion attention kernels with development variants of the library (build/libgmf_*.so)
 mkdir -p gpurun_out
-QUICK="--no-cpu-baseline --no-e2e --no-backbone --no-cfg3"
+QUICK="--no-cpu-baseline --no-e2e --no-backbone --no-cfg3 --no-train"
 cp gmf_b200/libgmf_b200.so /tmp/orig.so
 for v in "$@"; do
   cp build/libgmf_$v.so gmf_b200/libgmf_b200.so
