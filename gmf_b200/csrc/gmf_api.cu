@@ -1092,8 +1092,17 @@ static int forward_host_impl(gmf_ctx* ctx, const float* corr_pos, const float* s
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   // chunk boundaries.  The asynchronous entry point is meant for back-to-back submission: the whole upload of call k+1 already overlaps
   // the kernels of call k, so its batch is not split (every chunk pays the fixed cost of the small seed / pose kernels again).
-  std::vector<int> cuts = sync ? plan_host_chunks(B, N, std::min(48, ctx->chunk_pairs), sms) : std::vector<int>{0};
-  if (!sync) {
+  // ... unless nothing is in flight (first call of a burst: the forward that used the other input set has completed): then there is no
+  // compute to hide the upload behind and the call is cut like the synchronous one, which exposes ~1.5 ms of upload instead of ~13 ms.
+  bool chunked = sync || realloc_stage;                        // (a re-allocation synchronised the device: idle as well)
+  if (!chunked) {
+    const cudaError_t q = cudaEventQuery(ctx->in_done[ctx->in_set ^ 1]);
+    if (q == cudaSuccess) chunked = true;
+    else if (q == cudaErrorNotReady) (void)cudaGetLastError();
+    else return fail_cuda(q, "cudaEventQuery(in_done)");
+  }
+  std::vector<int> cuts = chunked ? plan_host_chunks(B, N, std::min(48, ctx->chunk_pairs), sms) : std::vector<int>{0};
+  if (!chunked) {
     for (int b0 = ctx->chunk_pairs; b0 < B; b0 += ctx->chunk_pairs) cuts.push_back(b0);
     cuts.push_back(B);
   }
