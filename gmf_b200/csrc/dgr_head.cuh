@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) desc_operand_kernel(const float* __restri
   }
 }
 
-enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4, DE_COMPAT = 5, DE_ARGMIN = 6, DE_STORE = 7 };
+enum { DE_RES = 0, DE_GEGLU = 1, DE_QIMG = 2, DE_KVIMG = 3, DE_DIST = 4, DE_COMPAT = 5, DE_ARGMIN = 6, DE_STORE = 7, DE_STORE_X3 = 8 };
 
 struct ImgGemmArgs {
   const float* a_img;      // [tiles][K/32][128 x 32] tf32 chunks (rows_to_img_kernel / DE_GEGLU epilogue)
@@ -175,11 +175,15 @@ struct IgCfg {
   // many small output blocks (seed kNN distances, feature compat, matcher): two stages only, so that two CTAs share an SM and one's
   // epilogue overlaps the other's loads and MMAs; the GEMMs of the DGR head (few CTAs) keep a 4-deep ring
   static constexpr bool SMALL = (EPI == DE_DIST || EPI == DE_COMPAT || EPI == DE_ARGMIN);
-  static constexpr int NSTG = SMALL ? 2 : 4;
+  // DE_STORE_X3 (training path, error-compensated "3xTF32" products): every K chunk of an operand image is a (hi, lo) pair of tf32 chunks,
+  // hi = tf32(v), lo = tf32(v - hi); a stage holds both pairs and the issuer accumulates hi hi + hi lo + lo hi from ONE load of the stage
+  static constexpr bool X3 = (EPI == DE_STORE_X3);
+  static constexpr bool STORE = (EPI == DE_STORE || EPI == DE_STORE_X3);
+  static constexpr int NSTG = SMALL ? 2 : (X3 ? 3 : 4);
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = NB * 128;
-  static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = (EPI == DE_RES || EPI == DE_DIST || EPI == DE_COMPAT || EPI == DE_STORE) ? 4 * 4096 : 0;
+  static constexpr int STAGE = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
+  static constexpr int STG_BYTES = (EPI == DE_RES || EPI == DE_DIST || EPI == DE_COMPAT || STORE) ? 4 * 4096 : 0;
   static constexpr int SMEM = 1024 + NSTG * STAGE + 256 + STG_BYTES;
 };
 
@@ -214,16 +218,17 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
 
   if (warp == 0) {
     const uint32_t leader = elect_one() ? 1u : 0u;
-    const float* asrc = a.a_img + blockIdx.z * a.a_pair_stride + (size_t)tile * nkc * 4096;
-    const float* wsrc = a.w_packed + blockIdx.z * a.w_pair_stride + (size_t)cb * nkc * (NB * 32);
+    constexpr int PER = Cfg::X3 ? 2 : 1;                 // tf32 chunks per K chunk of an operand image
+    const float* asrc = a.a_img + blockIdx.z * a.a_pair_stride + (size_t)tile * nkc * (4096 * PER);
+    const float* wsrc = a.w_packed + blockIdx.z * a.w_pair_stride + (size_t)cb * nkc * (NB * 32 * PER);
 #pragma unroll 1
     for (int kc = 0; kc < nkc; ++kc) {
       const int st = kc % Cfg::NSTG;
       if (kc >= Cfg::NSTG) mbar_wait(&empty[st], ((kc / Cfg::NSTG) - 1) & 1);
       uint8_t* dst = smem + st * Cfg::STAGE;
       mbar_expect_tx_p(&full[st], Cfg::STAGE, leader);
-      bulk_g2s_p(dst, asrc + (size_t)kc * 4096, Cfg::A_BYTES, &full[st], leader);
-      bulk_g2s_p(dst + Cfg::A_BYTES, wsrc + (size_t)kc * (NB * 32), Cfg::B_BYTES, &full[st], leader);
+      bulk_g2s_p(dst, asrc + (size_t)kc * (4096 * PER), Cfg::A_BYTES * PER, &full[st], leader);
+      bulk_g2s_p(dst + Cfg::A_BYTES * PER, wsrc + (size_t)kc * (NB * 32 * PER), Cfg::B_BYTES * PER, &full[st], leader);
     }
   } else if (warp == 1) {
     const uint32_t leader = elect_one() ? 1u : 0u;
@@ -236,9 +241,16 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
       tc_fence_after();
       if (leader) {
         const uint64_t ad = umma_desc_sw128(smem_u32(smem + st * Cfg::STAGE));
-        const uint64_t bd = umma_desc_sw128(smem_u32(smem + st * Cfg::STAGE + Cfg::A_BYTES));
+        const uint64_t bd = umma_desc_sw128(smem_u32(smem + st * Cfg::STAGE + Cfg::A_BYTES * (Cfg::X3 ? 2 : 1)));
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) tc_mma_tf32(tm, umma_desc_adv(ad, ks * 32), umma_desc_adv(bd, ks * 32), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+        if (Cfg::X3) {                                    // + hi lo + lo hi (stage = A_hi | A_lo | B_hi | B_lo)
+          const uint64_t al = umma_desc_adv(ad, Cfg::A_BYTES), bl = umma_desc_adv(bd, Cfg::B_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc_mma_tf32(tm, umma_desc_adv(ad, ks * 32), umma_desc_adv(bl, ks * 32), idesc, 1u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc_mma_tf32(tm, umma_desc_adv(al, ks * 32), umma_desc_adv(bd, ks * 32), idesc, 1u);
+        }
         tc_commit(&empty[st]);
         if (kc == nkc - 1) tc_commit(acc_full);
       }
@@ -290,7 +302,7 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
                                  (__uint_as_float(v[4 * j + 3]) + b1.w) * gelu_erf(__uint_as_float(gt[4 * j + 3]) + b2.w));
           *reinterpret_cast<float4*>(dst + swz_off(r, j)) = valid ? to_tf32(o) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      } else if (EPI == DE_DIST || EPI == DE_COMPAT || EPI == DE_STORE) {
+      } else if (EPI == DE_DIST || EPI == DE_COMPAT || Cfg::STORE) {
         tmem_ld_wait();
         // DE_DIST: squared feature distance of unit vectors, 2 - 2 <a, b> (models/common.py:64-66), rows = seeds, columns = points
         // DE_COMPAT: feature compatibility clamp(1 - (1 - <a, b>) / sigma^2, 0, 1) with a zero diagonal (models/PointDSC.py:231-234)
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o;
-          if (EPI == DE_STORE) {
+          if (Cfg::STORE) {
             o = make_float4(__uint_as_float(v[4 * j]) * a.scale, __uint_as_float(v[4 * j + 1]) * a.scale, __uint_as_float(v[4 * j + 2]) * a.scale,
                             __uint_as_float(v[4 * j + 3]) * a.scale);
           } else if (EPI == DE_DIST) {
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(192, IgCfg<NB, EPI>::SMALL ? 2 : 1) img_gemm_k
             float4 o = *reinterpret_cast<const float4*>(stg + rw * 32 + ((sj ^ (rw & 7)) << 2));
             float* dst = obase + (size_t)rw * a.ld + sj * 4;
             const int cc = col0 + sj * 4;
-            if (EPI == DE_STORE) {
+            if (Cfg::STORE) {
               float e[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t)

@@ -11,15 +11,15 @@
 
 namespace gmf {
 
-// Batched operand image: item z of `src` (element stride `stride`) -> img + z * tiles * kchg * 4096.  Layout as mat_to_img_kernel.
-// x3 (error-compensated products, "3xTF32"): every 32-wide K chunk becomes three chunks - (hi, hi, lo) for the row operand (role 0) and
-// (hi, lo, hi) for the column operand (role 1), hi = tf32(v), lo = tf32(v - hi) - so that the unchanged GEMM kernel accumulates
-// hi hi + hi lo + lo hi in fp32: products at ~2^-22 relative error instead of 2^-11, for three times the tensor work.
+// Batched operand image: item z of `src` (element stride `stride`) -> img + z * tiles * kch * per * 4096.  Layout as mat_to_img_kernel.
+// x3 (error-compensated products, "3xTF32"): every 32-wide K chunk becomes a (hi, lo) pair of chunks, hi = tf32(v), lo = tf32(v - hi);
+// img_gemm_kernel<128, DE_STORE_X3> loads the pair of both operands once per K chunk and accumulates hi hi + hi lo + lo hi in fp32:
+// products at ~2^-22 relative error instead of 2^-11, for three times the tensor work and twice the operand traffic.
 __global__ void __launch_bounds__(256) mat_to_img_b_kernel(const float* __restrict__ src0, size_t stride, int ld, int rows, int K, int trans, int kch,
-                                                           int tiles, int x3, int role, float* __restrict__ img0) {
+                                                           int tiles, int x3, float* __restrict__ img0) {
   const int tile = blockIdx.x, kc = blockIdx.y;
   const float* src = src0 + (size_t)blockIdx.z * stride;
-  const int per = x3 ? 3 : 1;
+  const int per = x3 ? 2 : 1;
   float* chunk0 = img0 + ((size_t)blockIdx.z * tiles * kch * per + ((size_t)tile * kch + kc) * per) * 4096;
   const bool vec = (ld & 3) == 0 && ((uintptr_t)src & 15) == 0;
   __shared__ float tbuf[32][129];                          // transposed operands: coalesced reads along r, then the row-major write pattern
@@ -45,9 +45,7 @@ __global__ void __launch_bounds__(256) mat_to_img_b_kernel(const float* __restri
     const uint32_t off = swz_off(rr, g);
     *reinterpret_cast<float4*>((uint8_t*)chunk0 + off) = hi;
     if (x3) {
-      const float4 lo = to_tf32(make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
-      *reinterpret_cast<float4*>((uint8_t*)(chunk0 + 4096) + off) = role ? lo : hi;
-      *reinterpret_cast<float4*>((uint8_t*)(chunk0 + 8192) + off) = role ? hi : lo;
+      *reinterpret_cast<float4*>((uint8_t*)(chunk0 + 4096) + off) = to_tf32(make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
     }
   }
 }

@@ -85,7 +85,7 @@ size_t pt_carve(PtWs& w, uint8_t* base, int L, int B, int N, int T, int x3) {
   auto p128 = [](size_t v) { return (v + 127) / 128 * 128; };
   auto p32 = [](size_t v) { return (v + 31) / 32 * 32; };
   w.x3 = x3 != 0;
-  w.img_cap = std::max(std::max(Bn * p128(Lm) * p32(Lm), p128(Rm) * (size_t)1024), (size_t)1024 * p32(Rm)) * (x3 ? 3 : 1);
+  w.img_cap = std::max(std::max(Bn * p128(Lm) * p32(Lm), p128(Rm) * (size_t)1024), (size_t)1024 * p32(Rm)) * (x3 ? 2 : 1);
   w.imgA = b.take<float>(w.img_cap); w.imgB = b.take<float>(w.img_cap);
   w.part = b.take<float>((size_t)(kSplitMax + 1) * 1024 * 128);
   return b.off + 1024;
@@ -102,18 +102,18 @@ int pt_ws(PtWs& w, void* ws, size_t bytes, int L, int B, int N, int T, int x3) {
 // (t = 0: element (r, k) = p[r * ld + k]) or the transpose of a row-major matrix (t = 1: p[k * ld + r]); z strides in elements.
 int pgemm(PtWs& w, const float* X, int ldx, size_t sx, int m, int K, int tx, const float* Y, int ldy, size_t sy, int n, int ty, float* out, int ldo, size_t so,
           float scale, const float* bias, const float* residual, int batch, cudaStream_t st) {
-  const int tm = cdiv(m, 128), tn = cdiv(n, 128), kch = cdiv(K, 32), kchg = kch * (w.x3 ? 3 : 1);
-  const size_t ia = (size_t)tm * kchg * 4096, ib = (size_t)tn * kchg * 4096;
+  const int tm = cdiv(m, 128), tn = cdiv(n, 128), kch = cdiv(K, 32), per = w.x3 ? 2 : 1;
+  const size_t ia = (size_t)tm * kch * per * 4096, ib = (size_t)tn * kch * per * 4096;
   if (ia * batch > w.img_cap || ib * batch > w.img_cap) return fail(GMF_ERR_STATE, "pointdsc training: operand image exceeds the workspace");
   if (residual && batch != 1) return fail(GMF_ERR_INVALID, "pointdsc training: residual with a batched product");
-  mat_to_img_b_kernel<<<dim3(tm, kch, batch), 256, 0, st>>>(X, sx, ldx, m, K, tx, kch, tm, w.x3, 0, w.imgA);
+  mat_to_img_b_kernel<<<dim3(tm, kch, batch), 256, 0, st>>>(X, sx, ldx, m, K, tx, kch, tm, w.x3, w.imgA);
   LAUNCHED();
-  mat_to_img_b_kernel<<<dim3(tn, kch, batch), 256, 0, st>>>(Y, sy, ldy, n, K, ty, kch, tn, w.x3, 1, w.imgB);
+  mat_to_img_b_kernel<<<dim3(tn, kch, batch), 256, 0, st>>>(Y, sy, ldy, n, K, ty, kch, tn, w.x3, w.imgB);
   LAUNCHED();
   ImgGemmArgs a{};
-  a.a_img = w.imgA; a.w_packed = w.imgB; a.K = kchg * 32; a.L = m; a.tiles = tm; a.out = out; a.ld = ldo; a.ncols = n; a.scale = scale; a.bias = bias;
+  a.a_img = w.imgA; a.w_packed = w.imgB; a.K = kch * 32; a.L = m; a.tiles = tm; a.out = out; a.ld = ldo; a.ncols = n; a.scale = scale; a.bias = bias;
   a.residual = residual; a.a_pair_stride = ia; a.w_pair_stride = ib; a.out_pair_stride = so;
-  cudaError_t e = launch_img_gemm<128, DE_STORE>(a, tn, st, batch);
+  cudaError_t e = w.x3 ? launch_img_gemm<128, DE_STORE_X3>(a, tn, st, batch) : launch_img_gemm<128, DE_STORE>(a, tn, st, batch);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail_cuda(e, "pointdsc training GEMM launch");
   return 0;

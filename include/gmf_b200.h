@@ -201,7 +201,7 @@ int gmf_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t
  * inputs; grads is overwritten (entries of running statistics and sigma_spat stay 0); d_p_tokens / d_q_tokens [B,T,128] (the gradient that
  * flows on into the PyTorch image backbone) may be NULL.  Matrix products run on the tensor pipe: tf32x3 = 0 plain TF32 (gradients within a few
  * per cent of fp32 autograd through 12 layers), tf32x3 = 1 error-compensated (hi hi + hi lo + lo hi, fp32-level products, three times the tensor
- * work and operand-image workspace); everything else is fp32.  The same tf32x3 must be passed to all three calls of a step.
+ * work and twice the operand-image workspace); everything else is fp32.  The same tf32x3 must be passed to all three calls of a step.
  * Autograd entry (the reference's own trainer computes its losses in Python on `final_labels` and `M`): train_forward with gt_labels = losses =
  * NULL skips the fused loss head and can write the materialised M [B,N,N] (`M`, may be NULL otherwise too); train_backward then takes the
  * caller's d_logits [B,N] / d_M [B,N,N] / d_features [B,N,128] (any of them NULL = zero; all three NULL = use the fused loss head). */
