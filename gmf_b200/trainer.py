@@ -176,6 +176,8 @@ class _TrainForward(torch.autograd.Function):
                 if getattr(p, "_gmf_running_stat", False):
                     p.copy_(flat[o:o + n].reshape(p.shape))
                 o += n
+        st.generation += 1                                    # the saved activations live in st.ws: a later forward overwrites them
+        ctx.generation = st.generation
         ctx.st, ctx.flat, ctx.inputs, ctx.shapes = st, flat, (cp, pt, qt), [p.shape for p in params]
         ctx.dims = (B, N, T)
         return logits, M, feats
@@ -183,6 +185,9 @@ class _TrainForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_logits, d_M, d_feats):
         st, (cp, pt, qt), (B, N, T) = ctx.st, ctx.inputs, ctx.dims
+        if ctx.generation != st.generation:
+            raise _lib.GmfError("gmf_b200 training-mode backward: the activations of this forward were overwritten by a later training-mode forward of "
+                                "the same module (one workspace per module) - call backward() before the next forward")
         dev = cp.device
         grads = torch.empty_like(ctx.flat)
         d_p, d_q = torch.empty_like(pt), torch.empty_like(qt)
@@ -209,7 +214,7 @@ class TrainState:
         if precision not in ("tf32", "tf32x3"):
             raise ValueError("precision must be 'tf32' or 'tf32x3'")
         self.lib = _lib.load()
-        self.num_layers, self.x3, self.ws = int(num_layers), 1 if precision == "tf32x3" else 0, None
+        self.num_layers, self.x3, self.ws, self.generation = int(num_layers), 1 if precision == "tf32x3" else 0, None, 0
 
 
 def train_forward(st: TrainState, corr_pos, src, tgt, p_tok, q_tok, named_tensors: Dict[str, torch.Tensor]):

@@ -253,6 +253,10 @@ def test_module_in_training_mode_runs_the_reference_trainer_step():
         _, cl, sl = iteration()
         opt.step()
     assert cl + sl < first, (first, cl + sl)
+    stale = m(inp)["final_labels"].sum()                          # two forwards, then backward of the first: refused, not silently wrong
+    m(inp)
+    with pytest.raises(Exception, match="overwritten"):
+        stale.backward()
     m.eval()                                                      # and the inference path picks up the trained weights / running statistics
     with torch.no_grad():
         ev = m({**{k: v[:1] for k, v in inp.items()}, "testing": True})
