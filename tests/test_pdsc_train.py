@@ -54,6 +54,21 @@ def test_loss_head_closed_form_matches_reference_losses(balanced):
     assert abs(float(sigma.grad) - float(dsigma)) < 1e-5 * abs(float(dsigma))
 
 
+def test_training_abi_host_side_sizes():
+    """pure host logic of the training C ABI (no device needed): flat parameter count == the state_dict table, workspace sizing"""
+    import __graft_entry__ as g
+    g.build()
+    from gmf_b200 import _lib
+    lib = _lib.load()
+    for layers in (1, 2, 12):
+        assert lib.gmf_pointdsc_param_count(layers) == sum(int(torch.Size(s).numel()) for s in hot_path_spec(layers).values())
+    assert lib.gmf_pointdsc_param_count(0) == 0
+    small, big = lib.gmf_pointdsc_train_workspace_bytes(2, 2, 256, 300, 1), lib.gmf_pointdsc_train_workspace_bytes(12, 16, 1000, 4800, 1)
+    assert 0 < small < big < 40 * 2 ** 30                        # the reference's training shape fits a fraction of 180 GB
+    assert lib.gmf_pointdsc_train_workspace_bytes(12, 16, 1000, 4800, 0) < big
+    assert lib.gmf_pointdsc_train_workspace_bytes(2, 0, 256, 300, 1) == 0 and lib.gmf_pointdsc_train_workspace_bytes(2, 2, 256, 0, 1) == 0
+
+
 def test_trainable_mask_freezes_buffers():
     from gmf_b200.trainer import trainable_mask
     spec = hot_path_spec(2)
