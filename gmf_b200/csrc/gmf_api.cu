@@ -249,7 +249,6 @@ struct gmf_ctx {
   int chunk_pairs = 64;
   int match_impl = 0;       // 0 = FP32 register-blocked matcher; 1 = tensor pipe (error-compensated tf32, argmin in the GEMM epilogue): correct but
                             // slower at K = 96 (6.3 vs 3.4 ms for 64 pairs x 5000^2): one 128 x 128 block per CTA is all fixed latency
-  int sc_impl = 0;          // development switch of the SC attention kernel variants (GMF_SC_IMPL); 0 = shipped configuration
   // staging for the host-buffer entry point
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
@@ -779,7 +778,6 @@ int gmf_create(gmf_ctx** out, int device, const gmf_config* cfg) {
   c->device = device;
   c->cfg = *cfg;
   if (const char* e = getenv("GMF_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, atoi(e));
-  if (const char* e = getenv("GMF_SC_IMPL")) c->sc_impl = atoi(e);
   if (const char* e = getenv("GMF_MATCH_IMPL")) c->match_impl = atoi(e);
   *out = c;
   return 0;

@@ -504,6 +504,28 @@ def test_kitti_shape_chunked_batch_cfg3():
         assert torch.equal(one["confidence"], out["confidence"][b:b + 1])
 
 
+def test_single_stream_schedule_equals_the_two_stream_schedule():
+    """GMF_NO_SIDE=1 (the measurement switch DESIGN.md section 6.1 names: SC attention and fusion attention of a layer on ONE stream) must give
+    bit-identical results to the shipped two-stream schedule - the fork / join only reorders independent kernels."""
+    from gmf_b200.synth import synth_pairs, synth_state_dict, synth_tokens
+    from gmf_b200.weights import hot_path_spec
+    cfg = dict(O.DEFAULT_CFG)
+    cfg.update(num_layers=3)
+    sd = synth_state_dict(hot_path_spec(3), seed=5, plain_init=True)
+    pr = synth_pairs(3, 1500, seed=41, inlier_ratio=0.3, noise=0.002)
+    p_tok, q_tok = synth_tokens(3, 300, 7), synth_tokens(3, 300, 8)
+    dev = [t.cuda() for t in (pr["corr_pos"], pr["src_keypts"], pr["tgt_keypts"], p_tok, q_tok)]
+    two = make_engine(cfg, sd).forward(*dev, testing=True)
+    os.environ["GMF_NO_SIDE"] = "1"
+    try:
+        one = make_engine(cfg, sd).forward(*dev, testing=True)          # the switch is read by an engine's first forward
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["GMF_NO_SIDE"]
+    for key in ("final_trans", "final_labels", "confidence", "seeds"):
+        assert torch.equal(one[key], two[key]), key
+
+
 def test_lomatch_stress_n10000_cfg4():
     """cfg#4: 10000 correspondences with 5 % inliers — the N x N matrices (400 MB each in the reference) are never materialised;
     workspace stays linear in N and the pose is still recovered."""
