@@ -28,6 +28,15 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTS)
 
 
+def test_integration_doc_accounts_for_every_export():
+    """INTEGRATION.md section 3 maps every declared entry point to the reference symbol it replaces (or says it has none)."""
+    hdr = open(os.path.join(ROOT, "include", "gmf_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name in set(re.findall(r"\b(gmf_[a-z0-9_]+)\s*\(", hdr)):
+        short = name.replace("gmf_dgr_head", "")          # the table abbreviates `gmf_dgr_head_create / _weight_spec / ...`
+        assert name in doc or (name.startswith("gmf_dgr_head_") and short in doc), name
+
+
 def test_weight_table_matches_python_spec(lib):
     from gmf_b200.weights import hot_path_spec
     for layers in (1, 2, 12):
