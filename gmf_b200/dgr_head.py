@@ -187,12 +187,8 @@ class DgrHeadTrainer:
 
     def step(self, lr: float = 0.1, momentum: float = 0.8, weight_decay: float = 1e-4, group=None) -> None:
         """all-reduce (sum) of the flat gradient over the process group, then SGD with the mean gradient"""
-        import torch.distributed as dist
-        world = 1
-        if dist.is_available() and dist.is_initialized():
-            world = dist.get_world_size(group)
-            if world > 1:
-                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
+        from .shard import exchange_gradients
+        world, _ = exchange_gradients(self.grads, group)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(self.lib.gmf_sgd_step(self.params.data_ptr(), self.grads.data_ptr(), self.momentum_buf.data_ptr(), self.params.numel(), lr, momentum,
                                          weight_decay, 1.0 / world, 1 if self.steps == 0 else 0, st))

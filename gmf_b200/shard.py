@@ -1,5 +1,6 @@
 """Pair sharding across ranks: fragment pairs are independent, so each rank owns a contiguous slice of the
-batch and the only cross-rank step is the final host gather of [B,4,4] poses (+ labels).  No collective on the data path."""
+batch and the only cross-rank step is the final host gather of [B,4,4] poses (+ labels).  No collective on the data path.
+The training steps (trainer.py, dgr_head.py) are data-parallel replicas with ONE collective: `exchange_gradients`."""
 from __future__ import annotations
 
 from typing import List, Tuple
@@ -30,3 +31,17 @@ def gather_poses(local_trans: torch.Tensor, num_pairs: int, rank: int, world: in
     outs: List[torch.Tensor] = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf, group=group)
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)]).cpu()
+
+
+def exchange_gradients(flat_grads: torch.Tensor, group=None, check_finite: bool = False) -> Tuple[int, bool]:
+    """The one collective of a data-parallel training step: all-reduce (sum) of the flat gradient over the process group (NCCL on the GPU
+    boxes, gloo in the CPU tests).  Returns (world, ok): the optimiser kernels scale by 1 / world (mean gradient); with `check_finite`, ok is the
+    reference's guard (libs/trainer.py:161-166) evaluated on the REDUCED gradient, so every rank takes the same skip decision."""
+    import torch.distributed as dist
+    world = 1
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    ok = bool(torch.isfinite(flat_grads).all()) if check_finite else True
+    return world, ok

@@ -129,13 +129,9 @@ class PointDSCTrainer:
     def step(self, lr: float = 1e-4, weight_decay: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, group=None) -> bool:
         """all-reduce (sum) of the flat gradient over the process group, the reference's finite-gradient guard, then Adam on the mean
         gradient.  Returns False when the step was skipped because of a non-finite gradient (trainer.py:161-168)."""
-        import torch.distributed as dist
-        world = 1
-        if dist.is_available() and dist.is_initialized():
-            world = dist.get_world_size(group)
-            if world > 1:
-                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
-        if not bool(torch.isfinite(self.grads).all()):
+        from .shard import exchange_gradients
+        world, ok = exchange_gradients(self.grads, group, check_finite=True)
+        if not ok:
             return False
         self.steps += 1
         _lib.check(self.lib.gmf_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),

@@ -145,6 +145,38 @@ def test_host_gather_world2_gloo():
     assert res[0] == res[1] == [float(i) for i in range(7)]
 
 
+def _gloo_grad_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from gmf_b200.shard import exchange_gradients
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.full((1000,), float(rank + 1))
+    w, ok = exchange_gradients(g, check_finite=True)
+    bad = torch.ones(8)
+    if rank == 1:
+        bad[3] = float("nan")                              # a non-finite gradient on ONE rank ...
+    _, ok_bad = exchange_gradients(bad, check_finite=True)
+    q.put((rank, w, ok, g.unique().tolist(), ok_bad))      # ... must make EVERY rank skip the step
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_world2_gloo():
+    """The collective of the data-parallel training steps (trainer.py / dgr_head.py `step`): sum over ranks, world size for the mean,
+    and a finite guard that all ranks agree on."""
+    import torch.multiprocessing as mp
+    from gmf_b200.shard import exchange_gradients
+    g = torch.arange(5.0)
+    assert exchange_gradients(g, check_finite=True) == (1, True) and torch.equal(g, torch.arange(5.0))       # no process group: untouched
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in range(2)]
+    [p.join(timeout=60) for p in ps]
+    for rank, w, ok, vals, ok_bad in res:
+        assert w == 2 and ok and vals == [3.0] and not ok_bad
+
+
 def test_host_chunk_plan_properties(lib):
     """plan_host_chunks (host entry point): chunks cover the batch exactly, respect the cap, start small and never shrink into a short tail."""
     buf = (C.c_int * 256)()
